@@ -1,0 +1,45 @@
+"""Golden-case definitions shared by oracle/make_golden.py (runs the REAL reference, build container
+only) and tests/ (replays the same cases through the oracle port and the CUDA path).
+TEST INFRASTRUCTURE ONLY."""
+import torch
+
+# name -> spec.  All use the reference's default MLP architectures (what Model(config) builds when
+# encoders/decoders are None) with weights from oracle.port.nets.synth_state_dict(seed).
+_DIMS3 = {"m0": (3, 8, 8), "m1": (1, 6, 6), "m2": (10,)}
+_DIST3 = {"m0": "laplace", "m1": "normal", "m2": "normal"}
+_PAR3 = {"m0": {"scale": 0.75}, "m1": {"scale": 0.5}, "m2": {}}
+
+CASES = {
+    "mmvaeplus_dreg": dict(model="mmvaeplus", dims=_DIMS3, B=6, cfg=dict(K=4, latent_dim=5, modalities_specific_dim=3, beta=2.5, loss="dreg_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "mmvaeplus_iwae": dict(model="mmvaeplus", dims=_DIMS3, B=6, cfg=dict(K=3, latent_dim=5, modalities_specific_dim=3, beta=1.0, loss="iwae_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3, learn_shared_prior=True)),
+    "mmvaeplus_normal": dict(model="mmvaeplus", dims=_DIMS3, B=5, cfg=dict(K=2, latent_dim=4, modalities_specific_dim=4, beta=1.5, loss="dreg_looser", prior_and_posterior_dist="normal", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mmvaeplus_softplus": dict(model="mmvaeplus", dims=_DIMS3, B=5, cfg=dict(K=2, latent_dim=4, modalities_specific_dim=4, beta=1.0, loss="iwae_looser", prior_and_posterior_dist="normal_with_softplus", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mmvaeplus_masked": dict(model="mmvaeplus", dims=_DIMS3, B=6, masks=True, cfg=dict(K=4, latent_dim=5, modalities_specific_dim=3, beta=2.5, loss="dreg_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mmvae_dreg": dict(model="mmvae", dims=_DIMS3, B=6, cfg=dict(K=4, latent_dim=5, loss="dreg_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "mmvae_iwae": dict(model="mmvae", dims=_DIMS3, B=6, cfg=dict(K=3, latent_dim=5, loss="iwae_looser", prior_and_posterior_dist="normal", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mmvae_masked": dict(model="mmvae", dims=_DIMS3, B=6, masks=True, cfg=dict(K=3, latent_dim=5, loss="iwae_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mvtcae": dict(model="mvtcae", dims=_DIMS3, B=6, cfg=dict(latent_dim=5, alpha=0.1, beta=2.5, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "mvtcae_masked": dict(model="mvtcae", dims=_DIMS3, B=6, masks=True, cfg=dict(latent_dim=5, alpha=0.3, beta=1.0, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mvae": dict(model="mvae", dims=_DIMS3, B=6, fwd=dict(epoch=12, batch_ratio=0.5), cfg=dict(latent_dim=5, k=0, beta=2.0, warmup=10, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "mvae_warmup_k1": dict(model="mvae", dims=_DIMS3, B=6, fwd=dict(epoch=3, batch_ratio=0.25), np_seed=7, cfg=dict(latent_dim=5, k=1, beta=1.0, warmup=10, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mvae_masked": dict(model="mvae", dims=_DIMS3, B=6, masks=True, fwd=dict(epoch=12, batch_ratio=0.5), cfg=dict(latent_dim=5, k=0, beta=1.0, warmup=10, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mopoe": dict(model="mopoe", dims=_DIMS3, B=9, cfg=dict(latent_dim=5, beta=2.5, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "mopoe_5mod": dict(model="mopoe", dims={f"m{i}": (2, 4, 4) for i in range(5)}, B=40, cfg=dict(latent_dim=6, beta=2.5, decoders_dist={f"m{i}": "laplace" for i in range(5)}, decoder_dist_params={f"m{i}": {"scale": 0.75} for i in range(5)})),
+    "mopoe_masked": dict(model="mopoe", dims=_DIMS3, B=9, masks=True, cfg=dict(latent_dim=5, beta=1.0, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+}
+
+
+def make_data(spec):
+    """Synthetic inputs: U[0,1) from per-modality generators."""
+    data = {}
+    for i, (m, d) in enumerate(spec["dims"].items()):
+        data[m] = torch.rand(spec["B"], *d, generator=torch.Generator().manual_seed(1000 + i))
+    masks = None
+    if spec.get("masks"):
+        B = spec["B"]
+        mods = list(spec["dims"])
+        masks = {m: torch.ones(B, dtype=torch.bool) for m in mods}
+        masks[mods[1]][: B // 2] = False  # mod1 missing for the first half (like the reference's test fixture)
+        masks[mods[2]][B - 1] = False
+        masks[mods[0]][B // 2] = False
+    return data, masks

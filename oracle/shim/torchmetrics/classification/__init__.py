@@ -1,0 +1,3 @@
+class MulticlassAccuracy:
+    def __init__(self, *a, **k):
+        raise NotImplementedError

@@ -1,0 +1,3 @@
+class StructuralSimilarityIndexMeasure:
+    def __init__(self, *a, **k):
+        raise NotImplementedError
