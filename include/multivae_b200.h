@@ -1,0 +1,119 @@
+/*
+ * multivae_b200 C-ABI — the drop-in boundary of the B200-native multimodal-VAE training step.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream handle
+ * (cudaStream_t passed as void*), allocates nothing (all workspaces are caller-provided) and
+ * returns an int status: 0 = ok, !=0 = error (message via mv_last_error(), thread-local).
+ * No exception crosses this boundary.  The reference (MultiVae, pure Python/PyTorch) has no FFI of
+ * its own; each function cites the reference code it replaces (paths relative to
+ * /root/reference/src/multivae/).  The Python binding a MultiVae maintainer would add is the
+ * ctypes stub in multivae_b200/_cabi.py.
+ */
+#ifndef MULTIVAE_B200_H
+#define MULTIVAE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MV_OK 0
+#define MV_ERR_ARG 1
+#define MV_ERR_CUDA 2
+#define MV_ERR_UNSUPPORTED 3
+
+/* element types of activation / reconstruction buffers */
+#define MV_F32 0
+#define MV_BF16 1
+
+/* decoder output distributions: models/base/base_utils.py:62-87 (set_decoder_dist) */
+#define MV_DIST_NORMAL 0
+#define MV_DIST_LAPLACE 1
+#define MV_DIST_BERNOULLI 2
+
+/* latent prior/posterior families: models/mmvaePlus/mmvaePlus_model.py:57-73 */
+#define MV_LATENT_LAPLACE 0
+#define MV_LATENT_NORMAL 1
+
+/* IWAE objectives: mmvaePlus_model.py:305-363, mmvae_model.py:238-292 */
+#define MV_LOSS_IWAE 0
+#define MV_LOSS_DREG 1
+
+/* prior-expert modes of the PoE family: mvtcae_model.py:166 (never), mvae_model.py:75-79 (always,
+ * stable_poe), mopoe_model.py:252-261 (only for the full subset) */
+#define MV_PRIOR_NEVER 0
+#define MV_PRIOR_ALWAYS_STABLE 1
+#define MV_PRIOR_FULL_SUBSET 2
+
+/* fused epilogues of the tensor-core GEMM / implicit-GEMM convolution */
+#define MV_ACT_NONE 0
+#define MV_ACT_RELU 1
+#define MV_ACT_LRELU02 2
+#define MV_ACT_SIGMOID 3
+
+const char* mv_last_error(void);
+/* library/version probe; returns the compiled SM architecture (100 for sm_100a) */
+int mv_version(int* major, int* minor, int* sm_arch);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused ELBO path, MoE family (MMVAE, MMVAE+).
+ * ------------------------------------------------------------------------------------------- */
+
+/* lpx[c,k,b] (+)= rescale * mask_r[b] * sum_d log p(x[b,d] | recon[c,k,b,d])
+ * Replaces: recon_log_probs[recon_mod](x_recon, x).view(K,B,-1).mul(rescale).sum(-1) accumulated
+ * over recon_mod — mmvaePlus_model.py:277-292, mmvae_model.py:208-225, base_utils.py:62-87.
+ * recon: [C,K,B,D] (dtype MV_F32|MV_BF16), x: [B,D] f32, lpx: [C,K,B] f32, mask_r: [B] u8 or NULL. */
+int mv_moe_lpx_fwd(const void* recon, int recon_dtype, const float* x, float* lpx, int C, int K, int B,
+                   int64_t D, int dist, float dist_scale, float rescale, const uint8_t* mask_r,
+                   int accumulate, void* stream);
+
+/* g_recon[c,k,b,d] = g_loss * coef[c,k,b] * rescale * mask_r[b] * d/d(recon) log p(x|recon)
+ * Backward of the above through the IWAE/DReG weights (coef = d loss / d lw, from mv_moe_lw_fwd). */
+int mv_moe_lpx_bwd(const void* recon, int recon_dtype, const float* x, const float* coef,
+                   const float* g_loss, void* g_recon, int C, int K, int B, int64_t D, int dist,
+                   float dist_scale, float rescale, const uint8_t* mask_r, void* stream);
+
+/* Latent terms + importance weights + loss for one batch, and their unit gradients.
+ * Replaces _compute_k_lws + _dreg_looser/_iwae_looser (mmvaePlus_model.py:230-363) and
+ * compute_k_lws + dreg_looser/iwae_looser (mmvae_model.py:160-292).
+ *   u [C,K,B,L], w [C,K,B,Lw] (Lw may be 0: MMVAE), posterior mu_u/sig_u [C,B,L], mu_w/sig_w [C,B,Lw],
+ *   prior pz_mean/pz_std [L+Lw], lpx [C,K,B], masks [C,B] u8 or NULL (mask of modality c for sample b).
+ * Outputs: lw, wk, coef [C,K,B]; loss_b [B] (per-sample loss, already negated and divided by n_mods);
+ *   unit gradients (for d loss = 1): g_u [C,K,B,L], g_w [C,K,B,Lw] (direct terms only, NOT yet multiplied
+ *   by the DReG wk); g_mu_u,g_sig_u [C,B,L], g_mu_w,g_sig_w [C,B,Lw] (zero-filled when detach_post != 0);
+ *   g_pz_std [B,L+Lw] per-sample partials of d loss / d prior std. */
+int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, const float* sig_u, const float* mu_w,
+                  const float* sig_w, const float* pz_mean, const float* pz_std, const float* lpx,
+                  const uint8_t* masks, float* lw, float* wk, float* coef, float* loss_b, float* g_u,
+                  float* g_w, float* g_mu_u, float* g_sig_u, float* g_mu_w, float* g_sig_w, float* g_pz_std,
+                  int C, int K, int B, int L, int Lw, int latent_kind, int loss_kind, float beta,
+                  int detach_post, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused posterior aggregation, PoE family (MVTCAE, MVAE, MoPoE).
+ *   mu, lv      [M,B,L] f32  unimodal posterior parameters (encoder outputs)
+ *   masks       [M,B] u8 or NULL: unavailable experts are excluded (the reference sets their log-variance to
+ *               +inf: mvtcae_model.py:126-130, mvae_model.py:65-70)
+ *   subsets     [S] u32 bitmasks (bit m = modality m), the table of mopoe_model.py:76-106 / mvae_model.py:159-172
+ *   sel         [B] i32 index into `subsets` of the posterior each sample is drawn from
+ *               (deterministic_mixture_component_selection, mopoe_model.py:435-465), NULL = subset 0
+ *   w           [S,B] f32 per-sample subset weights of the KL sum, or NULL = w_uniform for all
+ *   prior_mode  MV_PRIOR_*; stable != 0 selects stable_poe (base_utils.py:133-147), else poe with `eps` (:122-130)
+ * Outputs: z [B,L] = mu_sel + exp(0.5*lv_sel)*noise (rsample_from_gaussian, base_utils.py:150-172), optional
+ *   joint_mu/joint_lv [B,L], kl_b [B] = sum_s w_s * KL(q_s || N(0,I)) (mopoe_model.py:108-145, mvae_model.py:105,
+ *   mvtcae_model.py:52-54), kldm_b [M,B] = KL(q_sel || q_m) (mvtcae_model.py:82-88) or NULL.
+ * mv_poe_bwd recomputes the aggregation and returns d/d(mu,lv) given d/dz, d/dkl_b, d/dkldm_b.
+ * ------------------------------------------------------------------------------------------- */
+int mv_poe_fwd(const float* mu, const float* lv, const uint8_t* masks, const uint32_t* subsets, int S,
+               const int32_t* sel, const float* w, float w_uniform, const float* noise, int prior_mode, int stable,
+               float eps, float* z, float* joint_mu, float* joint_lv, float* kl_b, float* kldm_b, int M, int B,
+               int L, void* stream);
+int mv_poe_bwd(const float* mu, const float* lv, const uint8_t* masks, const uint32_t* subsets, int S,
+               const int32_t* sel, const float* w, float w_uniform, const float* noise, int prior_mode, int stable,
+               float eps, const float* g_z, const float* g_kl, const float* g_kldm, float* g_mu, float* g_lv, int M,
+               int B, int L, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,537 @@
+// Fused ELBO path for the mixture-of-experts models (MMVAE, MMVAE+): HBM-bound elementwise +
+// reduction kernels, 128-bit streaming loads, warp-shuffle reductions, no tensor cores.
+//
+//   mv_moe_lpx_fwd : lpx[c,k,b]  = sum_r rescale_r * sum_d log p_r(x_r[b,d] | recon_r[c,k,b,d])
+//   mv_moe_lw_fwd  : latent log-probs, MoE log-mean-exp, lw, IWAE/DReG weights, loss, unit latent grads
+//   mv_moe_lpx_bwd : g_recon = g_loss * coef[c,k,b] * rescale * dlogp/drecon
+//
+// Work decomposition of the two streaming kernels: one warp owns one (cond modality c, sample b,
+// D-chunk) and keeps the target row x[b, chunk] in registers while it walks the K importance samples,
+// so x is read once per K rows and the only HBM stream is `recon` (read once) / `g_recon` (written once).
+#include "common.cuh"
+
+namespace mv {
+
+// ---- per-element terms (torch.distributions.{Normal,Laplace,Bernoulli}.log_prob) ----------------
+template <int DIST>
+__device__ __forceinline__ float lp_term(float x, float r) {
+  if (DIST == MV_DIST_NORMAL) {
+    float t = x - r;
+    return t * t;
+  } else if (DIST == MV_DIST_LAPLACE) {
+    return fabsf(x - r);
+  } else {  // Bernoulli(logits=r).log_prob(x) = x*r - softplus(r)
+    return x * r - (fmaxf(r, 0.f) + log1pf(__expf(-fabsf(r))));
+  }
+}
+template <int DIST>
+__device__ __forceinline__ float lp_grad(float x, float r, float inv_s) {
+  if (DIST == MV_DIST_NORMAL) {
+    return (x - r) * inv_s * inv_s;
+  } else if (DIST == MV_DIST_LAPLACE) {
+    float t = x - r;
+    return t > 0.f ? inv_s : (t < 0.f ? -inv_s : 0.f);
+  } else {
+    return x - 1.f / (1.f + __expf(-r));
+  }
+}
+
+constexpr int kChunkElems = 2560;  // elements of D one warp keeps in registers (80 floats / lane)
+
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_fwd_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                      float* __restrict__ lpx, int C, int K, int B, int64_t D,
+                                                      float mul, float add_per_elem, float rescale,
+                                                      const uint8_t* __restrict__ mask, int accumulate, int nchunks) {
+  constexpr int VE = Vec<T>::N;
+  constexpr int NV = kChunkElems / (32 * VE);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= int64_t(C) * B * nchunks) return;
+  const int chunk = int(warp % nchunks);
+  const int64_t cb = warp / nchunks;
+  const int b = int(cb % B), c = int(cb / B);
+  const bool live = mask == nullptr || mask[b] != 0;
+  const int64_t nvec = D / VE;
+  const int64_t v0 = int64_t(chunk) * NV * 32 + lane;
+  float xr[NV][VE];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int64_t v = v0 + j * 32;
+    if (live && v < nvec) {
+      const float4* xp = reinterpret_cast<const float4*>(x + int64_t(b) * D + v * VE);
+#pragma unroll
+      for (int q = 0; q < VE / 4; ++q) {
+        float4 t = __ldg(xp + q);
+        xr[j][4 * q + 0] = t.x; xr[j][4 * q + 1] = t.y; xr[j][4 * q + 2] = t.z; xr[j][4 * q + 3] = t.w;
+      }
+    }
+  }
+  int64_t n_here = nvec - int64_t(chunk) * NV * 32;
+  n_here = (n_here > NV * 32 ? NV * 32 : n_here) * VE;
+  for (int k = 0; k < K; ++k) {
+    const int64_t row = (int64_t(c) * K + k) * B + b;
+    float acc = 0.f;
+    if (live) {
+      uint4 rv[NV];
+      const T* rp = recon + row * D;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int64_t v = v0 + j * 32;
+        if (v < nvec) rv[j] = ld_stream(rp + v * VE);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int64_t v = v0 + j * 32;
+        if (v < nvec) {
+          float r[VE];
+          Vec<T>::unpack(rv[j], r);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) acc += lp_term<DIST>(xr[j][e], r[e]);
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float val = live ? rescale * (acc * mul + add_per_elem * float(n_here)) : 0.f;
+      if (nchunks == 1) {
+        lpx[row] = accumulate ? lpx[row] + val : val;
+      } else {
+        atomicAdd(lpx + row, val);
+      }
+    }
+  }
+}
+
+// scalar fallback for rows whose byte length is not a multiple of 16 (e.g. D = 10)
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_fwd_scalar_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                             float* __restrict__ lpx, int C, int K, int B, int64_t D,
+                                                             float mul, float add_per_elem, float rescale,
+                                                             const uint8_t* __restrict__ mask, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= int64_t(C) * K * B) return;
+  const int b = int(row % B);
+  const bool live = mask == nullptr || mask[b] != 0;
+  float acc = 0.f;
+  if (live)
+    for (int64_t d = lane; d < D; d += 32)
+      acc += lp_term<DIST>(x[int64_t(b) * D + d], Vec<T>::load1(recon + row * D + d));
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float val = live ? rescale * (acc * mul + add_per_elem * float(D)) : 0.f;
+    lpx[row] = accumulate ? lpx[row] + val : val;
+  }
+}
+
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_bwd_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                      const float* __restrict__ coef, const float* __restrict__ g_loss,
+                                                      T* __restrict__ g_recon, int C, int K, int B, int64_t D,
+                                                      float inv_s, float rescale, const uint8_t* __restrict__ mask,
+                                                      int nchunks) {
+  constexpr int VE = Vec<T>::N;
+  constexpr int NV = kChunkElems / (32 * VE);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= int64_t(C) * B * nchunks) return;
+  const int chunk = int(warp % nchunks);
+  const int64_t cb = warp / nchunks;
+  const int b = int(cb % B), c = int(cb / B);
+  const bool live = mask == nullptr || mask[b] != 0;
+  const int64_t nvec = D / VE;
+  const int64_t v0 = int64_t(chunk) * NV * 32 + lane;
+  const float gl = *g_loss * rescale;
+  float xr[NV][VE];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int64_t v = v0 + j * 32;
+    if (live && v < nvec) {
+      const float4* xp = reinterpret_cast<const float4*>(x + int64_t(b) * D + v * VE);
+#pragma unroll
+      for (int q = 0; q < VE / 4; ++q) {
+        float4 t = __ldg(xp + q);
+        xr[j][4 * q + 0] = t.x; xr[j][4 * q + 1] = t.y; xr[j][4 * q + 2] = t.z; xr[j][4 * q + 3] = t.w;
+      }
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    const int64_t row = (int64_t(c) * K + k) * B + b;
+    const float cf = live ? coef[row] * gl : 0.f;
+    const T* rp = recon + row * D;
+    T* gp = g_recon + row * D;
+    uint4 rv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int64_t v = v0 + j * 32;
+      if (live && v < nvec) rv[j] = ld_stream(rp + v * VE);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int64_t v = v0 + j * 32;
+      if (v < nvec) {
+        float g[VE];
+        if (live) {
+          float r[VE];
+          Vec<T>::unpack(rv[j], r);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) g[e] = cf * lp_grad<DIST>(xr[j][e], r[e], inv_s);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VE; ++e) g[e] = 0.f;
+        }
+        st_stream(gp + v * VE, Vec<T>::pack(g));
+      }
+    }
+  }
+}
+
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_bwd_scalar_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                             const float* __restrict__ coef,
+                                                             const float* __restrict__ g_loss, T* __restrict__ g_recon,
+                                                             int C, int K, int B, int64_t D, float inv_s, float rescale,
+                                                             const uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= int64_t(C) * K * B) return;
+  const int b = int(row % B);
+  const bool live = mask == nullptr || mask[b] != 0;
+  const float cf = live ? coef[row] * *g_loss * rescale : 0.f;
+  for (int64_t d = lane; d < D; d += 32) {
+    float g = live ? cf * lp_grad<DIST>(x[int64_t(b) * D + d], Vec<T>::load1(recon + row * D + d), inv_s) : 0.f;
+    Vec<T>::store1(g_recon + row * D + d, g);
+  }
+}
+
+// ---- latent log-densities -----------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float lat_lp(float x, float mu, float s) {
+  if (KIND == MV_LATENT_LAPLACE) return -__logf(2.f * s) - fabsf(x - mu) / s;
+  float t = (x - mu) / s;
+  return -0.5f * t * t - __logf(s) - 0.5f * kLog2Pi;
+}
+// d/dx of lat_lp (d/dmu is the negative)
+template <int KIND>
+__device__ __forceinline__ float lat_dx(float x, float mu, float s) {
+  if (KIND == MV_LATENT_LAPLACE) {
+    float t = x - mu;
+    return t > 0.f ? -1.f / s : (t < 0.f ? 1.f / s : 0.f);
+  }
+  return -(x - mu) / (s * s);
+}
+template <int KIND>
+__device__ __forceinline__ float lat_ds(float x, float mu, float s) {
+  if (KIND == MV_LATENT_LAPLACE) return -1.f / s + fabsf(x - mu) / (s * s);
+  float t = x - mu;
+  return -1.f / s + t * t / (s * s * s);
+}
+
+constexpr int kMaxC = 8;  // modalities handled by the latent kernel (reference configs: <= 5)
+
+// one warp per sample b
+template <int KIND>
+__global__ void __launch_bounds__(128) moe_lw_kernel(
+    const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ mu_u,
+    const float* __restrict__ sig_u, const float* __restrict__ mu_w, const float* __restrict__ sig_w,
+    const float* __restrict__ pz_mean, const float* __restrict__ pz_std, const float* __restrict__ lpx,
+    const uint8_t* __restrict__ masks, float* __restrict__ lw, float* __restrict__ wk, float* __restrict__ coef,
+    float* __restrict__ loss_b, float* __restrict__ g_u, float* __restrict__ g_w, float* __restrict__ g_mu_u,
+    float* __restrict__ g_sig_u, float* __restrict__ g_mu_w, float* __restrict__ g_sig_w, float* __restrict__ g_pz_std,
+    int C, int K, int B, int L, int Lw, int loss_kind, float beta, int detach_post) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  int nm = 0;
+  bool avail[kMaxC];
+#pragma unroll
+  for (int m = 0; m < kMaxC; ++m) {
+    avail[m] = m < C && (masks == nullptr || masks[m * B + b] != 0);
+    nm += avail[m] ? 1 : 0;
+  }
+  const float log_nm = __logf(float(nm > 0 ? nm : 1));
+  const float inv_nm = nm > 0 ? 1.f / float(nm) : 0.f;
+  const int LT = L + Lw;
+  // zero the per-sample accumulators this warp owns
+  for (int i = lane; i < LT; i += 32) g_pz_std[int64_t(b) * LT + i] = 0.f;
+  for (int m = 0; m < C; ++m) {
+    for (int l = lane; l < L; l += 32) {
+      g_mu_u[(int64_t(m) * B + b) * L + l] = 0.f;
+      g_sig_u[(int64_t(m) * B + b) * L + l] = 0.f;
+    }
+    for (int l = lane; l < Lw; l += 32) {
+      g_mu_w[(int64_t(m) * B + b) * Lw + l] = 0.f;
+      g_sig_w[(int64_t(m) * B + b) * Lw + l] = 0.f;
+    }
+  }
+  float loss_acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    // ---- pass 1: lw[c,k,b] for all k -----------------------------------------------------------
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const int64_t row = (int64_t(c) * K + k) * B + b;
+      float val = 0.f;
+      if (avail[c]) {
+        float lpz = 0.f, lqw = 0.f, lq[kMaxC];
+#pragma unroll
+        for (int m = 0; m < kMaxC; ++m) lq[m] = 0.f;
+        for (int l = lane; l < L; l += 32) {
+          const float uu = u[row * L + l];
+          lpz += lat_lp<KIND>(uu, pz_mean[l], pz_std[l]);
+#pragma unroll
+          for (int m = 0; m < kMaxC; ++m)
+            if (m < C && avail[m])
+              lq[m] += lat_lp<KIND>(uu, mu_u[(int64_t(m) * B + b) * L + l], sig_u[(int64_t(m) * B + b) * L + l]);
+        }
+        for (int l = lane; l < Lw; l += 32) {
+          const float ww = w[row * Lw + l];
+          lpz += lat_lp<KIND>(ww, pz_mean[L + l], pz_std[L + l]);
+          lqw += lat_lp<KIND>(ww, mu_w[(int64_t(c) * B + b) * Lw + l], sig_w[(int64_t(c) * B + b) * Lw + l]);
+        }
+        lpz = warp_sum(lpz);
+        lqw = warp_sum(lqw);
+        float mq = -INFINITY;
+#pragma unroll
+        for (int m = 0; m < kMaxC; ++m)
+          if (m < C && avail[m]) {
+            lq[m] = warp_sum(lq[m]);
+            mq = fmaxf(mq, lq[m]);
+          }
+        float se = 0.f;
+#pragma unroll
+        for (int m = 0; m < kMaxC; ++m)
+          if (m < C && avail[m]) se += __expf(lq[m] - mq);
+        const float lqu = mq + __logf(se) - log_nm;
+        val = lpx[row] + beta * (lpz - lqu - lqw);
+      }
+      if (lane == 0) lw[row] = val;
+      mx = fmaxf(mx, val);
+    }
+    __syncwarp();
+    // ---- softmax over k ------------------------------------------------------------------------
+    float se = 0.f;
+    for (int k = lane; k < K; k += 32) se += __expf(lw[(int64_t(c) * K + k) * B + b] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    float term = 0.f;  // sum_k wk*lw (DReG) or lse - log K (IWAE)
+    for (int k = lane; k < K; k += 32) {
+      const int64_t row = (int64_t(c) * K + k) * B + b;
+      const float v = lw[row];
+      const float wgt = __expf(v - lse);
+      wk[row] = wgt;
+      coef[row] = avail[c] ? -wgt * inv_nm : 0.f;
+      term += wgt * v;
+    }
+    term = warp_sum(term);
+    if (loss_kind == MV_LOSS_IWAE) term = lse - __logf(float(K));
+    if (avail[c]) loss_acc += term;
+    __syncwarp();
+    // ---- pass 2: unit gradients of the latent terms ----------------------------------------------
+    for (int k = 0; k < K; ++k) {
+      const int64_t row = (int64_t(c) * K + k) * B + b;
+      if (!avail[c]) {
+        for (int l = lane; l < L; l += 32) g_u[row * L + l] = 0.f;
+        for (int l = lane; l < Lw; l += 32) g_w[row * Lw + l] = 0.f;
+        continue;
+      }
+      const float cb = coef[row] * beta;  // d loss / d (lpz - lqu - lqw)
+      // MoE responsibilities sm_m = softmax_m(lq_m)
+      float lq[kMaxC];
+#pragma unroll
+      for (int m = 0; m < kMaxC; ++m) lq[m] = 0.f;
+      for (int l = lane; l < L; l += 32) {
+        const float uu = u[row * L + l];
+#pragma unroll
+        for (int m = 0; m < kMaxC; ++m)
+          if (m < C && avail[m])
+            lq[m] += lat_lp<KIND>(uu, mu_u[(int64_t(m) * B + b) * L + l], sig_u[(int64_t(m) * B + b) * L + l]);
+      }
+      float mq = -INFINITY;
+#pragma unroll
+      for (int m = 0; m < kMaxC; ++m)
+        if (m < C && avail[m]) {
+          lq[m] = warp_sum(lq[m]);
+          mq = fmaxf(mq, lq[m]);
+        }
+      float sq = 0.f;
+#pragma unroll
+      for (int m = 0; m < kMaxC; ++m)
+        if (m < C && avail[m]) {
+          lq[m] = __expf(lq[m] - mq);
+          sq += lq[m];
+        }
+      const float inv_sq = 1.f / sq;
+      for (int l = lane; l < L; l += 32) {
+        const float uu = u[row * L + l];
+        const float pm = pz_mean[l], ps = pz_std[l];
+        float gu = lat_dx<KIND>(uu, pm, ps);
+        g_pz_std[int64_t(b) * LT + l] += cb * lat_ds<KIND>(uu, pm, ps);
+#pragma unroll
+        for (int m = 0; m < kMaxC; ++m)
+          if (m < C && avail[m]) {
+            const int64_t pi = (int64_t(m) * B + b) * L + l;
+            const float mm = mu_u[pi], ss = sig_u[pi];
+            const float r = lq[m] * inv_sq;
+            const float dx = lat_dx<KIND>(uu, mm, ss);
+            gu -= r * dx;
+            if (!detach_post) {
+              g_mu_u[pi] += cb * r * dx;  // -(cb) * r * dlq/dmu, dlq/dmu = -dx
+              g_sig_u[pi] -= cb * r * lat_ds<KIND>(uu, mm, ss);
+            }
+          }
+        g_u[row * L + l] = cb * gu;
+      }
+      for (int l = lane; l < Lw; l += 32) {
+        const float ww = w[row * Lw + l];
+        const float pm = pz_mean[L + l], ps = pz_std[L + l];
+        const int64_t pi = (int64_t(c) * B + b) * Lw + l;
+        const float mm = mu_w[pi], ss = sig_w[pi];
+        const float dx = lat_dx<KIND>(ww, mm, ss);
+        g_w[row * Lw + l] = cb * (lat_dx<KIND>(ww, pm, ps) - dx);
+        g_pz_std[int64_t(b) * LT + L + l] += cb * lat_ds<KIND>(ww, pm, ps);
+        if (!detach_post) {
+          g_mu_w[pi] += cb * dx;
+          g_sig_w[pi] -= cb * lat_ds<KIND>(ww, mm, ss);
+        }
+      }
+    }
+  }
+  if (lane == 0) loss_b[b] = -loss_acc * inv_nm;
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+static void lp_consts(int dist, float s, float* mul, float* add) {
+  if (dist == MV_DIST_NORMAL) {
+    *mul = -1.f / (2.f * s * s);
+    *add = -logf(s) - 0.5f * kLog2Pi;
+  } else if (dist == MV_DIST_LAPLACE) {
+    *mul = -1.f / s;
+    *add = -logf(2.f * s);
+  } else {
+    *mul = 1.f;
+    *add = 0.f;
+  }
+}
+
+template <typename T>
+static int launch_lpx_fwd(const void* recon, const float* x, float* lpx, int C, int K, int B, int64_t D, int dist,
+                          float s, float rescale, const uint8_t* mask, int accumulate, cudaStream_t st) {
+  float mul, add;
+  lp_consts(dist, s, &mul, &add);
+  constexpr int VE = Vec<T>::N;
+  const T* r = static_cast<const T*>(recon);
+  const bool vec_ok = (D % VE == 0) && (reinterpret_cast<uintptr_t>(recon) % 16 == 0) &&
+                      (D % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+  if (vec_ok) {
+    const int nchunks = int((D + kChunkElems - 1) / kChunkElems);
+    if (nchunks > 1 && !accumulate) cudaMemsetAsync(lpx, 0, sizeof(float) * size_t(C) * K * B, st);
+    const int64_t warps = int64_t(C) * B * nchunks;
+    const int blocks = int((warps + 3) / 4);
+#define L_(DI) lpx_fwd_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, lpx, C, K, B, D, mul, add, rescale, mask, accumulate, nchunks)
+    if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
+    else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
+    else L_(MV_DIST_BERNOULLI);
+#undef L_
+  } else {
+    const int64_t rows = int64_t(C) * K * B;
+    const int blocks = int((rows + 3) / 4);
+#define L_(DI) lpx_fwd_scalar_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, lpx, C, K, B, D, mul, add, rescale, mask, accumulate)
+    if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
+    else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
+    else L_(MV_DIST_BERNOULLI);
+#undef L_
+  }
+  MV_CHECK_LAUNCH("mv_moe_lpx_fwd");
+  return MV_OK;
+}
+
+template <typename T>
+static int launch_lpx_bwd(const void* recon, const float* x, const float* coef, const float* g_loss, void* g_recon,
+                          int C, int K, int B, int64_t D, int dist, float s, float rescale, const uint8_t* mask,
+                          cudaStream_t st) {
+  constexpr int VE = Vec<T>::N;
+  const T* r = static_cast<const T*>(recon);
+  T* g = static_cast<T*>(g_recon);
+  const float inv_s = 1.f / s;
+  const bool vec_ok = (D % VE == 0) && (reinterpret_cast<uintptr_t>(recon) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(g_recon) % 16 == 0) && (D % 4 == 0) &&
+                      (reinterpret_cast<uintptr_t>(x) % 16 == 0);
+  if (vec_ok) {
+    const int nchunks = int((D + kChunkElems - 1) / kChunkElems);
+    const int64_t warps = int64_t(C) * B * nchunks;
+    const int blocks = int((warps + 3) / 4);
+#define L_(DI) lpx_bwd_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, coef, g_loss, g, C, K, B, D, inv_s, rescale, mask, nchunks)
+    if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
+    else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
+    else L_(MV_DIST_BERNOULLI);
+#undef L_
+  } else {
+    const int64_t rows = int64_t(C) * K * B;
+    const int blocks = int((rows + 3) / 4);
+#define L_(DI) lpx_bwd_scalar_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, coef, g_loss, g, C, K, B, D, inv_s, rescale, mask)
+    if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
+    else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
+    else L_(MV_DIST_BERNOULLI);
+#undef L_
+  }
+  MV_CHECK_LAUNCH("mv_moe_lpx_bwd");
+  return MV_OK;
+}
+
+extern "C" int mv_moe_lpx_fwd(const void* recon, int recon_dtype, const float* x, float* lpx, int C, int K, int B,
+                              int64_t D, int dist, float dist_scale, float rescale, const uint8_t* mask_r,
+                              int accumulate, void* stream) {
+  MV_CHECK_ARG(recon && x && lpx, "mv_moe_lpx_fwd: null pointer");
+  MV_CHECK_ARG(C > 0 && K > 0 && B > 0 && D > 0, "mv_moe_lpx_fwd: bad sizes C=%d K=%d B=%d D=%lld", C, K, B, (long long)D);
+  MV_CHECK_ARG(dist >= MV_DIST_NORMAL && dist <= MV_DIST_BERNOULLI, "mv_moe_lpx_fwd: unsupported distribution %d", dist);
+  MV_CHECK_ARG(dist == MV_DIST_BERNOULLI || dist_scale > 0.f, "mv_moe_lpx_fwd: scale must be > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (recon_dtype == MV_F32) return launch_lpx_fwd<float>(recon, x, lpx, C, K, B, D, dist, dist_scale, rescale, mask_r, accumulate, st);
+  if (recon_dtype == MV_BF16) return launch_lpx_fwd<__nv_bfloat16>(recon, x, lpx, C, K, B, D, dist, dist_scale, rescale, mask_r, accumulate, st);
+  mv::set_error("mv_moe_lpx_fwd: unsupported dtype %d", recon_dtype);
+  return MV_ERR_UNSUPPORTED;
+}
+
+extern "C" int mv_moe_lpx_bwd(const void* recon, int recon_dtype, const float* x, const float* coef,
+                              const float* g_loss, void* g_recon, int C, int K, int B, int64_t D, int dist,
+                              float dist_scale, float rescale, const uint8_t* mask_r, void* stream) {
+  MV_CHECK_ARG(recon && x && coef && g_loss && g_recon, "mv_moe_lpx_bwd: null pointer");
+  MV_CHECK_ARG(C > 0 && K > 0 && B > 0 && D > 0, "mv_moe_lpx_bwd: bad sizes");
+  MV_CHECK_ARG(dist >= MV_DIST_NORMAL && dist <= MV_DIST_BERNOULLI, "mv_moe_lpx_bwd: unsupported distribution %d", dist);
+  MV_CHECK_ARG(dist == MV_DIST_BERNOULLI || dist_scale > 0.f, "mv_moe_lpx_bwd: scale must be > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (recon_dtype == MV_F32) return launch_lpx_bwd<float>(recon, x, coef, g_loss, g_recon, C, K, B, D, dist, dist_scale, rescale, mask_r, st);
+  if (recon_dtype == MV_BF16) return launch_lpx_bwd<__nv_bfloat16>(recon, x, coef, g_loss, g_recon, C, K, B, D, dist, dist_scale, rescale, mask_r, st);
+  mv::set_error("mv_moe_lpx_bwd: unsupported dtype %d", recon_dtype);
+  return MV_ERR_UNSUPPORTED;
+}
+
+extern "C" int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, const float* sig_u, const float* mu_w,
+                             const float* sig_w, const float* pz_mean, const float* pz_std, const float* lpx,
+                             const uint8_t* masks, float* lw, float* wk, float* coef, float* loss_b, float* g_u,
+                             float* g_w, float* g_mu_u, float* g_sig_u, float* g_mu_w, float* g_sig_w, float* g_pz_std,
+                             int C, int K, int B, int L, int Lw, int latent_kind, int loss_kind, float beta,
+                             int detach_post, void* stream) {
+  MV_CHECK_ARG(u && mu_u && sig_u && pz_mean && pz_std && lpx && lw && wk && coef && loss_b && g_u && g_mu_u &&
+                   g_sig_u && g_pz_std, "mv_moe_lw_fwd: null pointer");
+  MV_CHECK_ARG(Lw == 0 || (w && mu_w && sig_w && g_w && g_mu_w && g_sig_w), "mv_moe_lw_fwd: null private-latent pointer");
+  MV_CHECK_ARG(C > 0 && C <= kMaxC, "mv_moe_lw_fwd: 1 <= n_modalities <= %d required, got %d", kMaxC, C);
+  MV_CHECK_ARG(K > 0 && B > 0 && L > 0 && Lw >= 0, "mv_moe_lw_fwd: bad sizes");
+  MV_CHECK_ARG(loss_kind == MV_LOSS_IWAE || loss_kind == MV_LOSS_DREG, "mv_moe_lw_fwd: unknown loss %d", loss_kind);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (B + 3) / 4;
+  if (latent_kind == MV_LATENT_LAPLACE)
+    moe_lw_kernel<MV_LATENT_LAPLACE><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post);
+  else if (latent_kind == MV_LATENT_NORMAL)
+    moe_lw_kernel<MV_LATENT_NORMAL><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post);
+  else {
+    mv::set_error("mv_moe_lw_fwd: unknown latent kind %d", latent_kind);
+    return MV_ERR_UNSUPPORTED;
+  }
+  MV_CHECK_LAUNCH("mv_moe_lw_fwd");
+  return MV_OK;
+}

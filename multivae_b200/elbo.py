@@ -1,0 +1,200 @@
+"""Host side of the fused ELBO path: torch.autograd.Function wrappers whose forward/backward call
+the CUDA kernels through the C-ABI (multivae_b200/_cabi.py).  No torch fallback.
+
+MoE family (MMVAE / MMVAE+): replaces _compute_k_lws + _dreg_looser / _iwae_looser
+(/root/reference/src/multivae/models/mmvaePlus/mmvaePlus_model.py:230-363,
+ models/mmvae/mmvae_model.py:160-292).
+"""
+import math
+
+import torch
+
+from . import _cabi as C
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+class MoEElboFn(torch.autograd.Function):
+    """loss = -sum_b sum_c [ sum_k wk*lw  |  logsumexp_k lw - log K ] / n_mods(b)
+
+    Tensor inputs (autograd): u (C,K,B,L), w (C,K,B,Lw) or None, mu_u/sig_u (C,B,L), mu_w/sig_w (C,B,Lw) or
+    None, pz_std (L+Lw,), then one reconstruction tensor per recon modality r: (C,K,B,*dims_r), fp32 or bf16.
+    `meta` carries the non-differentiable pieces: targets x_r (B,*dims) fp32, pz_mean, masks (C,B) uint8 or
+    None, per-r (dist, scale, rescale, mask-row index), latent kind, loss kind, beta, detach flag.
+    Also stores meta["wk"], meta["lw"] for the caller (DReG hooks, metrics, parity tests).
+    """
+
+    @staticmethod
+    def forward(ctx, meta, u, w, mu_u, sig_u, mu_w, sig_w, pz_std, *recons):
+        lib = C.lib()
+        Cn, K, B, L = u.shape
+        Lw = 0 if w is None else w.shape[-1]
+        dev = u.device
+        u, mu_u, sig_u, pz_std = _f32c(u), _f32c(mu_u), _f32c(sig_u), _f32c(pz_std)
+        if Lw:
+            w, mu_w, sig_w = _f32c(w), _f32c(mu_w), _f32c(sig_w)
+        masks = meta.get("masks")
+        lpx = torch.empty(Cn, K, B, device=dev, dtype=torch.float32)
+        recons = [r.contiguous() for r in recons]
+        xs = meta["x"]
+        for i, (r, x) in enumerate(zip(recons, xs)):
+            dist, scale, rescale, mrow = meta["recon"][i]
+            D = x[0].numel()
+            assert r.shape[:3] == (Cn, K, B) and r[0, 0, 0].numel() == D, (r.shape, x.shape)
+            mask_r = None if masks is None else masks[mrow]
+            C.check(lib.mv_moe_lpx_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, D, dist, scale,
+                                       rescale, C.ptr(mask_r), 1 if i > 0 else 0, C.stream()), "mv_moe_lpx_fwd")
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        lw, wk, coef, loss_b = f(Cn, K, B), f(Cn, K, B), f(Cn, K, B), f(B)
+        g_u, g_mu_u, g_sig_u = f(Cn, K, B, L), f(Cn, B, L), f(Cn, B, L)
+        g_w = f(Cn, K, B, Lw) if Lw else None
+        g_mu_w = f(Cn, B, Lw) if Lw else None
+        g_sig_w = f(Cn, B, Lw) if Lw else None
+        g_pz = f(B, L + Lw)
+        C.check(lib.mv_moe_lw_fwd(C.ptr(u), C.ptr(w), C.ptr(mu_u), C.ptr(sig_u), C.ptr(mu_w), C.ptr(sig_w),
+                                  C.ptr(meta["pz_mean"]), C.ptr(pz_std), C.ptr(lpx), C.ptr(masks), C.ptr(lw),
+                                  C.ptr(wk), C.ptr(coef), C.ptr(loss_b), C.ptr(g_u), C.ptr(g_w), C.ptr(g_mu_u),
+                                  C.ptr(g_sig_u), C.ptr(g_mu_w), C.ptr(g_sig_w), C.ptr(g_pz), Cn, K, B, L, Lw,
+                                  meta["latent_kind"], meta["loss_kind"], float(meta["beta"]),
+                                  1 if meta["detach"] else 0, C.stream()), "mv_moe_lw_fwd")
+        meta["wk"], meta["lw"], meta["lpx"] = wk, lw, lpx
+        ctx.meta = meta
+        ctx.dims = (Cn, K, B, L, Lw)
+        ctx.save_for_backward(coef, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz, *recons)
+        return loss_b.sum()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        lib = C.lib()
+        meta = ctx.meta
+        Cn, K, B, L, Lw = ctx.dims
+        coef, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz, *recons = ctx.saved_tensors
+        g_loss = g_loss.reshape(1).float().contiguous()
+        masks = meta.get("masks")
+        g_recons = []
+        need = ctx.needs_input_grad
+        for i, r in enumerate(recons):
+            if not need[8 + i]:
+                g_recons.append(None)
+                continue
+            dist, scale, rescale, mrow = meta["recon"][i]
+            x = meta["x"][i]
+            g = torch.empty_like(r)
+            mask_r = None if masks is None else masks[mrow]
+            C.check(lib.mv_moe_lpx_bwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(coef), C.ptr(g_loss), C.ptr(g), Cn, K,
+                                       B, x[0].numel(), dist, scale, rescale, C.ptr(mask_r), C.stream()),
+                    "mv_moe_lpx_bwd")
+            g_recons.append(g)
+        s = g_loss
+        det = meta["detach"]
+        return (None, g_u * s if need[1] else None, (g_w * s) if (Lw and need[2]) else None,
+                None if (det or not need[3]) else g_mu_u * s, None if (det or not need[4]) else g_sig_u * s,
+                None if (det or not Lw or not need[5]) else g_mu_w * s,
+                None if (det or not Lw or not need[6]) else g_sig_w * s,
+                (g_pz.sum(0) * s) if need[7] else None, *g_recons)
+
+
+def log_var_to_std(log_var, kind):
+    """mmvaePlus_model.py:113-123 / mmvae_model.py:66-74 (tiny (B,L) tensors; stays in torch)."""
+    if kind == "laplace_with_softmax":
+        return torch.softmax(log_var, dim=-1) * log_var.size(-1) + 1e-6
+    if kind == "normal_with_softplus":
+        return torch.nn.functional.softplus(log_var) + 1e-6
+    return torch.exp(0.5 * log_var)
+
+
+def standard_noise(shape, kind, device, generator=None):
+    """Standard Laplace(0,1) / Normal(0,1) draws e such that z = loc + scale * e, i.e. what
+    torch.distributions.{Laplace,Normal}.rsample draw internally."""
+    if kind == "laplace_with_softmax":
+        eps = torch.finfo(torch.float32).eps
+        u = torch.empty(shape, device=device, dtype=torch.float32).uniform_(eps - 1, 1, generator=generator)
+        return -u.sign() * torch.log1p(-u.abs().clamp(min=torch.finfo(torch.float32).tiny))
+    return torch.empty(shape, device=device, dtype=torch.float32).normal_(generator=generator)
+
+
+LOG_2PI = math.log(2 * math.pi)
+
+
+class PoEFn(torch.autograd.Function):
+    """Fused subset-PoE aggregation (mv_poe_fwd / mv_poe_bwd).
+
+    forward(meta, mu, lv) with mu, lv (M,B,L) -> (z (B,L), kl_b (B,), kldm_b (M,B) or empty).
+    meta: masks (M,B) u8|None, subsets (S,) int32 bitmasks, sel (B,) int32|None, w (S,B)|None, w_uniform,
+    noise (B,L), prior_mode, stable, eps, want_kldm."""
+
+    @staticmethod
+    def forward(ctx, meta, mu, lv):
+        lib = C.lib()
+        M, B, L = mu.shape
+        mu, lv = _f32c(mu), _f32c(lv)
+        dev = mu.device
+        z = torch.empty(B, L, device=dev, dtype=torch.float32)
+        kl_b = torch.empty(B, device=dev, dtype=torch.float32)
+        kldm = torch.empty(M, B, device=dev, dtype=torch.float32) if meta.get("want_kldm") else None
+        S = meta["subsets"].numel()
+        C.check(lib.mv_poe_fwd(C.ptr(mu), C.ptr(lv), C.ptr(meta.get("masks")), C.ptr(meta["subsets"]), S,
+                               C.ptr(meta.get("sel")), C.ptr(meta.get("w")), float(meta.get("w_uniform", 1.0)),
+                               C.ptr(meta["noise"]), meta["prior_mode"], 1 if meta["stable"] else 0,
+                               float(meta.get("eps", 1e-8)), C.ptr(z), None, None, C.ptr(kl_b), C.ptr(kldm), M, B, L,
+                               C.stream()), "mv_poe_fwd")
+        ctx.meta = meta
+        ctx.save_for_backward(mu, lv)
+        ctx.has_kldm = kldm is not None
+        if kldm is None:
+            kldm = torch.empty(0, device=dev)
+        return z, kl_b, kldm
+
+    @staticmethod
+    def backward(ctx, g_z, g_kl, g_kldm):
+        lib = C.lib()
+        meta = ctx.meta
+        mu, lv = ctx.saved_tensors
+        M, B, L = mu.shape
+        g_mu, g_lv = torch.empty_like(mu), torch.empty_like(lv)
+        S = meta["subsets"].numel()
+        gz = None if g_z is None else _f32c(g_z)
+        gk = None if g_kl is None else _f32c(g_kl)
+        gm = _f32c(g_kldm) if (ctx.has_kldm and g_kldm is not None) else None
+        C.check(lib.mv_poe_bwd(C.ptr(mu), C.ptr(lv), C.ptr(meta.get("masks")), C.ptr(meta["subsets"]), S,
+                               C.ptr(meta.get("sel")), C.ptr(meta.get("w")), float(meta.get("w_uniform", 1.0)),
+                               C.ptr(meta["noise"]), meta["prior_mode"], 1 if meta["stable"] else 0,
+                               float(meta.get("eps", 1e-8)), C.ptr(gz), C.ptr(gk), C.ptr(gm), C.ptr(g_mu), C.ptr(g_lv),
+                               M, B, L, C.stream()), "mv_poe_bwd")
+        return None, g_mu, g_lv
+
+
+class ReconNLLFn(torch.autograd.Function):
+    """nll_b[b] = -rescale * mask[b] * sum_d log p(x[b,d] | recon[b,d])  for one modality (rows = samples).
+    Same streaming kernels as the MoE family with C = K = 1 (mv_moe_lpx_fwd / mv_moe_lpx_bwd).
+    Replaces `(-recon_log_probs[m](recon, x) * rescale).reshape(B,-1).sum(-1)` (+ mask multiply) of
+    mvtcae_model.py:62-70, mvae_model.py:91-102, mopoe_model.py:186-201."""
+
+    @staticmethod
+    def forward(ctx, recon, x, mask, dist, scale, rescale):
+        lib = C.lib()
+        recon = recon.contiguous()
+        B = recon.shape[0]
+        D = recon[0].numel()
+        lp = torch.empty(B, device=recon.device, dtype=torch.float32)
+        C.check(lib.mv_moe_lpx_fwd(C.ptr(recon), C.dtype_code(recon), C.ptr(x), C.ptr(lp), 1, 1, B, D, dist, scale,
+                                   rescale, C.ptr(mask), 0, C.stream()), "mv_moe_lpx_fwd")
+        ctx.save_for_backward(recon, x, mask if mask is not None else torch.empty(0, device=recon.device))
+        ctx.args = (dist, scale, rescale, mask is not None)
+        return -lp
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = C.lib()
+        recon, x, mask = ctx.saved_tensors
+        dist, scale, rescale, has_mask = ctx.args
+        B, D = recon.shape[0], recon[0].numel()
+        coef = (-g).float().contiguous()  # d(-lp)/d lp = -1, times upstream
+        one = torch.ones(1, device=recon.device, dtype=torch.float32)
+        gr = torch.empty_like(recon)
+        C.check(lib.mv_moe_lpx_bwd(C.ptr(recon), C.dtype_code(recon), C.ptr(x), C.ptr(coef), C.ptr(one), C.ptr(gr), 1, 1,
+                                   B, D, dist, scale, rescale, C.ptr(mask) if has_mask else None, C.stream()),
+                "mv_moe_lpx_bwd")
+        return gr, None, None, None, None, None

@@ -1,0 +1,84 @@
+"""CPU tests of the host side: C-ABI library loads and exports every symbol the header declares,
+state_dict keys/shapes equal the reference's, integer subset logic, config errors, no silent fallback."""
+import os
+import re
+
+import pytest
+import torch
+
+import multivae_b200 as mb
+from multivae_b200 import _cabi
+from multivae_b200.subsets import all_subsets, deterministic_selection, mvae_random_subsets
+from oracle.cases import CASES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    hdr = open(os.path.join(ROOT, "include", "multivae_b200.h")).read()
+    declared = set(re.findall(r"\b(mv_[a-z0-9_]+)\s*\(", hdr))
+    lib = _cabi.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(_cabi.exported_symbols()), declared ^ set(_cabi.exported_symbols())
+    mj, mn, sm = (_cabi.ctypes.c_int(), _cabi.ctypes.c_int(), _cabi.ctypes.c_int())
+    assert lib.mv_version(mj, mn, sm) == 0 and sm.value == 100
+
+
+def test_no_cpu_fallback():
+    cfg = mb.MVTCAEConfig(n_modalities=2, latent_dim=4, input_dims={"a": (4,), "b": (6,)})
+    model = mb.MVTCAE(cfg)
+    ds = mb.MultimodalBaseDataset(data={"a": torch.rand(3, 4), "b": torch.rand(3, 6)})
+    with pytest.raises(_cabi.NativeLibraryError):
+        model(ds)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_keys_match_reference(name):
+    from tests.gpu_checks import MODELS
+    import copy
+    rec = torch.load(os.path.join(GOLD, f"elbo_{name}.pt"), weights_only=False)
+    spec = CASES[name]
+    cls, cfgcls = MODELS[spec["model"]]
+    model = cls(cfgcls(n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"])))
+    mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert mine == rec["state_shapes"]
+    ref_trainable = {k for k, g in rec["grads"].items() if g is not None or "prior" not in k}
+    mine_trainable = {k for k, p in model.named_parameters() if p.requires_grad}
+    assert {k for k in mine_trainable if "prior" in k} == {k for k in ref_trainable if "prior" in k}
+
+
+@pytest.mark.parametrize("net", ["enc_resnet_mmnist", "dec_resnet_mmnist", "enc_conv_mmnist", "dec_conv_mmnist", "enc_svhn", "dec_svhn", "enc_mlp", "enc_mlp_style", "dec_mlp"])
+def test_network_state_dict_matches_reference(net):
+    from multivae_b200 import nn as N
+    rec = torch.load(os.path.join(GOLD, f"nets_{net}.pt"), weights_only=False)
+    c = lambda i, l, s=0: mb.BaseAEConfig(input_dim=i, latent_dim=l, style_dim=s)  # noqa: E731
+    ctor = {"enc_resnet_mmnist": lambda: N.EncoderResnetMMNIST(32, 32), "dec_resnet_mmnist": lambda: N.DecoderResnetMMNIST(64),
+            "enc_conv_mmnist": lambda: N.EncoderConvMMNIST_adapted(c((3, 28, 28), 64)), "dec_conv_mmnist": lambda: N.DecoderConvMMNIST(c((3, 28, 28), 64)),
+            "enc_svhn": lambda: N.Encoder_VAE_SVHN(c((3, 32, 32), 20)), "dec_svhn": lambda: N.Decoder_VAE_SVHN(c((3, 32, 32), 20)),
+            "enc_mlp": lambda: N.Encoder_VAE_MLP(c((1, 28, 28), 20)), "enc_mlp_style": lambda: N.Encoder_VAE_MLP_Style(c((3, 8, 8), 8, 4)),
+            "dec_mlp": lambda: N.Decoder_AE_MLP(c((1, 28, 28), 20))}[net]
+    m = ctor()
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == rec["state_shapes"]
+
+
+def test_subset_logic_known_answers():
+    assert list(all_subsets(["mod1", "mod2", "mod3"]).keys()) == ["", "mod1", "mod2", "mod3", "mod1_mod2", "mod1_mod3", "mod2_mod3", "mod1_mod2_mod3"]
+    assert torch.bincount(deterministic_selection(256, 31).long()).tolist() == [8] * 30 + [16]
+    assert torch.bincount(deterministic_selection(32, 31).long()).tolist() == [1] * 30 + [2]
+    assert [list(s) for s in mvae_random_subsets(["a", "b", "c", "d"])] == [list(s) for s in __import__("itertools").combinations("abcd", 2)] + [list(s) for s in __import__("itertools").combinations("abcd", 3)]
+    assert mvae_random_subsets(["a", "b"]) == []
+
+
+def test_config_and_constructor_errors():
+    with pytest.raises(AttributeError):
+        mb.MMVAEPlus(mb.MMVAEPlusConfig(n_modalities=2, input_dims={"a": (4,), "b": (4,)}))  # modalities_specific_dim missing
+    with pytest.raises(AttributeError):
+        mb.MVTCAE(mb.MVTCAEConfig(n_modalities=3, input_dims={"a": (4,), "b": (4,)}))
+    with pytest.raises(ValueError):
+        mb.MMVAEConfig(n_modalities=2, loss="nope")
+    cfg = mb.MVAEConfig(n_modalities=2, input_dims={"a": (4,), "b": (4,)}, k=3)
+    assert mb.MVAE(cfg).k == 0  # k forced to 0 when M <= 2 (mvae_model.py:40-41)
