@@ -54,6 +54,8 @@ extern "C" {
 const char* mv_last_error(void);
 /* library/version probe; returns the compiled SM architecture (100 for sm_100a) */
 int mv_version(int* major, int* minor, int* sm_arch);
+/* number of CUDA kernels this library has launched in this process (bench.py's "gpu_launches") */
+unsigned long long mv_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused ELBO path, MoE family (MMVAE, MMVAE+).

@@ -19,6 +19,7 @@ LOSS = {"iwae_looser": 0, "dreg_looser": 1}
 ACT = {"none": 0, "relu": 1, "lrelu": 2, "sigmoid": 3}
 
 _lib = None
+_raw = None
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
@@ -41,25 +42,82 @@ class NativeLibraryError(RuntimeError):
     pass
 
 
+class KernelTimer:
+    """Optional per-entry-point device timing: when active, every C-ABI call is bracketed by CUDA
+    events on the launching (current) stream; `summary()` synchronises once and returns
+    {symbol: (calls, total_ms)}.  Used by bench.py for the live roofline numbers."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for key, e0, e1 in self.records:
+            c, t = out.get(key, (0, 0.0))
+            out[key] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+_timer = None
+
+
+def set_timer(t):
+    global _timer
+    _timer = t
+
+
+class _Lib:
+    """Attribute proxy over the CDLL: same callables, plus the optional KernelTimer bracket."""
+
+    def __init__(self, raw):
+        self._raw = raw
+
+    def __getattr__(self, name):
+        fn = getattr(self._raw, name)
+        if name not in _PROTOS or name == "mv_version":
+            return fn
+
+        def call(*args, tag=None):
+            if _timer is None:
+                return fn(*args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*args)
+            e1.record()
+            _timer.records.append((name if tag is None else f"{name}:{tag}", e0, e1))
+            return r
+
+        self.__dict__[name] = call
+        return call
+
+
 def lib():
     """Load (once) and return the shared library; raise loudly if it has not been built."""
-    global _lib
+    global _lib, _raw
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise NativeLibraryError(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                 "multivae_b200 has no CPU or eager fallback.")
-        _lib = ctypes.CDLL(LIB_PATH)
-        _lib.mv_last_error.restype = ctypes.c_char_p
+        _raw = ctypes.CDLL(LIB_PATH)
+        _raw.mv_last_error.restype = ctypes.c_char_p
+        _raw.mv_launch_count.restype = ctypes.c_ulonglong
+        _raw.mv_launch_count.argtypes = []
         for name, args in _PROTOS.items():
-            fn = getattr(_lib, name)
+            fn = getattr(_raw, name)
             fn.argtypes = args
             fn.restype = c_int
+        _lib = _Lib(_raw)
     return _lib
 
 
+def launch_count():
+    return int(lib().mv_launch_count())
+
+
 def exported_symbols():
-    return ["mv_last_error"] + list(_PROTOS)
+    return ["mv_last_error", "mv_launch_count"] + list(_PROTOS)
 
 
 def check(status, what):

@@ -23,6 +23,9 @@ class BaseMultiVAE(nn.Module):
         self.latent_dim = model_config.latent_dim
         self.device = None
         self.multiple_latent_spaces = False
+        # arithmetic type of the encoder/decoder contractions (bf16 operands, fp32 accumulate) — the
+        # parameters themselves and the whole ELBO path stay fp32 like the reference
+        self.compute_dtype = torch.float32
         self.use_likelihood_rescaling = model_config.uses_likelihood_rescaling
         if model_config.input_dims is not None and len(model_config.input_dims) != model_config.n_modalities:
             raise AttributeError(
@@ -106,6 +109,14 @@ class BaseMultiVAE(nn.Module):
             if not isinstance(dec, BaseDecoder):
                 raise AttributeError(f"For modality {m}, decoder must inherit from BaseDecoder class. Refer to documentation.")
             self.decoders[m] = dec
+
+    def _nn_ctx(self):
+        """Context in which the encoders / decoders run (library layers: bf16 autocast when
+        compute_dtype is bf16; the native tcgen05 layers read `compute_dtype` themselves)."""
+        import contextlib
+        if self.compute_dtype == torch.bfloat16 and torch.cuda.is_available():
+            return torch.autocast("cuda", dtype=torch.bfloat16)
+        return contextlib.nullcontext()
 
     def update(self):
         """Called by the trainer at the end of each epoch (base_trainer.py:738-741)."""

@@ -1,5 +1,6 @@
 // Error plumbing + version probe of the C-ABI.
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -11,7 +12,11 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace mv
+
+extern "C" unsigned long long mv_launch_count(void) { return __atomic_load_n(&mv::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* mv_last_error(void) { return mv::g_err; }
 

@@ -12,6 +12,7 @@
 namespace mv {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // bumps the counter behind mv_launch_count()
 
 #define MV_CHECK_ARG(cond, ...)       \
   do {                                \
@@ -28,6 +29,7 @@ void set_error(const char* fmt, ...);
       mv::set_error("%s: CUDA error %s", name, cudaGetErrorString(e__));       \
       return MV_ERR_CUDA;                                                      \
     }                                                                          \
+    mv::count_launch();                                                        \
   } while (0)
 
 constexpr float kLog2Pi = 1.8378770664093453f;

@@ -41,14 +41,16 @@ class MMVAE(BaseMultiVAE):
         B = len(inputs.data[mods[0]])
         mus, sigs, zs = [], [], []
         for c in mods:
-            o = self.encoders[c](inputs.data[c])
+            with self._nn_ctx():
+                o = self.encoders[c](inputs.data[c])
             s = log_var_to_std(o.log_covariance.float(), kind)
             mus.append(o.embedding.float()); sigs.append(s)
             zs.append(mus[-1] + s * self._noise((K, B, s.shape[-1]), dev))
         Z = torch.stack(zs)
         recons = []
         for r in mods:
-            rec = self.decoders[r](Z.reshape(-1, Z.shape[-1]))["reconstruction"]
+            with self._nn_ctx():
+                rec = self.decoders[r](Z.reshape(-1, Z.shape[-1]))["reconstruction"]
             recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
         pz_std = log_var_to_std(self.prior_log_var, kind).reshape(-1)
         meta = dict(x=[inputs.data[r].float().contiguous() for r in mods],

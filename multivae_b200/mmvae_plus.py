@@ -68,7 +68,8 @@ class MMVAEPlus(BaseMultiVAE):
         # u, w, then one prior draw per *other* modality: mmvaePlus_model.py:136-186)
         mu_u, sig_u, mu_w, sig_w, u, w, w_cross = [], [], [], [], [], [], {}
         for c in mods:
-            o = self.encoders[c](inputs.data[c])
+            with self._nn_ctx():
+                o = self.encoders[c](inputs.data[c])
             su = log_var_to_std(o.log_covariance.float(), kind)
             sw = log_var_to_std(o.style_log_covariance.float(), kind)
             mu_u.append(o.embedding.float()); sig_u.append(su)
@@ -86,7 +87,8 @@ class MMVAEPlus(BaseMultiVAE):
         for r in mods:
             wz = torch.stack([W[i] if c == r else w_cross[(c, r)] for i, c in enumerate(mods)])
             z = torch.cat([U, wz], dim=-1)
-            rec = self.decoders[r](z.reshape(-1, z.shape[-1]))["reconstruction"]
+            with self._nn_ctx():
+                rec = self.decoders[r](z.reshape(-1, z.shape[-1]))["reconstruction"]
             recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
 
         pz_std = log_var_to_std(self.logvars_priors["shared"], kind).reshape(-1)

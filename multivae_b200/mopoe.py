@@ -44,7 +44,8 @@ class MoPoE(BaseMultiVAE):
     def forward(self, inputs, **kwargs):
         order = list(self.encoders.keys())
         dev = inputs.data[order[0]].device
-        outs = [self.encoders[m](inputs.data[m]) for m in order]
+        with self._nn_ctx():
+            outs = [self.encoders[m](inputs.data[m]) for m in order]
         mu = torch.stack([o.embedding.float() for o in outs])
         lv = torch.stack([o.log_covariance.float() for o in outs])
         M, B, L = mu.shape
@@ -73,7 +74,8 @@ class MoPoE(BaseMultiVAE):
         results = {"joint_divergence": kl_b.mean()}
         loss = 0
         for i, m in enumerate(order):
-            rec = self.decoders[m](z).reconstruction
+            with self._nn_ctx():
+                rec = self.decoders[m](z).reconstruction
             dist, scale = self.recon_dists[m]
             mrow = inputs.masks[m].to(torch.uint8).contiguous() if hasattr(inputs, "masks") else None
             nll = ReconNLLFn.apply(rec, inputs.data[m].float().contiguous(), mrow, dist, scale,

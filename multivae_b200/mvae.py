@@ -37,7 +37,8 @@ class MVAE(BaseMultiVAE):
                 for i in choice(np.arange(len(self.subsets)), size=self.k, replace=False):
                     subsets.append(self.subsets[i])
         dev = inputs.data[order[0]].device
-        outs = {m: self.encoders[m](inputs.data[m]) for m in order}
+        with self._nn_ctx():
+            outs = {m: self.encoders[m](inputs.data[m]) for m in order}
         mu = torch.stack([outs[m].embedding.float() for m in order])
         lv = torch.stack([outs[m].log_covariance.float() for m in order])
         M, B, L = mu.shape
@@ -74,7 +75,8 @@ class MVAE(BaseMultiVAE):
             elbo = 0
             for m in self.decoders:
                 if m in s:
-                    rec = self.decoders[m](z).reconstruction
+                    with self._nn_ctx():
+                        rec = self.decoders[m](z).reconstruction
                     dist, scale = self.recon_dists[m]
                     mk = None
                     if has_masks:

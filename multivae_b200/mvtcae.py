@@ -18,7 +18,8 @@ class MVTCAE(BaseMultiVAE):
     def forward(self, inputs, **kwargs):
         mods = list(inputs.data.keys())
         dev = inputs.data[mods[0]].device
-        outs = [self.encoders[m](inputs.data[m]) for m in mods]
+        with self._nn_ctx():
+            outs = [self.encoders[m](inputs.data[m]) for m in mods]
         mu = torch.stack([o.embedding.float() for o in outs])
         lv = torch.stack([o.log_covariance.float() for o in outs])
         M, B, L = mu.shape
@@ -35,7 +36,8 @@ class MVTCAE(BaseMultiVAE):
         loss_rec = 0
         for i, m in enumerate(mods):
             # the reference iterates self.encoders.keys(); with complete inputs the orders coincide
-            rec = self.decoders[m](z).reconstruction
+            with self._nn_ctx():
+                rec = self.decoders[m](z).reconstruction
             dist, scale = self.recon_dists[m]
             nll = ReconNLLFn.apply(rec, inputs.data[m].float().contiguous(), None if masks is None else masks[i],
                                    dist, scale, float(self.rescale_factors[m]))

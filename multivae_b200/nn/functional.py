@@ -46,3 +46,10 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, act="none"):
 
 def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0, act="none"):
     return _ACT[act](F.conv_transpose2d(x, weight, bias, stride=stride, padding=padding, output_padding=output_padding))
+
+
+def backend_summary():
+    """Which implementation each layer family runs on (reported by bench.py)."""
+    from . import resnet_native as RN
+    return {"elbo": "native sm_100a kernels (C-ABI)", "resnet_decoder": RN.status("decoder"),
+            "resnet_encoder": RN.status("encoder"), "other_layers": "torch (cuDNN/cuBLAS library calls)"}

@@ -1,0 +1,217 @@
+"""Host side of the training step: a mirror of the reference's `BaseTrainer.train_step` /
+`_optimizers_step` / DDP wrap (/root/reference/src/multivae/trainers/base/base_trainer.py:350-361,
+682-750, 92-117, 171-219) for the five hot-path models, built B200-first:
+
+  * one process per GPU (`LOCAL_RANK`/`RANK`/`WORLD_SIZE` from the environment, like
+    base_trainer_config.py:80-100); the batch is sharded by rank exactly like
+    `DistributedSampler(num_replicas, rank, shuffle=False)`; parameters are replicated;
+  * gradients live in ONE flat fp32 buffer per model (every `p.grad` is a view into it), so the
+    data-parallel exchange is one NCCL all-reduce (mean) over NVLink per step instead of DDP's 25 MB
+    buckets (payloads are 6-89 MB) and `zero_grad` is one memset;
+  * no per-step `torch.cuda.empty_cache()` and no per-step `.item()`: `loss_sum` is accumulated on
+    the device and read back once per epoch (the NaN guard keeps the reference's `ArithmeticError`).
+
+Out of scope here (the reference's Python stays as is): callbacks, checkpoints, schedulers, eval/predict.
+"""
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .containers import DatasetOutput
+
+
+@dataclass
+class BaseTrainerConfig:
+    """The subset of base_trainer_config.py:10-152 the training step reads."""
+    per_device_train_batch_size: int = 64
+    num_epochs: int = 100
+    optimizer_cls: str = "Adam"
+    optimizer_params: Optional[dict] = None
+    learning_rate: float = 1e-4
+    no_cuda: bool = False
+    world_size: int = -1
+    local_rank: int = -1
+    rank: int = -1
+    dist_backend: str = "nccl"
+    master_addr: str = "127.0.0.1"
+    master_port: str = "12345"
+    gradient_clipping_max_norm: Optional[float] = None
+    beta_schedule: Optional[list] = field(default=None)
+
+    def __post_init__(self):
+        env = os.environ
+        if self.world_size == -1 and "WORLD_SIZE" in env:
+            self.world_size = int(env["WORLD_SIZE"])
+        if self.rank == -1 and "RANK" in env:
+            self.rank = int(env["RANK"])
+        if self.local_rank == -1 and "LOCAL_RANK" in env:
+            self.local_rank = int(env["LOCAL_RANK"])
+        if not hasattr(torch.optim, self.optimizer_cls):
+            raise AttributeError(f"Unable to import `{self.optimizer_cls}` optimizer from 'torch.optim'.")
+
+
+def shard_indices(n, world_size, rank):
+    """Indices of `DistributedSampler(dataset, num_replicas=world_size, rank=rank, shuffle=False,
+    drop_last=False)`: pad to a multiple of world_size by wrapping, then take rank::world_size."""
+    total = (n + world_size - 1) // world_size * world_size
+    idx = list(range(n))
+    idx += idx[: total - n]
+    return idx[rank:total:world_size]
+
+
+class FlatGrads:
+    """All parameter gradients as views of one flat fp32 buffer (the all-reduce bucket)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        o = 0
+        for p in self.params:
+            assert p.dtype == torch.float32, "master parameters are fp32 (reference is fp32 end to end)"
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def rebind(self):
+        """Autograd may replace .grad when it was set to None by user code; restore the views."""
+        o = 0
+        for p in self.params:
+            v = self.flat[o:o + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = v
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+            o += p.numel()
+
+    def allreduce_mean(self, group=None):
+        """DDP semantics: grad = (1/W) * sum_r grad_r  (base_trainer.py:116-117)."""
+        w = dist.get_world_size(group)
+        if w == 1:
+            return
+        if self.flat.is_cuda:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+        else:  # gloo (CPU tests) has no AVG
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(w)
+
+
+class BaseTrainer:
+    """`BaseTrainer(model, train_dataset, training_config=...)`; `.train_step(epoch)` returns
+    `(epoch_loss, epoch_metrics)` like the reference (epoch_loss = sum of loss_sum / len(train_dataset),
+    metrics averaged over batches)."""
+
+    def __init__(self, model, train_dataset, eval_dataset=None, training_config=None, callbacks=None,
+                 checkpoint=None):
+        self.training_config = training_config or BaseTrainerConfig()
+        cfg = self.training_config
+        self.model = model
+        self.train_dataset = train_dataset
+        self.world_size = max(cfg.world_size, 1)
+        self.rank = max(cfg.rank, 0)
+        self.local_rank = max(cfg.local_rank, 0)
+        self.distributed = cfg.world_size > 1
+        self.device = self._setup_devices()
+        self.model.to(self.device)
+        self.model.device = self.device
+        self.flat = FlatGrads(self.model.parameters())
+        self.set_optimizer()
+        self._broadcast_parameters()
+
+    # base_trainer.py:171-193
+    def _setup_devices(self):
+        cfg = self.training_config
+        if cfg.no_cuda or not torch.cuda.is_available():
+            device = torch.device("cpu")
+        else:
+            torch.cuda.set_device(self.local_rank)
+            device = torch.device("cuda", self.local_rank)
+        if self.distributed and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", cfg.master_addr)
+            os.environ.setdefault("MASTER_PORT", cfg.master_port)
+            backend = cfg.dist_backend if device.type == "cuda" else "gloo"
+            dist.init_process_group(backend=backend, init_method="env://", world_size=self.world_size,
+                                    rank=self.rank)
+        return device
+
+    def _broadcast_parameters(self):
+        """DDP's initial rank-0 parameter/buffer broadcast."""
+        if self.distributed:
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=0)
+
+    # base_trainer.py:230-246
+    def set_optimizer(self):
+        cfg = self.training_config
+        cls = getattr(torch.optim, cfg.optimizer_cls)
+        kw = dict(cfg.optimizer_params or {})
+        if self.device.type == "cuda" and cfg.optimizer_cls in ("Adam", "AdamW", "SGD"):
+            kw.setdefault("fused", True)
+        self.optimizer = cls([p for p in self.model.parameters() if p.requires_grad], lr=cfg.learning_rate, **kw)
+
+    def local_batches(self):
+        """This rank's batches of the dataset, in DistributedSampler order."""
+        n = len(self.train_dataset)
+        idx = shard_indices(n, self.world_size, self.rank) if self.distributed else list(range(n))
+        bs = self.training_config.per_device_train_batch_size
+        for i in range(0, len(idx), bs):
+            sel = idx[i:i + bs]
+            contiguous = sel == list(range(sel[0], sel[0] + len(sel)))
+            take = (lambda t: t[sel[0]:sel[0] + len(sel)]) if contiguous else (lambda t: t[torch.as_tensor(sel)])
+            out = DatasetOutput(data={m: take(t) for m, t in self.train_dataset.data.items()})
+            if hasattr(self.train_dataset, "masks"):
+                out["masks"] = {m: take(t) for m, t in self.train_dataset.masks.items()}
+            yield out
+
+    def _to_device(self, inputs):
+        mv = lambda t: t.to(self.device, non_blocking=True)  # noqa: E731
+        out = DatasetOutput(data={m: mv(t) for m, t in inputs.data.items()})
+        if hasattr(inputs, "masks"):
+            out["masks"] = {m: mv(t) for m, t in inputs.masks.items()}
+        return out
+
+    # base_trainer.py:350-361
+    def _optimizers_step(self, model_output):
+        self.flat.zero()
+        model_output.loss.backward()
+        self.flat.rebind()
+        if self.distributed:
+            self.flat.allreduce_mean()
+        self.optimizer.step()
+
+    def step_batch(self, inputs, epoch=1, batch_ratio=0.0, n_batches=1):
+        """One batch of train_step (base_trainer.py:704-728) without the host read-back."""
+        inputs = self._to_device(inputs)
+        sched = self.training_config.beta_schedule
+        beta_epoch = sched[epoch - 1] if sched is not None else 1
+        out = self.model(inputs, epoch=epoch, dataset_size=len(self.train_dataset), uses_ddp=self.distributed,
+                         batch_ratio=batch_ratio, beta=beta_epoch)
+        self._optimizers_step(out)
+        return out
+
+    # base_trainer.py:682-750
+    def train_step(self, epoch):
+        self.model.train()
+        batches = list(self.local_batches())
+        epoch_loss = torch.zeros((), device=self.device, dtype=torch.float64)
+        metrics = {}
+        for i, inputs in enumerate(batches):
+            out = self.step_batch(inputs, epoch=epoch, batch_ratio=i / len(batches), n_batches=len(batches))
+            loss = out.loss_sum if hasattr(out, "loss_sum") else out.loss
+            epoch_loss += loss.detach().double()
+            for k, v in out.metrics.items():
+                v = v.detach().double() if torch.is_tensor(v) else torch.tensor(float(v), device=self.device, dtype=torch.float64)
+                metrics[k] = metrics.get(k, 0) + v
+        total = float(epoch_loss)  # the one device->host sync of the epoch
+        if total != total:
+            raise ArithmeticError("NaN detected in train loss")
+        self.model.update()
+        metrics = {k: float(v) / len(batches) for k, v in metrics.items()}
+        return total / len(self.train_dataset), metrics
