@@ -115,6 +115,48 @@ int mv_poe_bwd(const float* mu, const float* lv, const uint8_t* masks, const uin
                float eps, const float* g_z, const float* g_kl, const float* g_kldm, float* g_mu, float* g_lv, int M,
                int B, int L, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core contractions of the encoders / decoders (tcgen05 + TMA, bf16 operands, fp32 accumulate).
+ *
+ * Activations of a convolutional stage live in a "shared-halo" NHWC matrix: rows = flat pixels,
+ * columns = channels (bf16).  Image i of height H, width W occupies rows [i*S, (i+1)*S), S = (H+1)*(W+1):
+ * first one zero row of W+1 pixels, then H rows of W real pixels followed by one zero pixel; after the
+ * last image comes one more zero row, so the matrix has n_img*S + (W+1) rows.  In this layout filter tap
+ * (r,s) of a 3x3 / stride 1 / pad 1 convolution reads the same matrix shifted by (r-1)*(W+1) + (s-1) rows.
+ *
+ * mv_tapgemm:  out[p, n] = epilogue( sum_t sum_c A[p + tap_off[t], c] * Wt[t*N_total + n, c] )
+ *   Replaces (forward and data-gradient) nn.Conv2d 3x3 / 1x1 and nn.Linear of models/nn/mmnist.py:214-366
+ *   (ResnetBlock :229-241, fc :289-295,339, conv_img :287,352-354) and default_architectures.py:31-39,237-241.
+ *   epilogue:  y = act(acc + bias[n]);  if dact1: y *= (dact1[p,n] > 0 ? 1 : slope1)
+ *              if out2 && out2_pre: out2[p,n] = y
+ *              o = alpha*y + (res ? res[p,n] : 0);  out[p,n] = o
+ *              if out2 && !out2_pre: out2[p,n] = alpha2 * o * (dact2 ? (dact2[p,n] > 0 ? 1 : slope2) : 1)
+ *   rows that are halo positions (img_stride > 0) are written as zeros.  out_mode 1 scatters the first
+ *   n_valid columns of the valid pixels to a dense NCHW bf16 image tensor [n_img, n_valid, H, W].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mv_tapgemm_args {
+  const void* A;        /* bf16 [a_rows, a_ld] (first Cin columns used) */
+  int64_t a_rows;
+  int32_t a_ld, Cin;    /* Cin: 16 or a multiple of 64 */
+  const void* Wt;       /* bf16 [T * N_total, Cin], K-major */
+  int32_t T;
+  int32_t tap_off[9];
+  int32_t N_total, BN;  /* output columns, columns per CTA tile (16/32/64/128) */
+  int64_t P;            /* output rows */
+  const float* bias;    /* [N_total] or NULL */
+  int32_t act;          /* MV_ACT_* */
+  float alpha;
+  const void* res; int32_t res_ld;
+  const void* dact1; int32_t dact1_ld; float slope1;
+  void* out; int32_t out_ld;
+  void* out2; int32_t out2_ld; int32_t out2_pre; float alpha2;
+  const void* dact2; int32_t dact2_ld; float slope2;
+  int32_t img_stride, Wp, W, H, n_img;   /* halo geometry (img_stride = 0: plain GEMM, no mask) */
+  int32_t out_mode, n_valid;
+} mv_tapgemm_args;
+int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,23 @@ _raw = None
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
+class TapGemmArgs(ctypes.Structure):
+    """mv_tapgemm_args of include/multivae_b200.h (field order and types must match)."""
+    _fields_ = [
+        ("A", c_void_p), ("a_rows", c_int64), ("a_ld", ctypes.c_int32), ("Cin", ctypes.c_int32),
+        ("Wt", c_void_p), ("T", ctypes.c_int32), ("tap_off", ctypes.c_int32 * 9),
+        ("N_total", ctypes.c_int32), ("BN", ctypes.c_int32), ("P", c_int64),
+        ("bias", c_void_p), ("act", ctypes.c_int32), ("alpha", c_float),
+        ("res", c_void_p), ("res_ld", ctypes.c_int32),
+        ("dact1", c_void_p), ("dact1_ld", ctypes.c_int32), ("slope1", c_float),
+        ("out", c_void_p), ("out_ld", ctypes.c_int32),
+        ("out2", c_void_p), ("out2_ld", ctypes.c_int32), ("out2_pre", ctypes.c_int32), ("alpha2", c_float),
+        ("dact2", c_void_p), ("dact2_ld", ctypes.c_int32), ("slope2", c_float),
+        ("img_stride", ctypes.c_int32), ("Wp", ctypes.c_int32), ("W", ctypes.c_int32), ("H", ctypes.c_int32),
+        ("n_img", ctypes.c_int32), ("out_mode", ctypes.c_int32), ("n_valid", ctypes.c_int32),
+    ]
+
+
 # symbol -> argtypes, exactly the prototypes in include/multivae_b200.h
 _PROTOS = {
     "mv_version": [ctypes.POINTER(c_int)] * 3,
@@ -33,6 +50,7 @@ _PROTOS = {
     "mv_moe_lw_fwd": [c_void_p] * 21 + [c_int] * 7 + [c_float, c_int, c_void_p],
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
+    "mv_tapgemm": [ctypes.POINTER(TapGemmArgs), c_void_p],
     "mv_poe_bwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
 }

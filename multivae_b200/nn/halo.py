@@ -1,0 +1,91 @@
+"""Shared-halo NHWC activation layout + thin Python wrappers over the tensor-core C-ABI entry points.
+
+Layout (include/multivae_b200.h): a stage with images of H x W pixels and C channels is ONE bf16 matrix
+[P, C], P = n_img*S + (W+1), S = (H+1)*(W+1): per image one zero row, then H rows of W pixels + 1 zero
+pixel; one more zero row after the last image.  Every 3x3/pad-1 tap is a constant row shift of it."""
+import torch
+
+from .. import _cabi as C
+
+
+class Geom:
+    def __init__(self, n_img, H, W):
+        self.n_img, self.H, self.W = n_img, H, W
+        self.Wp = W + 1
+        self.S = (H + 1) * self.Wp
+        self.P = n_img * self.S + self.Wp
+
+    def taps3x3(self):
+        """Row offsets of the 9 taps in (kh, kw) order of a torch Conv2d weight."""
+        return [(r - 1) * self.Wp + (s - 1) for r in range(3) for s in range(3)]
+
+    def up2(self):
+        return Geom(self.n_img, self.H * 2, self.W * 2)
+
+
+def to_halo(x, dtype=torch.bfloat16):
+    """NCHW -> halo matrix [P, C] (torch ops; used for inputs and by the tests)."""
+    n, c, h, w = x.shape
+    g = Geom(n, h, w)
+    buf = torch.zeros(g.P, c, device=x.device, dtype=dtype)
+    v = buf[: n * g.S].view(n, h + 1, g.Wp, c)
+    v[:, 1:, :w, :] = x.permute(0, 2, 3, 1).to(dtype)
+    return buf, g
+
+
+def from_halo(a, g):
+    """halo matrix [P, C] -> NCHW (same dtype)."""
+    c = a.shape[1]
+    v = a[: g.n_img * g.S].view(g.n_img, g.H + 1, g.Wp, c)
+    return v[:, 1:, : g.W, :].permute(0, 3, 1, 2).contiguous()
+
+
+def pack_conv_weight(w, dtype=torch.bfloat16):
+    """torch Conv2d weight [N, C, kh, kw] -> forward tap-major K-major pack [kh*kw*N, C]."""
+    n, c, kh, kw = w.shape
+    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw * n, c).to(dtype).contiguous()
+
+
+def pack_conv_weight_dgrad(w, dtype=torch.bfloat16):
+    """Data-gradient pack: [kh*kw*C, N] with the taps flipped (dX[p] = sum_t dY[p - off_t] W_t^T)."""
+    n, c, kh, kw = w.shape
+    return w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw * c, n).to(dtype).contiguous()
+
+
+def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act="none", alpha=1.0, res=None, dact1=None,
+            slope1=0.2, out=None, out2=None, out2_pre=False, alpha2=1.0, dact2=None, slope2=0.2, geom=None,
+            nchw_out=None, n_valid=0, tag=None):
+    """out[p, n] = epilogue(sum_t sum_c A[p + tap_off[t], c] * Wt[t*N_total + n, c]); see mv_tapgemm."""
+    lib = C.lib()
+    Cin = A.shape[1] if Cin is None else Cin
+    assert A.dtype == torch.bfloat16 and Wt.dtype == torch.bfloat16 and A.stride(1) == 1 and Wt.is_contiguous()
+    assert Wt.shape == (T * N_total, Cin), (Wt.shape, T, N_total, Cin)
+    if BN is None:
+        BN = 128 if N_total % 128 == 0 else (64 if N_total % 64 == 0 else (32 if N_total % 32 == 0 else 16))
+    a = C.TapGemmArgs()
+    a.A, a.a_rows, a.a_ld, a.Cin = A.data_ptr(), A.shape[0], A.stride(0), Cin
+    a.Wt, a.T = Wt.data_ptr(), T
+    for i, o in enumerate(tap_off):
+        a.tap_off[i] = int(o)
+    a.N_total, a.BN, a.P = N_total, BN, P
+    a.bias = None if bias is None else C.ptr(bias)
+    a.act, a.alpha = C.ACT[act], float(alpha)
+    if nchw_out is not None:
+        out = nchw_out
+        a.out_mode, a.n_valid, a.out_ld = 1, n_valid, 0
+    else:
+        if out is None:
+            out = torch.empty(P, N_total, device=A.device, dtype=torch.bfloat16)
+        a.out_mode, a.out_ld = 0, out.stride(0)
+    a.out = out.data_ptr()
+    for name, t in (("res", res), ("dact1", dact1), ("dact2", dact2), ("out2", out2)):
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.stride(1) == 1
+            setattr(a, name, t.data_ptr())
+            setattr(a, name + "_ld", t.stride(0))
+    a.slope1, a.slope2, a.out2_pre, a.alpha2 = float(slope1), float(slope2), int(out2_pre), float(alpha2)
+    if geom is not None:
+        a.img_stride, a.Wp, a.W, a.H, a.n_img = geom.S, geom.Wp, geom.W, geom.H, geom.n_img
+    kw = {} if tag is None else {"tag": tag}
+    C.check(lib.mv_tapgemm(a, C.stream(), **kw), "mv_tapgemm")
+    return out

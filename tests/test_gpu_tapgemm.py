@@ -1,0 +1,104 @@
+"""tcgen05 tap-GEMM (mv_tapgemm) against plain PyTorch fp32 references of the same ops on the same
+bf16-rounded operands: 3x3 / 1x1 convolutions in the shared-halo layout (forward and data-gradient
+packs), Linear, the fused epilogues and the NCHW image head."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.rand(*shape, device="cuda", generator=g) * 2 - 1) * scale
+
+
+def _close(got, ref, tol=2e-2):
+    err = float((got.float() - ref).abs().max())
+    den = float(ref.abs().max()) + 1e-6
+    assert err / den <= tol, (err, den)
+
+
+@pytest.mark.parametrize("n_img,H,cin,cout", [(37, 28, 64, 64), (300, 28, 64, 64), (23, 14, 128, 64), (41, 7, 256, 128),
+                                              (19, 7, 128, 128), (9, 14, 64, 64)])
+def test_conv3x3_forward_epilogues(n_img, H, cin, cout):
+    from multivae_b200.nn import halo as HL
+    x = _rnd(n_img, cin, H, H, seed=1).bfloat16()
+    w = _rnd(cout, cin, 3, 3, seed=2, scale=cin ** -0.5).bfloat16()
+    b = _rnd(cout, seed=3)
+    r = _rnd(n_img, cout, H, H, seed=4).bfloat16()
+    A, g = HL.to_halo(x)
+    R, _ = HL.to_halo(r)
+    act = torch.empty(g.P, cout, device="cuda", dtype=torch.bfloat16)
+    out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), cout, g.P, bias=b, act="lrelu", alpha=0.1, res=R,
+                     out2=act, out2_pre=True, geom=g)
+    y = F.leaky_relu(F.conv2d(x.float(), w.float(), b, padding=1), 0.2)
+    _close(HL.from_halo(act, g), y)
+    _close(HL.from_halo(out, g), r.float() + 0.1 * y)
+    # halo rows must stay exactly zero (they are the padding of the next convolution)
+    mask = torch.ones(g.P, dtype=torch.bool, device="cuda")
+    v = mask[: n_img * g.S].view(n_img, H + 1, g.Wp)
+    v[:, 1:, :H] = False
+    assert float(out[mask].abs().max()) == 0.0 and float(act[mask].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n_img,H,cin,cout", [(21, 28, 64, 64), (17, 14, 128, 64), (11, 7, 256, 128)])
+def test_conv3x3_dgrad_with_activation_derivative(n_img, H, cin, cout):
+    from multivae_b200.nn import halo as HL
+    gy = _rnd(n_img, cout, H, H, seed=5).bfloat16()
+    w = _rnd(cout, cin, 3, 3, seed=6, scale=cout ** -0.5).bfloat16()
+    saved = _rnd(n_img, cin, H, H, seed=7).bfloat16()   # activation of the layer below (sign decides lrelu')
+    short = _rnd(n_img, cin, H, H, seed=8).bfloat16()
+    G, g = HL.to_halo(gy)
+    S_, _ = HL.to_halo(saved)
+    R, _ = HL.to_halo(short)
+    out = HL.tapgemm(G, HL.pack_conv_weight_dgrad(w), 9, g.taps3x3(), cin, g.P, dact1=S_, res=R, geom=g)
+    ref = F.conv_transpose2d(gy.float(), w.float(), padding=1) * torch.where(saved.float() > 0, 1.0, 0.2) + short.float()
+    _close(HL.from_halo(out, g), ref)
+
+
+def test_conv1x1_and_two_outputs():
+    from multivae_b200.nn import halo as HL
+    n_img, H, cin, cout = 29, 14, 128, 64
+    x = _rnd(n_img, cin, H, H, seed=9).bfloat16()
+    w = _rnd(cout, cin, 1, 1, seed=10, scale=cin ** -0.5).bfloat16()
+    d = _rnd(n_img, cout, H, H, seed=11).bfloat16()
+    A, g = HL.to_halo(x)
+    D, _ = HL.to_halo(d)
+    o2 = torch.empty(g.P, cout, device="cuda", dtype=torch.bfloat16)
+    out = HL.tapgemm(A, HL.pack_conv_weight(w), 1, [0], cout, g.P, out2=o2, alpha2=0.1, dact2=D, geom=g)
+    ref = F.conv2d(x.float(), w.float())
+    _close(HL.from_halo(out, g), ref)
+    _close(HL.from_halo(o2, g), 0.1 * ref * torch.where(d.float() > 0, 1.0, 0.2))
+
+
+def test_image_head_nchw_and_cin16():
+    from multivae_b200.nn import halo as HL
+    n_img, H = 33, 28
+    x = _rnd(n_img, 64, H, H, seed=12).bfloat16()
+    w = _rnd(3, 64, 3, 3, seed=13, scale=0.05).bfloat16()
+    b = _rnd(3, seed=14)
+    A, g = HL.to_halo(x)
+    wp = torch.zeros(16, 64, 3, 3, device="cuda", dtype=torch.bfloat16)
+    wp[:3] = w
+    bp = torch.zeros(16, device="cuda")
+    bp[:3] = b
+    img = torch.empty(n_img, 3, H, H, device="cuda", dtype=torch.bfloat16)
+    HL.tapgemm(A, HL.pack_conv_weight(wp), 9, g.taps3x3(), 16, g.P, bias=bp, act="lrelu", geom=g, nchw_out=img, n_valid=3)
+    _close(img, F.leaky_relu(F.conv2d(x.float(), w.float(), b, padding=1), 0.2))
+    # data gradient of the head: 16 (3 real) channels in, 64 out  -> the SWIZZLE_32B operand path
+    gy = torch.zeros(n_img, 16, H, H, device="cuda", dtype=torch.bfloat16)
+    gy[:, :3] = _rnd(n_img, 3, H, H, seed=15).bfloat16()
+    G, _ = HL.to_halo(gy)
+    out = HL.tapgemm(G, HL.pack_conv_weight_dgrad(wp), 9, g.taps3x3(), 64, g.P, geom=g)
+    _close(HL.from_halo(out, g), F.conv_transpose2d(gy[:, :3].float(), w.float(), padding=1))
+
+
+@pytest.mark.parametrize("rows,K,N", [(1000, 64, 16384), (333, 512, 256), (128, 16384, 64)])
+def test_linear(rows, K, N):
+    from multivae_b200.nn import halo as HL
+    x = _rnd(rows, K, seed=16).bfloat16()
+    w = _rnd(N, K, seed=17, scale=K ** -0.5).bfloat16()
+    b = _rnd(N, seed=18)
+    out = HL.tapgemm(x, w, 1, [0], N, rows, bias=b, act="relu")
+    _close(out, F.relu(F.linear(x.float(), w.float(), b)))
