@@ -19,6 +19,8 @@
 //   warp 1   allocates TMEM, one lane issues tcgen05.mma and commits to the mbarriers
 //   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's MMAs
 //            overlap), bias / activation / activation-derivative / residual / halo mask, bf16 store
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -27,7 +29,7 @@ namespace mv {
 using bf16 = __nv_bfloat16;
 
 constexpr int kMaxTaps = 9;
-constexpr int kMaxInStages = 4;
+constexpr int kMaxInStages = 3;
 constexpr int kMaxWStages = 20;
 constexpr int kBM = 128;
 
@@ -57,30 +59,196 @@ struct TapGemmParams {
   float slope2;
   int img_stride, Wp, W, H, n_img;
   int out_mode, n_valid;
+  int use_tma_store;       // outputs leave through a swizzled shared-memory staging tile + TMA store
+  uint32_t stage_out_bytes; // bytes of one output's staging area (BN/64 boxes of 128 rows x 128 B)
+  uint32_t epi_flags;       // EF_* bits describing which epilogue terms are present
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case MV_ACT_RELU: return fmaxf(v, 0.f);
-    case MV_ACT_LRELU02: return v > 0.f ? v : 0.2f * v;
-    case MV_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    default: return v;
-  }
-}
 
-// 8 consecutive bf16 of a row (16-byte vector) -> floats
-__device__ __forceinline__ void ld8(const bf16* p, float* f) {
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
+// 8 consecutive bf16 of a row (16-byte vector) <-> floats
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
   f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
 }
-__device__ __forceinline__ void st8(bf16* p, const float* f) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 ldg16(const bf16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
 }
 
-template <int CK>
-__global__ void __launch_bounds__(192, 1)
-tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TapGemmParams p) {
+constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter, interleaved over column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // producer warp + MMA warp + epilogue warps
+
+// Epilogue variants are compile-time flag sets (the runtime-flag version cost ~90 instructions per column).
+enum : uint32_t {
+  EF_BIAS = 1, EF_RES = 2, EF_DACT1 = 4, EF_OUT2_PRE = 8, EF_OUT2_POST = 16, EF_DACT2 = 32, EF_SIGMOID = 64,
+  EF_NCHW = 128, EF_GENERIC = 0x80000000u
+};
+template <uint32_t F>
+__device__ __forceinline__ bool has(const TapGemmParams& p, uint32_t bit) {
+  return (F & EF_GENERIC) ? (p.epi_flags & bit) != 0 : (F & bit) != 0;
+}
+
+struct RowCtx {
+  int row, rloc;  // global row, row within the tile
+  bool valid;
+  int img, y, x;
+};
+
+// One chunk of CW accumulator columns of one row: side inputs prefetched by load_side.
+template <int CW>
+struct Side {
+  uint4 a[CW / 8], b[CW / 8];  // a: residual or dact1 source; b: dact2 source
+};
+template <int CW, uint32_t F>
+__device__ __forceinline__ void load_side(Side<CW>& s, const TapGemmParams& p, const RowCtx& r, int n) {
+  if (!r.valid) return;
+  if (has<F>(p, EF_RES)) {
+#pragma unroll
+    for (int g = 0; g < CW / 8; ++g) s.a[g] = ldg16(p.res + size_t(r.row) * p.res_ld + n + g * 8);
+  } else if (has<F>(p, EF_DACT1)) {
+#pragma unroll
+    for (int g = 0; g < CW / 8; ++g) s.a[g] = ldg16(p.dact1 + size_t(r.row) * p.dact1_ld + n + g * 8);
+  }
+  if (has<F>(p, EF_DACT2)) {
+#pragma unroll
+    for (int g = 0; g < CW / 8; ++g) s.b[g] = ldg16(p.dact2 + size_t(r.row) * p.dact2_ld + n + g * 8);
+  }
+}
+
+template <int CW, uint32_t F>
+__device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t* v, const Side<CW>& s, const float* s_bias,
+                                          int cb /*column within the tile*/, int n /*global column*/, const RowCtx& r,
+                                          float neg, uint8_t* st_out, uint8_t* st_out2) {
+#pragma unroll
+  for (int g = 0; g < CW / 8; ++g) {
+    float o[8], o2[8];
+    if (r.valid) {
+      float yv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[e] = __uint_as_float(v[g * 8 + e]);
+      if (has<F>(p, EF_BIAS)) {
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cb + g * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cb + g * 8 + 4);
+        yv[0] += b0.x; yv[1] += b0.y; yv[2] += b0.z; yv[3] += b0.w;
+        yv[4] += b1.x; yv[5] += b1.y; yv[6] += b1.z; yv[7] += b1.w;
+      }
+      // none / relu / leaky-relu as one max: slope `neg` is 1 / 0 / 0.2
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[e] = fmaxf(yv[e], neg * yv[e]);
+      if (has<F>(p, EF_SIGMOID)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] = 1.f / (1.f + __expf(-yv[e]));
+      }
+      if (has<F>(p, EF_DACT1) && !has<F>(p, EF_RES)) {
+        float d[8];
+        unpack8(s.a[g], d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
+      } else if (has<F>(p, EF_DACT1)) {  // both a residual and dact1: dact1 is fetched late (rare)
+        float d[8];
+        unpack8(ldg16(p.dact1 + size_t(r.row) * p.dact1_ld + n + g * 8), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
+      }
+      if (has<F>(p, EF_OUT2_PRE)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o2[e] = yv[e];
+      }
+      if (has<F>(p, EF_RES)) {
+        float rr[8];
+        unpack8(s.a[g], rr);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(p.alpha, yv[e], rr[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = p.alpha * yv[e];
+      }
+      if (has<F>(p, EF_OUT2_POST)) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o2[e] = p.alpha2 * o[e];
+        if (has<F>(p, EF_DACT2)) {
+          float d[8];
+          unpack8(s.b[g], d);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o2[e] *= d[e] > 0.f ? 1.f : p.slope2;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { o[e] = 0.f; o2[e] = 0.f; }
+    }
+    const int nn = n + g * 8;
+    const bool two = has<F>(p, EF_OUT2_PRE) || has<F>(p, EF_OUT2_POST);
+    if (has<F>(p, EF_NCHW)) {
+      if (r.valid) {  // NCHW scatter of the first n_valid channels (decoder image head)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int ch = nn + e;
+          if (ch < p.n_valid)
+            p.out[((size_t(r.img) * p.n_valid + ch) * p.H + (r.y - 1)) * p.W + r.x] = __float2bfloat16_rn(o[e]);
+        }
+      }
+    } else if (st_out) {
+      // staging tile: 64-column boxes of 128 rows x 128 B, SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7))
+      const int col = cb + g * 8;
+      const uint32_t off = uint32_t(col >> 6) * 16384u + uint32_t(r.rloc) * 128u + uint32_t((((col & 63) >> 3) ^ (r.rloc & 7)) << 4);
+      *reinterpret_cast<uint4*>(st_out + off) = pack8(o);
+      if (two) *reinterpret_cast<uint4*>(st_out2 + off) = pack8(o2);
+    } else if (r.row < p.P) {
+      *reinterpret_cast<uint4*>(p.out + size_t(r.row) * p.out_ld + nn) = pack8(o);
+      if (two) *reinterpret_cast<uint4*>(p.out2 + size_t(r.row) * p.out2_ld + nn) = pack8(o2);
+    }
+  }
+}
+
+// The epilogue of one tile for one warp (its TMEM lane quarter, every second column chunk).
+template <int BN, uint32_t F>
+__device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half,
+                                         uint32_t taddr, uint64_t* full_bar, uint32_t full_parity, float neg, uint8_t* stg_base,
+                                         int et) {
+  constexpr int CW = BN >= 32 ? 32 : 16;
+  constexpr int NCH = BN / CW;
+  Side<CW> cur, nxt;
+  if (half < NCH) load_side<CW, F>(cur, p, r, n0 + half * CW);
+  tc::mbar_wait(full_bar, full_parity);
+  tc::fence_after_sync();
+  uint8_t* st_out = nullptr;
+  uint8_t* st_out2 = nullptr;
+  if (p.use_tma_store) {
+    // the previous tile's TMA store must have finished READING the staging tile before it is rewritten
+    if (et == 0) tc::tma_store_wait_read<0>();
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    st_out = stg_base;
+    st_out2 = stg_base + p.stage_out_bytes;
+  }
+#pragma unroll
+  for (int ch = half; ch < NCH; ch += 2) {
+    if (ch + 2 < NCH) load_side<CW, F>(nxt, p, r, n0 + (ch + 2) * CW);
+    uint32_t v[32];
+    if (CW == 32) tc::tmem_ld_32x32(taddr + ch * CW, v);
+    else tc::tmem_ld_32x16(taddr + ch * CW, v);
+    tc::tmem_ld_wait();
+    epi_apply<CW, F>(p, v, cur, s_bias, ch * CW, n0 + ch * CW, r, neg, st_out, st_out2);
+    if (ch + 2 < NCH) cur = nxt;
+  }
+}
+
+// rarely used flag combinations: one out-of-line copy so that its register needs do not tax the hot variants
+template <int BN>
+__device__ __noinline__ void epi_tile_generic(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half,
+                                              uint32_t taddr, uint64_t* full_bar, uint32_t full_parity, float neg,
+                                              uint8_t* stg_base, int et) {
+  epi_tile<BN, EF_GENERIC>(p, r, s_bias, n0, half, taddr, full_bar, full_parity, neg, stg_base, et);
+}
+
+template <int CK, int BN, int TT>
+__global__ void __launch_bounds__(kThreads, 1)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const TapGemmParams p) {
   constexpr uint32_t ROWB = CK * 2;            // bytes per shared-memory row (one pixel, CK channels)
   constexpr int KSTEPS = CK / 16;              // UMMA K = 16 for bf16
   constexpr uint32_t SWZ = CK == 64 ? tc::SW_128 : tc::SW_32;
@@ -89,7 +257,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* in_base = smem;
   uint8_t* w_base = smem + size_t(p.in_stages) * p.in_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + size_t(p.w_stages) * p.w_stage_bytes);
+  uint8_t* stg_base = w_base + ((size_t(p.w_stages) * p.w_stage_bytes + 1023) & ~size_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (p.use_tma_store ? 2 * size_t(p.stage_out_bytes) : 0));
   uint64_t* in_full = bars;
   uint64_t* in_empty = in_full + kMaxInStages;
   uint64_t* w_full = in_empty + kMaxInStages;
@@ -97,12 +266,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tm_full = w_empty + kMaxWStages;
   uint64_t* tm_empty = tm_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  const int T = TT > 0 ? TT : p.T;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kEpiWarps); }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
@@ -115,164 +286,192 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles_total = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      int is = 0, iph = 0, ws = 0, wph = 0;
-      if (p.w_resident) {
-        for (int j = 0; j < p.T * p.n_kc; ++j) {
-          const int kc = j / p.T, t = j % p.T;
+    // ================= TMA producer =================
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses and coordinates in uniform
+    // registers); one elected lane arms the barrier and issues the copy.
+    int is = 0, iph = 0, ws = 0, wph = 0;
+    if (p.w_resident) {
+      for (int j = 0; j < T * p.n_kc; ++j) {
+        const int kc = j / T, t = j % T;
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(&w_full[j], p.w_stage_bytes);
           tc::tma_load_2d(w_base + size_t(j) * p.w_stage_bytes, &tmW, &w_full[j], kc * CK, t * p.N_total);
         }
+        __syncwarp();
       }
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * p.BN;
-        for (int kc = 0; kc < p.n_kc; ++kc) {
-          tc::mbar_wait(&in_empty[is], iph ^ 1);
+    }
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        tc::mbar_wait(&in_empty[is], iph ^ 1);
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * ROWB);
           tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], kc * CK, p0 - p.halo_lo);
-          if (++is == p.in_stages) { is = 0; iph ^= 1; }
-          if (!p.w_resident) {
-            for (int t = 0; t < p.T; ++t) {
-              tc::mbar_wait(&w_empty[ws], wph ^ 1);
+        }
+        __syncwarp();
+        if (++is == p.in_stages) { is = 0; iph ^= 1; }
+        if (!p.w_resident) {
+          for (int t = 0; t < T; ++t) {
+            tc::mbar_wait(&w_empty[ws], wph ^ 1);
+            if (tc::elect_one()) {
               tc::mbar_expect_tx(&w_full[ws], p.w_stage_bytes);
               tc::tma_load_2d(w_base + size_t(ws) * p.w_stage_bytes, &tmW, &w_full[ws], kc * CK, t * p.N_total + n0);
-              if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
             }
+            __syncwarp();
+            if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      const uint32_t idesc = tc::idesc_bf16(kBM, p.BN, 0, 0);
-      int is = 0, iph = 0, ws = 0, wph = 0, it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-        const int acc = it & 1, acc_ph = (it >> 1) & 1;
-        tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
-        tc::fence_after_sync();
-        const uint32_t tmem_d = tmem_base + uint32_t(acc * p.acc_stride);
-        for (int kc = 0; kc < p.n_kc; ++kc) {
-          tc::mbar_wait(&in_full[is], iph);
-          tc::fence_after_sync();
-          const uint32_t a_base = tc::smem_u32(in_base + size_t(is) * p.in_stage_bytes);
-          for (int t = 0; t < p.T; ++t) {
-            uint32_t b_base;
-            if (p.w_resident) {
-              const int j = kc * p.T + t;
-              if (it == 0) { tc::mbar_wait(&w_full[j], 0); tc::fence_after_sync(); }
-              b_base = tc::smem_u32(w_base + size_t(j) * p.w_stage_bytes);
-            } else {
-              tc::mbar_wait(&w_full[ws], wph);
-              tc::fence_after_sync();
-              b_base = tc::smem_u32(w_base + size_t(ws) * p.w_stage_bytes);
-            }
-            const uint32_t a_tap = a_base + uint32_t(p.halo_lo + p.tap_off[t]) * ROWB;
+    // ================= MMA issuer =================
+    // Warp-uniform loop, one elected lane issues.  The 64-bit shared-memory descriptors differ only in
+    // their 14-bit start-address field, so the loop carries 32-bit low words and one constant high word;
+    // with the tap count known at compile time the per-tap row offsets sit in registers and the MMAs of a
+    // K chunk are issued back to back.
+    const uint32_t idesc = tc::idesc_bf16(kBM, BN, 0, 0);
+    const uint32_t desc_hi = uint32_t(tc::smem_desc(0, 16, SBO, SWZ) >> 32);
+    const uint32_t desc_lo_const = uint32_t(tc::smem_desc(0, 16, SBO, SWZ) & 0xffffffffu);
+    constexpr int TU = TT > 0 ? TT : 1;
+    uint32_t tap_lo[TU];   // (tap_off * ROWB) >> 4, added to the descriptor start-address field
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              tc::umma_bf16(tmem_d, tc::smem_desc(a_tap + k * 32, 16, SBO, SWZ), tc::smem_desc(b_base + k * 32, 16, SBO, SWZ),
-                            idesc, (kc | t | k) != 0);
-            }
-            if (!p.w_resident) {
-              tc::umma_commit(&w_empty[ws]);
-              if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
-            }
-          }
-          tc::umma_commit(&in_empty[is]);
-          if (++is == p.in_stages) { is = 0; iph ^= 1; }
-        }
-        tc::umma_commit(&tm_full[acc]);
-      }
-    }
-  } else {
-    // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
-    const int q = warp & 3;
-    int it = 0;
+    for (int t = 0; t < TU; ++t) tap_lo[t] = uint32_t(int(p.halo_lo + p.tap_off[t]) * int(ROWB)) >> 4;
+    int is = 0, iph = 0, ws = 0, wph = 0, it = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-      const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * p.BN;
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
-      const int row = p0 + q * 32 + lane;
-      bool valid = row < p.P;
-      int img = 0, y = 0, x = 0;
-      if (p.img_stride > 0) {
-        img = row / p.img_stride;
-        const int r = row - img * p.img_stride;
-        y = r / p.Wp;
-        x = r - y * p.Wp;
-        valid = valid && img < p.n_img && y >= 1 && x < p.W;
-      }
-      tc::mbar_wait(&tm_full[acc], acc_ph);
+      tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t v[32];
-        const int ncol = p.BN - c0 >= 32 ? 32 : 16;
-        if (ncol == 32) tc::tmem_ld_32x32(taddr + c0, v);
-        else tc::tmem_ld_32x16(taddr + c0, v);
-        tc::tmem_ld_wait();
-        if (row >= p.P) continue;
-        const int n = n0 + c0;
+      const uint32_t tmem_d = tmem_base + uint32_t(acc * p.acc_stride);
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        tc::mbar_wait(&in_full[is], iph);
+        tc::fence_after_sync();
+        const uint32_t a_lo0 = desc_lo_const | ((tc::smem_u32(in_base + size_t(is) * p.in_stage_bytes) & 0x3FFFFu) >> 4);
+        if (p.w_resident) {
+          if (it == 0) {
+            for (int t = 0; t < T; ++t) tc::mbar_wait(&w_full[kc * T + t], 0);
+            tc::fence_after_sync();
+          }
+          const uint32_t b_lo0 = desc_lo_const | ((tc::smem_u32(w_base + size_t(kc * T) * p.w_stage_bytes) & 0x3FFFFu) >> 4);
+          const uint32_t b_step = p.w_stage_bytes >> 4;
+          if (tc::elect_one()) {
+            if (TT > 0) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 8 >= ncol) break;
-          float o[8], o2[8];
+              for (int t = 0; t < TU; ++t) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { o[e] = 0.f; o2[e] = 0.f; }
-          if (valid) {
-            float yv[8];
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo0 + tap_lo[t] + 2u * k);
+                  const uint64_t bd = (uint64_t(desc_hi) << 32) | (b_lo0 + uint32_t(t) * b_step + 2u * k);
+                  tc::umma_bf16(tmem_d, ad, bd, idesc, (kc | t | k) != 0);
+                }
+              }
+            } else {
+              for (int t = 0; t < T; ++t) {
+                const uint32_t tl = uint32_t(int(p.halo_lo + p.tap_off[t]) * int(ROWB)) >> 4;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float a = __uint_as_float(v[g * 8 + e]);
-              if (p.bias) a += __ldg(p.bias + n + g * 8 + e);
-              yv[e] = apply_act(a, p.act);
-            }
-            if (p.dact1) {
-              float d[8];
-              ld8(p.dact1 + size_t(row) * p.dact1_ld + n + g * 8, d);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
-            }
-            if (p.out2 && p.out2_pre) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o2[e] = yv[e];
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = p.alpha * yv[e];
-            if (p.res) {
-              float r[8];
-              ld8(p.res + size_t(row) * p.res_ld + n + g * 8, r);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] += r[e];
-            }
-            if (p.out2 && !p.out2_pre) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o2[e] = p.alpha2 * o[e];
-              if (p.dact2) {
-                float d[8];
-                ld8(p.dact2 + size_t(row) * p.dact2_ld + n + g * 8, d);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o2[e] *= d[e] > 0.f ? 1.f : p.slope2;
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo0 + tl + 2u * k);
+                  const uint64_t bd = (uint64_t(desc_hi) << 32) | (b_lo0 + uint32_t(t) * b_step + 2u * k);
+                  tc::umma_bf16(tmem_d, ad, bd, idesc, (kc | t | k) != 0);
+                }
               }
             }
           }
-          if (p.out_mode == 0) {
-            st8(p.out + size_t(row) * p.out_ld + n + g * 8, o);
-            if (p.out2) st8(p.out2 + size_t(row) * p.out2_ld + n + g * 8, o2);
-          } else if (valid) {  // NCHW scatter of the first n_valid channels (decoder image head)
+          __syncwarp();
+        } else {
+          for (int t = 0; t < T; ++t) {
+            tc::mbar_wait(&w_full[ws], wph);
+            tc::fence_after_sync();
+            const uint32_t b_lo = desc_lo_const | ((tc::smem_u32(w_base + size_t(ws) * p.w_stage_bytes) & 0x3FFFFu) >> 4);
+            const uint32_t tl = TT > 0 ? 0u : (uint32_t(int(p.halo_lo + p.tap_off[t]) * int(ROWB)) >> 4);
+            if (tc::elect_one()) {
+              uint32_t a_lo = a_lo0 + tl;
+              if (TT > 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int ch = n + g * 8 + e;
-              if (ch < p.n_valid)
-                p.out[((size_t(img) * p.n_valid + ch) * p.H + (y - 1)) * p.W + x] = __float2bfloat16_rn(o[e]);
+                for (int u = 0; u < TU; ++u) a_lo = (u == t) ? a_lo0 + tap_lo[u] : a_lo;
+              }
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo + 2u * k);
+                const uint64_t bd = (uint64_t(desc_hi) << 32) | (b_lo + 2u * k);
+                tc::umma_bf16(tmem_d, ad, bd, idesc, (kc | t | k) != 0);
+              }
+              tc::umma_commit(&w_empty[ws]);
             }
+            __syncwarp();
+            if (++ws == p.w_stages) { ws = 0; wph ^= 1; }
           }
         }
+        if (tc::elect_one()) tc::umma_commit(&in_empty[is]);
+        __syncwarp();
+        if (++is == p.in_stages) { is = 0; iph ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&tm_full[acc]);
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue (warps 2..9) =================
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the tile's column
+    // chunks.  The CTA uses (almost) all shared memory, so there is no L1 and every global load is an L2
+    // round trip: bias sits in shared memory and the side inputs of a chunk are fetched one chunk ahead
+    // (the first one before the wait on the accumulator barrier), so their latency hides behind the MMAs.
+    // Outputs go to a swizzled staging tile and leave with one TMA store per 64-column box.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;             // 0 or 1
+    const int et = threadIdx.x - 64;
+    const float neg = p.act == MV_ACT_LRELU02 ? 0.2f : (p.act == MV_ACT_RELU ? 0.f : 1.f);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+      const int acc = it & 1, acc_ph = (it >> 1) & 1;
+      RowCtx r;
+      r.rloc = q * 32 + lane;
+      r.row = p0 + r.rloc;
+      r.valid = r.row < p.P;
+      r.img = 0; r.y = 0; r.x = 0;
+      if (p.img_stride > 0) {
+        r.img = r.row / p.img_stride;
+        const int rr = r.row - r.img * p.img_stride;
+        r.y = rr / p.Wp;
+        r.x = rr - r.y * p.Wp;
+        r.valid = r.valid && r.img < p.n_img && r.y >= 1 && r.x < p.W;
+      }
+      if ((p.epi_flags & EF_BIAS) && (it == 0 || p.n_tiles > 1)) {
+        if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (et < BN) s_bias[et] = p.bias[n0 + et];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
+      const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
+#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et)
+      switch (p.epi_flags) {
+        case 0u: MV_EPI(0u); break;
+        case EF_BIAS: MV_EPI(EF_BIAS); break;
+        case EF_BIAS | EF_RES | EF_OUT2_PRE: MV_EPI(EF_BIAS | EF_RES | EF_OUT2_PRE); break;
+        case EF_DACT1: MV_EPI(EF_DACT1); break;
+        case EF_RES: MV_EPI(EF_RES); break;
+        case EF_OUT2_POST | EF_DACT2: MV_EPI(EF_OUT2_POST | EF_DACT2); break;
+        case EF_BIAS | EF_NCHW: MV_EPI(EF_BIAS | EF_NCHW); break;
+        default: epi_tile_generic<BN>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et); break;
+      }
+#undef MV_EPI
+      // accumulator drained: hand the TMEM buffer back to the MMA warp before the stores go out
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
+      if (p.use_tma_store) {
+        tc::fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (et == 0) {
+#pragma unroll
+          for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b) {
+            tc::tma_store_2d(&tmO, stg_base + b * 16384, n0 + b * 64, p0);
+            if (p.epi_flags & (EF_OUT2_PRE | EF_OUT2_POST))
+              tc::tma_store_2d(&tmO2, stg_base + p.stage_out_bytes + b * 16384, n0 + b * 64, p0);
+          }
+          tc::tma_store_commit();
+        }
+      }
     }
+    if (p.use_tma_store && et == 0) tc::tma_store_wait_all<0>();
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -325,23 +524,35 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   const uint32_t rowb = CK * 2;
   p.in_stage_bytes = (uint32_t(p.R) * rowb + 1023u) & ~1023u;
   p.w_stage_bytes = uint32_t(a->BN) * rowb;
-  const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 4) * 8 + 16;
+  if (const char* e = getenv("MV_TG_IN_STAGE_BYTES")) {  // layout experiments
+    uint32_t v = uint32_t(atoi(e));
+    if (v >= p.in_stage_bytes) p.in_stage_bytes = v & ~1023u;
+  }
+  const size_t fixed = 2048 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 4) * 8 + 16 + 128 * 4;
   const int w_tiles = p.T * p.n_kc;
+  p.use_tma_store = (a->out_mode == 0 && a->BN >= 64 && a->out_ld % 8 == 0 && (!a->out2 || a->out2_ld % 8 == 0)) ? 1 : 0;
+  p.stage_out_bytes = uint32_t(a->BN / 64) * 16384u;
+  const size_t stg = p.use_tma_store ? 2 * size_t(p.stage_out_bytes) + 1024 : 0;
+  const size_t budget = kSmemLimit - fixed - stg;
   // weights resident for the whole kernel if they fit next to >= 2 input stages
   p.w_resident = (p.n_tiles == 1 && w_tiles <= kMaxWStages &&
-                  fixed + size_t(w_tiles) * p.w_stage_bytes + 2 * size_t(p.in_stage_bytes) <= kSmemLimit) ? 1 : 0;
+                  size_t(w_tiles) * p.w_stage_bytes + 2 * size_t(p.in_stage_bytes) <= budget) ? 1 : 0;
   if (p.w_resident) {
     p.w_stages = w_tiles;
-    size_t left = kSmemLimit - fixed - size_t(w_tiles) * p.w_stage_bytes;
+    size_t left = budget - size_t(w_tiles) * p.w_stage_bytes;
     p.in_stages = int(left / p.in_stage_bytes);
   } else {
     p.in_stages = p.n_kc >= 2 ? 3 : 2;
-    size_t left = kSmemLimit - fixed - size_t(p.in_stages) * p.in_stage_bytes;
+    size_t left = budget - size_t(p.in_stages) * p.in_stage_bytes;
     p.w_stages = int(left / p.w_stage_bytes);
     if (p.w_stages > 8) p.w_stages = 8;
     MV_CHECK_ARG(p.w_stages >= 2, "mv_tapgemm: not enough shared memory for the weight ring");
   }
   if (p.in_stages > kMaxInStages) p.in_stages = kMaxInStages;
+  if (const char* e = getenv("MV_TG_IN_STAGES")) {
+    int v = atoi(e);
+    if (v >= 1 && v <= p.in_stages) p.in_stages = v;
+  }
   MV_CHECK_ARG(p.in_stages >= 1, "mv_tapgemm: not enough shared memory for one input stage");
   p.acc_stride = a->BN < 32 ? 32 : a->BN;
   p.tmem_cols = 2 * p.acc_stride;  // 64 / 128 / 256: powers of two
@@ -355,6 +566,10 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   p.out_mode = a->out_mode; p.n_valid = a->n_valid;
   MV_CHECK_ARG(a->out_mode == 0 || (a->img_stride > 0 && a->n_valid > 0), "mv_tapgemm: NCHW scatter needs the image geometry");
 
+  p.epi_flags = (a->bias ? EF_BIAS : 0u) | (a->res ? EF_RES : 0u) | (a->dact1 ? EF_DACT1 : 0u) |
+                ((a->out2 && a->out2_pre) ? EF_OUT2_PRE : 0u) | ((a->out2 && !a->out2_pre) ? EF_OUT2_POST : 0u) |
+                ((a->out2 && !a->out2_pre && a->dact2) ? EF_DACT2 : 0u) | (a->act == MV_ACT_SIGMOID ? EF_SIGMOID : 0u) |
+                (a->out_mode == 1 ? EF_NCHW : 0u);
   CUtensorMap tmA, tmW;
   const CUtensorMapSwizzle sw = CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.R), CK, sw) ||
@@ -362,18 +577,51 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
     mv::set_error("mv_tapgemm: cuTensorMapEncodeTiled failed (A %p rows %lld ld %d, W %p)", a->A, (long long)a->a_rows, a->a_ld, a->Wt);
     return MV_ERR_CUDA;
   }
-  const size_t smem = fixed + size_t(p.in_stages) * p.in_stage_bytes + size_t(p.w_stages) * p.w_stage_bytes;
+  CUtensorMap tmO = tmA, tmO2 = tmA;  // placeholders when the direct-store path is used
+  if (p.use_tma_store) {
+    bool ok = tc::make_tmap_2d_bf16(&tmO, a->out, uint64_t(a->P), uint64_t(a->N_total), uint64_t(a->out_ld) * 2, 128, 64,
+                                    CU_TENSOR_MAP_SWIZZLE_128B);
+    if (ok && a->out2)
+      ok = tc::make_tmap_2d_bf16(&tmO2, a->out2, uint64_t(a->P), uint64_t(a->N_total), uint64_t(a->out2_ld) * 2, 128, 64,
+                                 CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!ok) {
+      mv::set_error("mv_tapgemm: cuTensorMapEncodeTiled failed for the output (out %p ld %d)", a->out, a->out_ld);
+      return MV_ERR_CUDA;
+    }
+  }
+  const size_t smem = fixed + stg + size_t(p.in_stages) * p.in_stage_bytes + size_t(p.w_stages) * p.w_stage_bytes;
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set[2] = {false, false};
+
+#define MV_TG_LAUNCH(CK_, BN_, TT_)                                                                                      \
+  do {                                                                                                                   \
+    static bool attr_done = false;                                                                                       \
+    if (!attr_done) {                                                                                                    \
+      cudaFuncSetAttribute(tapgemm_kernel<CK_, BN_, TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)); \
+      attr_done = true;                                                                                                  \
+    }                                                                                                                    \
+    tapgemm_kernel<CK_, BN_, TT_><<<grid, kThreads, smem, st>>>(tmA, tmW, tmO, tmO2, p);                                 \
+  } while (0)
+#define MV_TG_T(CK_, BN_)                                  \
+  do {                                                     \
+    if (a->T == 9) MV_TG_LAUNCH(CK_, BN_, 9);              \
+    else if (a->T == 1) MV_TG_LAUNCH(CK_, BN_, 1);         \
+    else MV_TG_LAUNCH(CK_, BN_, 0);                        \
+  } while (0)
   if (CK == 64) {
-    if (!attr_set[0]) { cudaFuncSetAttribute(tapgemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)); attr_set[0] = true; }
-    tapgemm_kernel<64><<<grid, 192, smem, st>>>(tmA, tmW, p);
+    if (a->BN == 128) MV_TG_T(64, 128);
+    else if (a->BN == 64) MV_TG_T(64, 64);
+    else if (a->BN == 32) MV_TG_T(64, 32);
+    else MV_TG_T(64, 16);
   } else {
-    if (!attr_set[1]) { cudaFuncSetAttribute(tapgemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)); attr_set[1] = true; }
-    tapgemm_kernel<16><<<grid, 192, smem, st>>>(tmA, tmW, p);
+    if (a->BN == 128) MV_TG_T(16, 128);
+    else if (a->BN == 64) MV_TG_T(16, 64);
+    else if (a->BN == 32) MV_TG_T(16, 32);
+    else MV_TG_T(16, 16);
   }
+#undef MV_TG_T
+#undef MV_TG_LAUNCH
   MV_CHECK_LAUNCH("mv_tapgemm");
   return MV_OK;
 }
