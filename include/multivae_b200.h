@@ -157,6 +157,14 @@ typedef struct mv_tapgemm_args {
 } mv_tapgemm_args;
 int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 
+/* Weight gradient of a tap-GEMM layer:  dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]   (fp32, accumulating).
+ * Replaces the weight-gradient half of autograd's convolution_backward / addmm backward for the layers above
+ * (the reference reaches it through loss.backward(), trainers/base/base_trainer.py:359).
+ *   X bf16 [x_rows, x_ld] (Cin = 64 / 128 / 256 columns used), G bf16 [g_rows, g_ld] (N = 16 / 64 / 128 columns),
+ *   dW fp32 [T, N, Cin], must be initialised by the caller (zeros, or a running gradient). */
+int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
+             const int* tap_off, int64_t P, float* dW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

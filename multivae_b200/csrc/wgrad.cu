@@ -1,0 +1,266 @@
+// Weight gradient of the tap-GEMM layers (3x3 / 1x1 convolutions and Linear) on tcgen05:
+//
+//   dW[t, n, c] += sum_p  G[p, n] * X[p + off_t, c]          (fp32 accumulate, bf16 operands)
+//
+// The reduction runs over flat pixels p, i.e. over the ROWS of both activation matrices, so both UMMA
+// operands are "MN-major": the contiguous 128-byte row of 64 channels is the M (or N) direction and K
+// walks down the rows.  Exactly the same TMA boxes as the forward kernel are used (X window of
+// 128 + halo rows per 64-channel chunk, SWIZZLE_128B); a filter tap is again a row shift of the
+// descriptor start address.  UMMA M is always 128 = two 64-channel blocks whose distance is the
+// descriptor's leading-byte-offset: either the next 64-channel chunk buffer (Cin >= 128) or — for
+// Cin = 64 — the SAME buffer shifted by the row distance to another tap, so two taps share one MMA.
+// Every (tap pair | chunk pair) owns one fp32 accumulator of N columns in TMEM for the whole kernel;
+// a CTA walks its share of the 128-pixel K tiles, then adds its partial dW into global memory with
+// fp32 reductions.  Layers whose dW exceeds 512 TMEM columns are split into passes (grid.y).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace mv {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kWgMaxAcc = 16;   // accumulators per pass (16 x 32 columns = 512)
+constexpr int kWgMaxStages = 4;
+constexpr int kWgThreads = 192;
+
+struct WgAcc {
+  int row_off;      // window row of block 0 (halo_lo + tap offset)
+  int chunk;        // 64-channel chunk buffer of block 0
+  uint32_t lbo;     // byte distance from block 0 to block 1 inside the stage
+  int t0, c0;       // output coordinates of block 0: tap, channel chunk
+  int t1, c1;       // ... of block 1 (t1 < 0: block 1 is padding, not stored)
+};
+
+struct WgradParams {
+  int n_ktiles, kt_per_cta_stride;
+  int n_chunks;                 // Cin / 64
+  int N, Ncols;                 // G columns, TMEM column stride per accumulator
+  int halo_lo, R;
+  uint32_t x_chunk_bytes;       // bytes of one chunk buffer (R rows x 128 B, 1 KB aligned)
+  uint32_t g_bytes, g_row_bytes, g_box_cols;
+  uint32_t stage_bytes;
+  int stages;
+  int n_acc[8];                 // accumulators per pass
+  int acc_begin[8];
+  WgAcc acc[48];
+  int Cin, N_total_out;         // dW is [T][N_total_out][Cin] fp32
+  float* dW;
+  int tmem_cols;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgMaxStages;
+  uint64_t* done = empty + kWgMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pass = blockIdx.y;
+  const int nacc = p.n_acc[pass];
+  const WgAcc* accs = p.acc + p.acc_begin[pass];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(done, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmX);
+    tc::prefetch_tmap(&tmG);
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, p.tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t g_off = uint32_t(p.n_chunks) * p.x_chunk_bytes;  // G tile follows the X chunk buffers in a stage
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    int s = 0, ph = 0;
+    for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x) {
+      tc::mbar_wait(&empty[s], ph ^ 1);
+      if (tc::elect_one()) {
+        uint8_t* st = smem + size_t(s) * p.stage_bytes;
+        tc::mbar_expect_tx(&full[s], uint32_t(p.n_chunks) * uint32_t(p.R) * 128u + p.g_bytes);
+        for (int c = 0; c < p.n_chunks; ++c) tc::tma_load_2d(st + size_t(c) * p.x_chunk_bytes, &tmX, &full[s], c * 64, kt * 128 - p.halo_lo);
+        const int nbox = p.N / int(p.g_box_cols);
+        for (int b = 0; b < nbox; ++b)
+          tc::tma_load_2d(st + g_off + size_t(b) * 128 * p.g_row_bytes, &tmG, &full[s], b * int(p.g_box_cols), kt * 128);
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = tc::idesc_bf16(128, uint32_t(p.N), 1, 1);
+    const uint32_t g_sw = p.g_row_bytes == 128 ? tc::SW_128 : tc::SW_32;
+    const uint32_t g_kstep = 16 * p.g_row_bytes;                       // 16 pixel rows per UMMA K step
+    // G: blocks of 64 columns are separate boxes (128 rows x 128 B) -> LBO = 16 KB; 8-row groups -> SBO
+    const uint64_t g_desc0 = tc::smem_desc(0, 128 * p.g_row_bytes, 8 * p.g_row_bytes, g_sw);
+    int s = 0, ph = 0, it = 0;
+    for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x, ++it) {
+      tc::mbar_wait(&full[s], ph);
+      tc::fence_after_sync();
+      const uint32_t st = tc::smem_u32(smem + size_t(s) * p.stage_bytes);
+      if (tc::elect_one()) {
+        for (int a = 0; a < nacc; ++a) {
+          const WgAcc& A = accs[a];
+          const uint32_t x0 = st + uint32_t(A.chunk) * p.x_chunk_bytes + uint32_t(A.row_off) * 128u;
+          const uint64_t xd0 = tc::smem_desc(0, A.lbo, 1024, tc::SW_128);
+          const uint32_t tm = tmem_base + uint32_t(a * p.Ncols);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t xd = xd0 | uint64_t(((x0 + uint32_t(k) * 2048u) & 0x3FFFFu) >> 4);
+            const uint64_t gd = g_desc0 | uint64_t(((st + g_off + uint32_t(k) * g_kstep) & 0x3FFFFu) >> 4);
+            tc::umma_bf16(tm, xd, gd, idesc, (it | k) != 0);
+          }
+        }
+        tc::umma_commit(&empty[s]);
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    if (tc::elect_one()) tc::umma_commit(done);
+    __syncwarp();
+  } else {
+    // ================= epilogue: partial dW -> global fp32 reductions =================
+    const int q = warp & 3;
+    tc::mbar_wait(done, 0);
+    tc::fence_after_sync();
+    const bool any = blockIdx.x < p.n_ktiles;   // a CTA without K tiles has nothing in TMEM
+    const int m = q * 32 + lane;                // accumulator row = (block, channel)
+    const int blk = m >> 6, ch = m & 63;
+    for (int a = 0; a < nacc; ++a) {
+      const WgAcc& A = accs[a];
+      const int t = blk == 0 ? A.t0 : A.t1, cc = blk == 0 ? A.c0 : A.c1;
+      for (int n0 = 0; n0 < p.N; n0 += 16) {
+        uint32_t v[16];
+        tc::tmem_ld_32x16(tmem_base + uint32_t(a * p.Ncols + n0) + (uint32_t(q * 32) << 16), v);
+        tc::tmem_ld_wait();
+        if (any && t >= 0) {
+          float* dst = p.dW + (size_t(t) * p.N_total_out + n0) * p.Cin + cc * 64 + ch;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + size_t(j) * p.Cin, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int num_sms();
+constexpr size_t kWgSmemLimit = 232448;
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
+                        int T, const int* tap_off, int64_t P, float* dW, void* stream) {
+  MV_CHECK_ARG(X && G && dW && tap_off, "mv_wgrad: null pointer");
+  MV_CHECK_ARG(Cin % 64 == 0 && Cin >= 64 && Cin <= 256, "mv_wgrad: Cin must be 64/128/192/256, got %d", Cin);
+  MV_CHECK_ARG(N == 16 || N == 64 || N == 128, "mv_wgrad: N must be 16, 64 or 128, got %d", N);
+  MV_CHECK_ARG(T >= 1 && T <= 9, "mv_wgrad: 1 <= taps <= 9");
+  MV_CHECK_ARG(x_ld % 8 == 0 && g_ld % 8 == 0, "mv_wgrad: leading dimensions must be multiples of 8");
+  WgradParams p{};
+  int lo = 0, hi = 0;
+  for (int t = 0; t < T; ++t) {
+    lo = tap_off[t] < lo ? tap_off[t] : lo;
+    hi = tap_off[t] > hi ? tap_off[t] : hi;
+  }
+  p.halo_lo = -lo;
+  p.R = 128 - lo + hi;
+  MV_CHECK_ARG(p.R <= 256, "mv_wgrad: tap offsets span %d rows", p.R);
+  p.n_chunks = Cin / 64;
+  p.N = N;
+  p.Ncols = N < 32 ? 32 : N;
+  p.Cin = Cin;
+  p.N_total_out = N;
+  p.dW = dW;
+  p.n_ktiles = int((P + 127) / 128);
+  // +8 rows of slack: the padding block of an odd tap count may read a few rows past the window
+  p.x_chunk_bytes = (uint32_t(p.R + 8) * 128u + 1023u) & ~1023u;
+  p.g_row_bytes = N >= 64 ? 128u : uint32_t(N) * 2u;
+  p.g_box_cols = N >= 64 ? 64u : uint32_t(N);
+  p.g_bytes = 128u * uint32_t(N) * 2u;
+  p.stage_bytes = uint32_t(p.n_chunks) * p.x_chunk_bytes + ((p.g_bytes + 1023u) & ~1023u);
+  // accumulator table
+  int na = 0;
+  if (p.n_chunks == 1) {
+    // pair taps: block 1 is the same buffer shifted to another tap (taps sorted by offset so that LBO > 0)
+    int order[9];
+    for (int t = 0; t < T; ++t) order[t] = t;
+    for (int i = 0; i < T; ++i)
+      for (int j = i + 1; j < T; ++j)
+        if (tap_off[order[j]] < tap_off[order[i]]) { int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    for (int i = 0; i < T;) {
+      WgAcc& A = p.acc[na++];
+      A.row_off = p.halo_lo + tap_off[order[i]];
+      A.chunk = 0;
+      A.t0 = order[i]; A.c0 = 0;
+      if (i + 1 < T && tap_off[order[i + 1]] > tap_off[order[i]]) {
+        A.lbo = uint32_t(tap_off[order[i + 1]] - tap_off[order[i]]) * 128u;
+        A.t1 = order[i + 1]; A.c1 = 0;
+        i += 2;
+      } else {
+        A.lbo = 128u;  // padding block: one row further, never stored
+        A.t1 = -1; A.c1 = 0;
+        i += 1;
+      }
+    }
+  } else {
+    MV_CHECK_ARG(p.n_chunks % 2 == 0, "mv_wgrad: Cin must be 64 or a multiple of 128");
+    for (int t = 0; t < T; ++t)
+      for (int c = 0; c < p.n_chunks; c += 2) {
+        WgAcc& A = p.acc[na++];
+        A.row_off = p.halo_lo + tap_off[t];
+        A.chunk = c;
+        A.lbo = p.x_chunk_bytes;
+        A.t0 = t; A.c0 = c; A.t1 = t; A.c1 = c + 1;
+      }
+  }
+  const int per_pass_max = 512 / p.Ncols > kWgMaxAcc ? kWgMaxAcc : 512 / p.Ncols;
+  const int passes = (na + per_pass_max - 1) / per_pass_max;
+  MV_CHECK_ARG(passes <= 8, "mv_wgrad: too many passes (%d)", passes);
+  for (int i = 0, b = 0; i < passes; ++i) {
+    const int cnt = (na - b + (passes - i) - 1) / (passes - i);  // balanced split
+    p.acc_begin[i] = b;
+    p.n_acc[i] = cnt;
+    b += cnt;
+  }
+  int max_acc = 0;
+  for (int i = 0; i < passes; ++i) max_acc = p.n_acc[i] > max_acc ? p.n_acc[i] : max_acc;
+  int cols = max_acc * p.Ncols;
+  p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+  const size_t fixed = 2048 + (2 * kWgMaxStages + 1) * 8 + 16;
+  p.stages = int((kWgSmemLimit - fixed) / p.stage_bytes);
+  if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
+  MV_CHECK_ARG(p.stages >= 1, "mv_wgrad: stage does not fit shared memory");
+  CUtensorMap tmX, tmG;
+  const bool ok = tc::make_tmap_2d_bf16(&tmX, X, uint64_t(x_rows), uint64_t(Cin), uint64_t(x_ld) * 2, uint32_t(p.R), 64,
+                                        CU_TENSOR_MAP_SWIZZLE_128B) &&
+                  tc::make_tmap_2d_bf16(&tmG, G, uint64_t(g_rows), uint64_t(N), uint64_t(g_ld) * 2, 128, p.g_box_cols,
+                                        N >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
+  if (!ok) {
+    mv::set_error("mv_wgrad: cuTensorMapEncodeTiled failed");
+    return MV_ERR_CUDA;
+  }
+  int gx = num_sms() / passes;
+  if (gx > p.n_ktiles) gx = p.n_ktiles;
+  if (gx < 1) gx = 1;
+  const size_t smem = fixed + size_t(p.stages) * p.stage_bytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWgSmemLimit));
+    attr_done = true;
+  }
+  wgrad_kernel<<<dim3(gx, passes), kWgThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmG, p);
+  MV_CHECK_LAUNCH("mv_wgrad");
+  return MV_OK;
+}

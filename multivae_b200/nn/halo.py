@@ -89,3 +89,25 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
     kw = {} if tag is None else {"tag": tag}
     C.check(lib.mv_tapgemm(a, C.stream(), **kw), "mv_tapgemm")
     return out
+
+
+def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None):
+    """dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]  (fp32 [T, N, Cin]); see mv_wgrad."""
+    import ctypes
+    lib = C.lib()
+    Cin = X.shape[1] if Cin is None else Cin
+    N = G.shape[1] if N is None else N
+    assert X.dtype == torch.bfloat16 and G.dtype == torch.bfloat16 and X.stride(1) == 1 and G.stride(1) == 1
+    if dW is None:
+        dW = torch.zeros(T, N, Cin, device=X.device, dtype=torch.float32)
+    offs = (ctypes.c_int32 * 9)(*[int(o) for o in tap_off])
+    kw = {} if tag is None else {"tag": tag}
+    C.check(lib.mv_wgrad(X.data_ptr(), X.shape[0], X.stride(0), Cin, G.data_ptr(), G.shape[0], G.stride(0), N, T, offs, P,
+                         dW.data_ptr(), C.stream(), **kw), "mv_wgrad")
+    return dW
+
+
+def unpack_conv_wgrad(dW, kh, kw):
+    """[kh*kw, N, C] fp32 -> torch Conv2d weight-gradient layout [N, C, kh, kw]."""
+    t, n, c = dW.shape
+    return dW.view(kh, kw, n, c).permute(2, 3, 0, 1)
