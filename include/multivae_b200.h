@@ -165,6 +165,18 @@ int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
              const int* tap_off, int64_t P, float* dW, void* stream);
 
+/* HBM-bound helpers of the shared-halo layout (all tensors bf16 unless noted):
+ *   mv_upsample2x_fwd  nn.Upsample(scale_factor=2) (models/nn/mmnist.py:345): in (H x W, C ch) -> out (2H x 2W, C ch)
+ *   mv_upsample2x_bwd  its gradient: g_in = sum of the 2x2 children of g_out; optional g_pre = alpha*g_in*lrelu'(act)
+ *                      (the residual-branch gradient of the ResnetBlock below, mmnist.py:243-246)
+ *   mv_head_grad_pack  dense NCHW gradient [n_img, ch, H, W] times lrelu'(y_out) -> halo matrix [P, 16]
+ *   mv_colsum          out[n] += sum_p G[p, n] (bias gradients; out fp32) */
+int mv_upsample2x_fwd(const void* in, void* out, int n_img, int H, int W, int C, void* stream);
+int mv_upsample2x_bwd(const void* g_out, const void* act, void* g_in, void* g_pre, int n_img, int H, int W, int C, float alpha,
+                      float slope, void* stream);
+int mv_head_grad_pack(const void* g, const void* y_out, void* out, int n_img, int H, int W, int ch, float slope, void* stream);
+int mv_colsum(const void* G, int64_t P, int ld, int N, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

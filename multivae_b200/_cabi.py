@@ -51,6 +51,10 @@ _PROTOS = {
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "mv_tapgemm": [ctypes.POINTER(TapGemmArgs), c_void_p],
+    "mv_upsample2x_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mv_upsample2x_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
+    "mv_head_grad_pack": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "mv_colsum": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
     "mv_wgrad": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                  c_int64, c_void_p, c_void_p],
     "mv_poe_bwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +

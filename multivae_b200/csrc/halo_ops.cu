@@ -1,0 +1,184 @@
+// HBM-bound helpers of the shared-halo NHWC layout (see include/multivae_b200.h): nearest-neighbour
+// upsampling forward / backward (nn.Upsample(scale_factor=2), models/nn/mmnist.py:345), packing of the image-head
+// gradient, and column sums (bias gradients).  One 16-byte vector (8 bf16 channels) per thread, coalesced.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mv {
+
+using bf16 = __nv_bfloat16;
+
+struct HaloGeom {
+  int n_img, H, W, Wp, S, P;
+};
+static HaloGeom make_geom(int n_img, int H, int W) {
+  HaloGeom g;
+  g.n_img = n_img; g.H = H; g.W = W; g.Wp = W + 1; g.S = (H + 1) * (W + 1); g.P = n_img * g.S + g.Wp;
+  return g;
+}
+// row -> (img, y in 1..H, x in 0..W-1) or invalid
+__device__ __forceinline__ bool decode_row(const HaloGeom& g, int row, int& img, int& y, int& x) {
+  img = row / g.S;
+  const int r = row - img * g.S;
+  y = r / g.Wp;
+  x = r - y * g.Wp;
+  return row < g.P && img < g.n_img && y >= 1 && x < g.W;
+}
+
+__device__ __forceinline__ void unpack8f(const uint4& v, float* f) {
+  f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+  f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8f(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// out (2H x 2W) [Pout, C] <- in (H x W) [Pin, C]
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, HaloGeom gi,
+                                                            HaloGeom go, int C) {
+  const int vec_per_row = C >> 3;
+  const int64_t total = int64_t(go.P) * vec_per_row;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int img, y, x;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (decode_row(go, row, img, y, x)) {
+      const int src = img * gi.S + (1 + ((y - 1) >> 1)) * gi.Wp + (x >> 1);
+      val = ld_stream(in + int64_t(src) * C + v * 8);
+    }
+    st_stream(out + int64_t(row) * C + v * 8, val);
+  }
+}
+
+// g_in (H x W) = sum of the 2x2 children of g_out (2H x 2W); optionally g_pre = alpha * g_in * lrelu'(act)
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ act,
+                                                            bf16* __restrict__ g_in, bf16* __restrict__ g_pre, HaloGeom gi,
+                                                            HaloGeom go, int C, float alpha, float slope) {
+  const int vec_per_row = C >> 3;
+  const int64_t total = int64_t(gi.P) * vec_per_row;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int img, y, x;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (decode_row(gi, row, img, y, x)) {
+      const int base = img * go.S + (1 + 2 * (y - 1)) * go.Wp + 2 * x;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float f[8];
+          unpack8f(ld_stream(g_out + int64_t(base + dy * go.Wp + dx) * C + v * 8), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s[e] += f[e];
+        }
+      if (g_pre) {
+        float a[8];
+        unpack8f(ld_stream(act + int64_t(row) * C + v * 8), a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pre[e] = alpha * s[e] * (a[e] > 0.f ? 1.f : slope);
+      }
+    }
+    st_stream(g_in + int64_t(row) * C + v * 8, pack8f(s));
+    if (g_pre) st_stream(g_pre + int64_t(row) * C + v * 8, pack8f(pre));
+  }
+}
+
+// image-head gradient: g [n_img, ch, H, W] (dense NCHW bf16) * lrelu'(y) -> halo matrix [P, 16] (channels >= ch zero)
+__global__ void __launch_bounds__(256) head_grad_pack_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y_out,
+                                                            bf16* __restrict__ out, HaloGeom gg, int ch, float slope) {
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < gg.P; row += gridDim.x * blockDim.x) {
+    int img, y, x;
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = 0.f;
+    if (decode_row(gg, row, img, y, x)) {
+      for (int c = 0; c < ch; ++c) {
+        const int64_t idx = ((int64_t(img) * ch + c) * gg.H + (y - 1)) * gg.W + x;
+        const float gv = __bfloat162float(g[idx]);
+        f[c] = y_out ? gv * (__bfloat162float(y_out[idx]) > 0.f ? 1.f : slope) : gv;
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + int64_t(row) * 16);
+    o[0] = pack8f(f);
+    o[1] = pack8f(f + 8);
+  }
+}
+
+// out[n] += sum_p G[p, n]   (N <= 256, N % 8 == 0)
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ G, int64_t P, int ld, int N, float* __restrict__ out) {
+  __shared__ float red[256 * 8];
+  const int groups = N >> 3;                 // 16-byte column groups
+  const int lanes = 256 / groups;            // row lanes per block
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes) {
+    for (int64_t row = int64_t(blockIdx.x) * lanes + rl; row < P; row += int64_t(gridDim.x) * lanes) {
+      float f[8];
+      unpack8f(ld_stream(G + row * ld + cg * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int g2 = threadIdx.x >> 3, e = threadIdx.x & 7;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(l * groups + g2) * 8 + e];
+    atomicAdd(out + threadIdx.x, s);
+  }
+}
+
+int num_sms();
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_upsample2x_fwd(const void* in, void* out, int n_img, int H, int W, int C, void* stream) {
+  MV_CHECK_ARG(in && out && n_img > 0 && H > 0 && W > 0 && C % 8 == 0, "mv_upsample2x_fwd: bad arguments");
+  const HaloGeom gi = make_geom(n_img, H, W), go = make_geom(n_img, 2 * H, 2 * W);
+  const int64_t total = int64_t(go.P) * (C / 8);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  upsample2x_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(in), static_cast<bf16*>(out),
+                                                                               gi, go, C);
+  MV_CHECK_LAUNCH("mv_upsample2x_fwd");
+  return MV_OK;
+}
+
+extern "C" int mv_upsample2x_bwd(const void* g_out, const void* act, void* g_in, void* g_pre, int n_img, int H, int W, int C,
+                                 float alpha, float slope, void* stream) {
+  MV_CHECK_ARG(g_out && g_in && n_img > 0 && H > 0 && W > 0 && C % 8 == 0, "mv_upsample2x_bwd: bad arguments");
+  MV_CHECK_ARG(!g_pre || act, "mv_upsample2x_bwd: g_pre needs the saved activation");
+  const HaloGeom gi = make_geom(n_img, H, W), go = make_geom(n_img, 2 * H, 2 * W);
+  const int64_t total = int64_t(gi.P) * (C / 8);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  upsample2x_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(g_out), static_cast<const bf16*>(act), static_cast<bf16*>(g_in), static_cast<bf16*>(g_pre), gi, go, C,
+      alpha, slope);
+  MV_CHECK_LAUNCH("mv_upsample2x_bwd");
+  return MV_OK;
+}
+
+extern "C" int mv_head_grad_pack(const void* g, const void* y_out, void* out, int n_img, int H, int W, int ch, float slope,
+                                 void* stream) {
+  MV_CHECK_ARG(g && out && n_img > 0 && ch >= 1 && ch <= 16, "mv_head_grad_pack: bad arguments");
+  const HaloGeom gg = make_geom(n_img, H, W);
+  const int blocks = std::min((gg.P + 255) / 256, num_sms() * 16);
+  head_grad_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(y_out),
+                                                                               static_cast<bf16*>(out), gg, ch, slope);
+  MV_CHECK_LAUNCH("mv_head_grad_pack");
+  return MV_OK;
+}
+
+extern "C" int mv_colsum(const void* G, int64_t P, int ld, int N, float* out, void* stream) {
+  MV_CHECK_ARG(G && out && P > 0 && N % 8 == 0 && N >= 8 && N <= 256 && ld % 8 == 0, "mv_colsum: bad arguments (N=%d)", N);
+  MV_CHECK_ARG(256 % (N / 8) == 0, "mv_colsum: N/8 must divide 256");
+  const int lanes = 256 / (N / 8);
+  const int blocks = int(std::min<int64_t>((P + lanes - 1) / lanes, int64_t(num_sms()) * 8));
+  colsum_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(G), P, ld, N, out);
+  MV_CHECK_LAUNCH("mv_colsum");
+  return MV_OK;
+}
