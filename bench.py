@@ -225,12 +225,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps   # host enqueue time per step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -254,6 +258,7 @@ def run_gpu(args):
         sampler.start()
     n0 = _cabi.launch_count()
     ms = timed(step_resident, args.steps)
+    host_enqueue_ms = host_ms[0]
     launches = _cabi.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times for the roofline (separate short pass so the events do not perturb `value`)
@@ -304,7 +309,7 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": M * B * D * 4, "d2h_bytes_per_step": 4, "last_loss": last.get("loss")},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": roof,
         "step_fraction_of_tensor_ceiling": value / world / (peaks["bf16_tflops_sustained"] * 1e3 / GFLOP_PER_SAMPLE),
         "elbo_rel_err": rel,
@@ -340,6 +345,9 @@ def roofline_from(summary, prof_ms, B):
         achieved = info["work"] / per_launch_s / 1e12
         peak, unit = peaks["bf16_tflops_sustained"], "TFLOP/s"
     shares = {k: round(v[1] / prof_ms, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1][1])[:8]}
+    if os.environ.get("MV_BENCH_DUMP"):
+        with open(os.environ["MV_BENCH_DUMP"], "w") as f:
+            json.dump({"prof_ms": prof_ms, "kernels": {k: {"calls": v[0], "ms": v[1]} for k, v in summary.items()}}, f, indent=1)
     return {"kernel": name, "bound": info["bound"], "achieved": achieved, "peak": peak, "unit": unit,
             "frac": achieved / peak, "peak_source": peaks["source"], "traffic": info.get("traffic"),
             "algorithmic_work_per_launch": info["work"], "avg_launch_us": per_launch_s * 1e6, "launches": calls,

@@ -62,6 +62,8 @@ struct TapGemmParams {
   int use_tma_store;       // outputs leave through a swizzled shared-memory staging tile + TMA store
   uint32_t stage_out_bytes; // bytes of one output's staging area (BN/64 boxes of 128 rows x 128 B)
   uint32_t epi_flags;       // EF_* bits describing which epilogue terms are present
+  int side_tma;             // the primary side input (res, else dact1, else dact2) arrives as TMA tiles in shared memory
+  int side_kind;            // 0 res, 1 dact1, 2 dact2
 };
 
 
@@ -98,29 +100,21 @@ struct RowCtx {
   int img, y, x;
 };
 
-// One chunk of CW accumulator columns of one row: side inputs prefetched by load_side.
-template <int CW>
-struct Side {
-  uint4 a[CW / 8], b[CW / 8];  // a: residual or dact1 source; b: dact2 source
-};
-template <int CW, uint32_t F>
-__device__ __forceinline__ void load_side(Side<CW>& s, const TapGemmParams& p, const RowCtx& r, int n) {
-  if (!r.valid) return;
-  if (has<F>(p, EF_RES)) {
-#pragma unroll
-    for (int g = 0; g < CW / 8; ++g) s.a[g] = ldg16(p.res + size_t(r.row) * p.res_ld + n + g * 8);
-  } else if (has<F>(p, EF_DACT1)) {
-#pragma unroll
-    for (int g = 0; g < CW / 8; ++g) s.a[g] = ldg16(p.dact1 + size_t(r.row) * p.dact1_ld + n + g * 8);
-  }
-  if (has<F>(p, EF_DACT2)) {
-#pragma unroll
-    for (int g = 0; g < CW / 8; ++g) s.b[g] = ldg16(p.dact2 + size_t(r.row) * p.dact2_ld + n + g * 8);
-  }
+// Side inputs (residual / activation-derivative sources).  The primary one arrives as TMA tiles in shared
+// memory with the same swizzled layout as the output staging tile; others are read from global memory.
+__device__ __forceinline__ uint32_t tile_off(int col, int rloc) {
+  return uint32_t(col >> 6) * 16384u + uint32_t(rloc) * 128u + uint32_t((((col & 63) >> 3) ^ (rloc & 7)) << 4);
+}
+__device__ __forceinline__ uint4 side_vec(const TapGemmParams& p, const uint8_t* side_tile, int kind, int col, int n,
+                                          const RowCtx& r) {
+  if (side_tile && p.side_kind == kind) return *reinterpret_cast<const uint4*>(side_tile + tile_off(col, r.rloc));
+  const bf16* base = kind == 0 ? p.res + size_t(r.row) * p.res_ld
+                               : (kind == 1 ? p.dact1 + size_t(r.row) * p.dact1_ld : p.dact2 + size_t(r.row) * p.dact2_ld);
+  return ldg16(base + n);
 }
 
 template <int CW, uint32_t F>
-__device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t* v, const Side<CW>& s, const float* s_bias,
+__device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t* v, const uint8_t* side_tile, const float* s_bias,
                                           int cb /*column within the tile*/, int n /*global column*/, const RowCtx& r,
                                           float neg, uint8_t* st_out, uint8_t* st_out2) {
 #pragma unroll
@@ -143,14 +137,9 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[e] = 1.f / (1.f + __expf(-yv[e]));
       }
-      if (has<F>(p, EF_DACT1) && !has<F>(p, EF_RES)) {
+      if (has<F>(p, EF_DACT1)) {
         float d[8];
-        unpack8(s.a[g], d);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
-      } else if (has<F>(p, EF_DACT1)) {  // both a residual and dact1: dact1 is fetched late (rare)
-        float d[8];
-        unpack8(ldg16(p.dact1 + size_t(r.row) * p.dact1_ld + n + g * 8), d);
+        unpack8(side_vec(p, side_tile, 1, cb + g * 8, n + g * 8, r), d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
       }
@@ -160,7 +149,7 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
       }
       if (has<F>(p, EF_RES)) {
         float rr[8];
-        unpack8(s.a[g], rr);
+        unpack8(side_vec(p, side_tile, 0, cb + g * 8, n + g * 8, r), rr);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(p.alpha, yv[e], rr[e]);
       } else {
@@ -172,7 +161,7 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
         for (int e = 0; e < 8; ++e) o2[e] = p.alpha2 * o[e];
         if (has<F>(p, EF_DACT2)) {
           float d[8];
-          unpack8(s.b[g], d);
+          unpack8(side_vec(p, side_tile, 2, cb + g * 8, n + g * 8, r), d);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o2[e] *= d[e] > 0.f ? 1.f : p.slope2;
         }
@@ -194,8 +183,7 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
       }
     } else if (st_out) {
       // staging tile: 64-column boxes of 128 rows x 128 B, SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7))
-      const int col = cb + g * 8;
-      const uint32_t off = uint32_t(col >> 6) * 16384u + uint32_t(r.rloc) * 128u + uint32_t((((col & 63) >> 3) ^ (r.rloc & 7)) << 4);
+      const uint32_t off = tile_off(cb + g * 8, r.rloc);
       *reinterpret_cast<uint4*>(st_out + off) = pack8(o);
       if (two) *reinterpret_cast<uint4*>(st_out2 + off) = pack8(o2);
     } else if (r.row < p.P) {
@@ -209,13 +197,12 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
 template <int BN, uint32_t F>
 __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half,
                                          uint32_t taddr, uint64_t* full_bar, uint32_t full_parity, float neg, uint8_t* stg_base,
-                                         int et) {
+                                         int et, const uint8_t* side_tile, uint64_t* side_full, uint32_t side_parity) {
   constexpr int CW = BN >= 32 ? 32 : 16;
   constexpr int NCH = BN / CW;
-  Side<CW> cur, nxt;
-  if (half < NCH) load_side<CW, F>(cur, p, r, n0 + half * CW);
   tc::mbar_wait(full_bar, full_parity);
   tc::fence_after_sync();
+  if (side_tile) tc::mbar_wait(side_full, side_parity);
   uint8_t* st_out = nullptr;
   uint8_t* st_out2 = nullptr;
   if (p.use_tma_store) {
@@ -227,13 +214,11 @@ __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r
   }
 #pragma unroll
   for (int ch = half; ch < NCH; ch += 2) {
-    if (ch + 2 < NCH) load_side<CW, F>(nxt, p, r, n0 + (ch + 2) * CW);
     uint32_t v[32];
     if (CW == 32) tc::tmem_ld_32x32(taddr + ch * CW, v);
     else tc::tmem_ld_32x16(taddr + ch * CW, v);
     tc::tmem_ld_wait();
-    epi_apply<CW, F>(p, v, cur, s_bias, ch * CW, n0 + ch * CW, r, neg, st_out, st_out2);
-    if (ch + 2 < NCH) cur = nxt;
+    epi_apply<CW, F>(p, v, side_tile, s_bias, ch * CW, n0 + ch * CW, r, neg, st_out, st_out2);
   }
 }
 
@@ -241,14 +226,16 @@ __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r
 template <int BN>
 __device__ __noinline__ void epi_tile_generic(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half,
                                               uint32_t taddr, uint64_t* full_bar, uint32_t full_parity, float neg,
-                                              uint8_t* stg_base, int et) {
-  epi_tile<BN, EF_GENERIC>(p, r, s_bias, n0, half, taddr, full_bar, full_parity, neg, stg_base, et);
+                                              uint8_t* stg_base, int et, const uint8_t* side_tile, uint64_t* side_full,
+                                              uint32_t side_parity) {
+  epi_tile<BN, EF_GENERIC>(p, r, s_bias, n0, half, taddr, full_bar, full_parity, neg, stg_base, et, side_tile, side_full, side_parity);
 }
 
 template <int CK, int BN, int TT>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const TapGemmParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+               const __grid_constant__ CUtensorMap tmS, const TapGemmParams p) {
   constexpr uint32_t ROWB = CK * 2;            // bytes per shared-memory row (one pixel, CK channels)
   constexpr int KSTEPS = CK / 16;              // UMMA K = 16 for bf16
   constexpr uint32_t SWZ = CK == 64 ? tc::SW_128 : tc::SW_32;
@@ -258,14 +245,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* in_base = smem;
   uint8_t* w_base = smem + size_t(p.in_stages) * p.in_stage_bytes;
   uint8_t* stg_base = w_base + ((size_t(p.w_stages) * p.w_stage_bytes + 1023) & ~size_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (p.use_tma_store ? 2 * size_t(p.stage_out_bytes) : 0));
+  uint8_t* side_base = stg_base + (p.use_tma_store ? 2 * size_t(p.stage_out_bytes) : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_base + (p.side_tma ? 2 * size_t(p.stage_out_bytes) : 0));
   uint64_t* in_full = bars;
   uint64_t* in_empty = in_full + kMaxInStages;
   uint64_t* w_full = in_empty + kMaxInStages;
   uint64_t* w_empty = w_full + kMaxWStages;
   uint64_t* tm_full = w_empty + kMaxWStages;
   uint64_t* tm_empty = tm_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+  uint64_t* side_full = tm_empty + 2;
+  uint64_t* side_empty = side_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   const int T = TT > 0 ? TT : p.T;
 
@@ -274,6 +264,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], kEpiWarps); }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
@@ -300,8 +291,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
     }
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+    int pit = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++pit) {
       const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+      if (p.side_tma) {
+        // side-input tile of this output tile (consumed by the epilogue two tiles behind the producer at most)
+        const int ss = pit & 1, sph = (pit >> 1) & 1;
+        tc::mbar_wait(&side_empty[ss], sph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&side_full[ss], p.stage_out_bytes);
+#pragma unroll
+          for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b)
+            tc::tma_load_2d(side_base + size_t(ss) * p.stage_out_bytes + b * 16384, &tmS, &side_full[ss], n0 + b * 64, p0);
+        }
+        __syncwarp();
+      }
       for (int kc = 0; kc < p.n_kc; ++kc) {
         tc::mbar_wait(&in_empty[is], iph ^ 1);
         if (tc::elect_one()) {
@@ -441,7 +445,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
       const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
-#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et)
+      const uint8_t* side_tile = p.side_tma ? side_base + size_t(acc) * p.stage_out_bytes : nullptr;
+#define MV_EPI(FLAGS)                                                                                                 \
+  epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et, side_tile, \
+                        &side_full[acc], uint32_t(acc_ph))
       switch (p.epi_flags) {
         case 0u: MV_EPI(0u); break;
         case EF_BIAS: MV_EPI(EF_BIAS); break;
@@ -450,13 +457,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         case EF_RES: MV_EPI(EF_RES); break;
         case EF_OUT2_POST | EF_DACT2: MV_EPI(EF_OUT2_POST | EF_DACT2); break;
         case EF_BIAS | EF_NCHW: MV_EPI(EF_BIAS | EF_NCHW); break;
-        default: epi_tile_generic<BN>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et); break;
+        default:
+          epi_tile_generic<BN>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et, side_tile,
+                               &side_full[acc], uint32_t(acc_ph));
+          break;
       }
 #undef MV_EPI
-      // accumulator drained: hand the TMEM buffer back to the MMA warp before the stores go out
+      // accumulator drained: hand the TMEM buffer (and the side tile) back before the stores go out
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
+      if (lane == 0) {
+        tc::mbar_arrive(&tm_empty[acc]);
+        if (p.side_tma) tc::mbar_arrive(&side_empty[acc]);
+      }
       if (p.use_tma_store) {
         tc::fence_proxy_async();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -528,11 +541,15 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
     uint32_t v = uint32_t(atoi(e));
     if (v >= p.in_stage_bytes) p.in_stage_bytes = v & ~1023u;
   }
-  const size_t fixed = 2048 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 4) * 8 + 16 + 128 * 4;
+  const size_t fixed = 2048 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 8) * 8 + 16 + 128 * 4;
   const int w_tiles = p.T * p.n_kc;
   p.use_tma_store = (a->out_mode == 0 && a->BN >= 64 && a->out_ld % 8 == 0 && (!a->out2 || a->out2_ld % 8 == 0)) ? 1 : 0;
   p.stage_out_bytes = uint32_t(a->BN / 64) * 16384u;
-  const size_t stg = p.use_tma_store ? 2 * size_t(p.stage_out_bytes) + 1024 : 0;
+  const void* side_ptr = a->res ? a->res : (a->dact1 ? a->dact1 : ((a->out2 && !a->out2_pre) ? a->dact2 : nullptr));
+  const int side_ld = a->res ? a->res_ld : (a->dact1 ? a->dact1_ld : a->dact2_ld);
+  p.side_kind = a->res ? 0 : (a->dact1 ? 1 : 2);
+  p.side_tma = (side_ptr && a->BN >= 64 && side_ld % 8 == 0) ? 1 : 0;
+  const size_t stg = (p.use_tma_store ? 2 * size_t(p.stage_out_bytes) + 1024 : 0) + (p.side_tma ? 2 * size_t(p.stage_out_bytes) : 0);
   const size_t budget = kSmemLimit - fixed - stg;
   // weights resident for the whole kernel if they fit next to >= 2 input stages
   p.w_resident = (p.n_tiles == 1 && w_tiles <= kMaxWStages &&
@@ -589,6 +606,13 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
       return MV_ERR_CUDA;
     }
   }
+  CUtensorMap tmS = tmA;
+  if (p.side_tma &&
+      !tc::make_tmap_2d_bf16(&tmS, side_ptr, uint64_t(a->P), uint64_t(a->N_total), uint64_t(side_ld) * 2, 128, 64,
+                             CU_TENSOR_MAP_SWIZZLE_128B)) {
+    mv::set_error("mv_tapgemm: cuTensorMapEncodeTiled failed for the side input");
+    return MV_ERR_CUDA;
+  }
   const size_t smem = fixed + stg + size_t(p.in_stages) * p.in_stage_bytes + size_t(p.w_stages) * p.w_stage_bytes;
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -601,7 +625,7 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
       cudaFuncSetAttribute(tapgemm_kernel<CK_, BN_, TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit)); \
       attr_done = true;                                                                                                  \
     }                                                                                                                    \
-    tapgemm_kernel<CK_, BN_, TT_><<<grid, kThreads, smem, st>>>(tmA, tmW, tmO, tmO2, p);                                 \
+    tapgemm_kernel<CK_, BN_, TT_><<<grid, kThreads, smem, st>>>(tmA, tmW, tmO, tmO2, tmS, p);                                 \
   } while (0)
 #define MV_TG_T(CK_, BN_)                                  \
   do {                                                     \

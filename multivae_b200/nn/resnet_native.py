@@ -166,8 +166,8 @@ _PERM_CACHE = {}
 
 
 def _fc_perm(device):
-    """Row permutation that makes fc emit the halo layout at 7x7 directly: output feature (y'*8 + x)*256 + c
-    reads fc row c*49 + (y'-1)*7 + x; halo positions read an all-zero extra row."""
+    """(gather, scatter): `gather` [64*256] maps halo feature (y'*8 + x)*256 + c to fc row c*49 + (y'-1)*7 + x (halo
+    positions -> the extra all-zero row 12544); `scatter` [12544] is its inverse on the real rows."""
     key = str(device)
     if key not in _PERM_CACHE:
         idx = torch.full((8, 8, 256), 256 * 49, dtype=torch.long)
@@ -175,8 +175,39 @@ def _fc_perm(device):
         for y in range(1, 8):
             for x in range(7):
                 idx[y, x] = c * 49 + (y - 1) * 7 + x
-        _PERM_CACHE[key] = idx.reshape(-1).to(device)
+        idx = idx.reshape(-1)
+        inv = torch.empty(256 * 49, dtype=torch.long)
+        pos = torch.nonzero(idx < 256 * 49).squeeze(1)
+        inv[idx[pos]] = pos
+        _PERM_CACHE[key] = (idx.to(device), inv.to(device))
     return _PERM_CACHE[key]
+
+
+class FcHaloFn(torch.autograd.Function):
+    """fc of the decoder emitting the 7x7 halo matrix directly: rows of the weight are gathered into halo order
+    (zero rows at halo positions), so `z @ Wp^T + bp` IS the [n_img*64, 256] activation matrix.  Library GEMMs
+    (1.6 of 213 MFLOP per image); the backward gathers the real rows back (no scatter-add)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, bias):
+        gather, scatter = _fc_perm(z.device)
+        w_ext = torch.cat([weight.detach(), weight.new_zeros(1, weight.shape[1])], 0).to(torch.bfloat16)
+        b_ext = torch.cat([bias.detach(), bias.new_zeros(1)], 0).to(torch.bfloat16)
+        wp = w_ext[gather]
+        zb = z.detach().to(torch.bfloat16)
+        h0 = torch.addmm(b_ext[gather], zb, wp.t())
+        ctx.save_for_backward(zb, wp)
+        ctx.scatter = scatter
+        return h0
+
+    @staticmethod
+    def backward(ctx, g):
+        zb, wp = ctx.saved_tensors
+        g = g.reshape(zb.shape[0], -1).to(torch.bfloat16)
+        gz = (g @ wp).float() if ctx.needs_input_grad[0] else None
+        gw = (g.t() @ zb).float()[ctx.scatter]
+        gb = g.float().sum(0)[ctx.scatter]
+        return gz, gw, gb
 
 
 def decoder_params(dec):
@@ -193,12 +224,7 @@ def decoder_params(dec):
 def decoder_forward(dec, z, out_dtype=None):
     zz = z.reshape(-1, z.size(-1))
     n_img = zz.shape[0]
-    idx = _fc_perm(z.device)
-    w_ext = torch.cat([dec.fc.weight, dec.fc.weight.new_zeros(1, dec.fc.weight.shape[1])], 0)
-    b_ext = torch.cat([dec.fc.bias, dec.fc.bias.new_zeros(1)], 0)
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        h0 = F.linear(zz, w_ext[idx], b_ext[idx])          # [n_img, 64*256] == halo matrix [n_img*64, 256]
-    h0 = h0.view(n_img * 64, 256)
+    h0 = FcHaloFn.apply(zz, dec.fc.weight, dec.fc.bias).view(n_img * 64, 256)  # halo matrix at 7x7
     recon = DecoderStackFn.apply(h0, n_img, *decoder_params(dec))
     recon = recon.view(*z.size()[:-1], *recon.shape[1:])
     return ModelOutput(reconstruction=recon)
