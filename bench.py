@@ -157,13 +157,15 @@ def north_star_model(device):
     return mb.MMVAEPlus(cfg, enc, dec).to(device)
 
 
-def elbo_rel_err(device):
-    """|loss_gpu - loss_oracle| / |loss_oracle| on a tiny batch with injected noise (fp32 master path)."""
+def elbo_rel_err(device, compute_dtype=torch.float32):
+    """|loss_gpu - loss_oracle| / |loss_oracle| on a tiny batch with injected noise.  fp32: library networks + native ELBO
+    kernels; bf16: the tcgen05 decoders (bf16 operands) + native ELBO kernels, against the same fp32 CPU oracle."""
     import multivae_b200 as mb
     from oracle.port import elbo as E
     from oracle.port import nets as N
     B, Kk = 2, 2
     model = north_star_model(device)
+    model.compute_dtype = compute_dtype
     mods = [f"m{i}" for i in range(M)]
     data = synthetic_batch(B)
     g = torch.Generator().manual_seed(2000)
@@ -214,7 +216,7 @@ def run_gpu(args):
     host = synthetic_batch(B, pinned=True)
     ds = mb.MultimodalBaseDataset(data=host)
     tcfg = BaseTrainerConfig(per_device_train_batch_size=B, learning_rate=1e-3, optimizer_cls="Adam",
-                             world_size=world, rank=rank, local_rank=local_rank)
+                             world_size=world, rank=rank, local_rank=local_rank, use_cuda_graph=not args.no_graph)
     trainer = BaseTrainer(model, ds, training_config=tcfg)
     model.train()
     resident = mb.DatasetOutput(data={k: v.to(device) for k, v in host.items()})
@@ -251,15 +253,14 @@ def run_gpu(args):
         out = trainer.step_batch(pinned)  # H2D of the five pinned image tensors inside
         last["loss"] = float(out.loss_sum)  # D2H read of the step's result
 
-    for _ in range(args.warmup):
+    # untimed: W warm-up steps (eager), plus the CUDA-graph capture step and one replay when graphs are on
+    for _ in range(args.warmup if args.no_graph else max(args.warmup, tcfg.graph_warmup_steps + 2)):
         step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    n0 = _cabi.launch_count()
     ms = timed(step_resident, args.steps)
     host_enqueue_ms = host_ms[0]
-    launches = _cabi.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times for the roofline (separate short pass so the events do not perturb `value`)
     timer = _cabi.KernelTimer()
@@ -268,8 +269,11 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e0.record()
     nprof = max(1, min(3, args.steps))
+    n0 = _cabi.launch_count()
     for _ in range(nprof):
-        step_resident()
+        trainer.step_batch(resident, allow_graph=False)   # per-kernel events need host-launched kernels
+    # kernels of this library per step (the same launches are what the CUDA graph replays in the timed region)
+    launches = (_cabi.launch_count() - n0) // nprof * args.steps
     e1.record()
     summary = timer.summary()
     _cabi.set_timer(None)
@@ -284,10 +288,11 @@ def run_gpu(args):
     value = world * B * args.steps / (ms / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     roof = roofline_from(summary, prof_ms, B)
-    rel = None
+    rel = rel16 = None
     if not args.no_check:
         try:
             rel = elbo_rel_err(device)
+            rel16 = elbo_rel_err(device, torch.bfloat16)
         except Exception as e:  # the check must not hide the timing line
             rel = f"failed: {type(e).__name__}: {e}"
     cpu = None
@@ -312,7 +317,7 @@ def run_gpu(args):
         "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": roof,
         "step_fraction_of_tensor_ceiling": value / world / (peaks["bf16_tflops_sustained"] * 1e3 / GFLOP_PER_SAMPLE),
-        "elbo_rel_err": rel,
+        "elbo_rel_err": rel, "elbo_rel_err_bf16_tensor_path": rel16,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -345,13 +350,31 @@ def roofline_from(summary, prof_ms, B):
         achieved = info["work"] / per_launch_s / 1e12
         peak, unit = peaks["bf16_tflops_sustained"], "TFLOP/s"
     shares = {k: round(v[1] / prof_ms, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1][1])[:8]}
+    # the HBM-bound fused ELBO kernels next to it (north_star asks for both rooflines)
+    elbo = {}
+    for sym in ("mv_moe_lpx_fwd", "mv_moe_lpx_bwd", "mv_moe_lw_fwd"):
+        if sym in summary:
+            c, t = summary[sym]
+            w = R.describe(sym, B=B, M=M, K=K, D=D, L=L, LW=LW)["work"]
+            elbo[sym] = {"avg_launch_us": t / c * 1e3, "achieved_GBps": w / (t / c / 1e3) / 1e9,
+                         "frac_of_measured_hbm": w / (t / c / 1e3) / 1e9 / peaks["hbm_gbs"], "bytes_per_launch": w}
+    # all tensor-core launches together: useful flops / summed kernel time
+    tflops = tms = 0.0
+    for k, (c, t) in summary.items():
+        inf = R.describe(k, B=B, M=M, K=K, D=D, L=L, LW=LW)
+        if inf["bound"] == "tensor":
+            tflops += inf["work"] * c
+            tms += t
+    tensor_all = {"useful_TFLOPs_per_s": tflops / (tms / 1e3) / 1e12 if tms else None,
+                  "frac_of_sustained_peak": tflops / (tms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"] if tms else None,
+                  "share_of_step": tms / prof_ms}
     if os.environ.get("MV_BENCH_DUMP"):
         with open(os.environ["MV_BENCH_DUMP"], "w") as f:
             json.dump({"prof_ms": prof_ms, "kernels": {k: {"calls": v[0], "ms": v[1]} for k, v in summary.items()}}, f, indent=1)
     return {"kernel": name, "bound": info["bound"], "achieved": achieved, "peak": peak, "unit": unit,
             "frac": achieved / peak, "peak_source": peaks["source"], "traffic": info.get("traffic"),
             "algorithmic_work_per_launch": info["work"], "avg_launch_us": per_launch_s * 1e6, "launches": calls,
-            "share_of_step": total_ms / prof_ms, "shares": shares}
+            "share_of_step": total_ms / prof_ms, "shares": shares, "elbo_kernels": elbo, "tensor_kernels_total": tensor_all}
 
 
 def run_reference(args):
@@ -384,6 +407,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

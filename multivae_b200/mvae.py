@@ -12,6 +12,8 @@ from .subsets import mvae_random_subsets, subset_bitmask
 
 
 class MVAE(BaseMultiVAE):
+    step_depends_on_epoch = True  # KL warm-up reads (epoch, batch_ratio): a captured step is only valid for one value
+
     def __init__(self, model_config, encoders=None, decoders=None):
         super().__init__(model_config, encoders, decoders)
         self.subsampling = model_config.use_subsampling

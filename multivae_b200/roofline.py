@@ -1,11 +1,29 @@
-"""Algorithmic work per launch of each native entry point (the numerators of bench.py's roofline);
-the formulas are the ones stated in DESIGN.md."""
+"""Algorithmic work per launch of each native entry point (the numerators of bench.py's roofline); the
+formulas are the ones stated in DESIGN.md.  Tensor-core kernels count USEFUL flops (real pixels only — the
+halo rows the kernels also multiply are overhead, not work)."""
+
+# decoder layer tags (multivae_b200/nn/resnet_native.py) -> (H, Cin, Cout, taps)
+_DEC_LAYERS = {
+    "b1.sc": (7, 256, 128, 1), "b1.c0": (7, 256, 128, 9), "b1.c1": (7, 128, 128, 9),
+    "b2.sc": (14, 128, 64, 1), "b2.c0": (14, 128, 64, 9), "b2.c1": (14, 64, 64, 9),
+    "b3.c0": (28, 64, 64, 9), "b3.c1": (28, 64, 64, 9), "head": (28, 64, 3, 9),
+}
+
+
+def _layer(tag):
+    base = tag[:-1] if tag.endswith("d") and tag[:-1] in _DEC_LAYERS else tag   # "b3.c1d" = data gradient of b3.c1
+    if tag == "head.d":
+        base = "head"
+    return _DEC_LAYERS.get(base)
 
 
 def describe(name, *, B, M, K, D, L, LW):
     """name = C-ABI symbol (optionally ':tag').  Returns {"bound", "work" (bytes or flops per launch)}."""
-    sym = name.split(":")[0]
+    sym, _, tag = name.partition(":")
     rows = M * K * B  # (cond modality, importance sample, batch sample) rows of one reconstructed modality
+    if sym in ("mv_tapgemm", "mv_wgrad") and _layer(tag):
+        H, cin, cout, taps = _layer(tag)
+        return {"bound": "tensor", "work": 2.0 * rows * H * H * cin * cout * taps, "layer": (H, cin, cout, taps)}
     if sym == "mv_moe_lpx_fwd":
         # read recon (bf16) once + targets (fp32) once, write lpx
         return {"bound": "hbm", "work": rows * D * 2 + B * D * 4 + rows * 4}

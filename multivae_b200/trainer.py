@@ -39,6 +39,10 @@ class BaseTrainerConfig:
     master_addr: str = "127.0.0.1"
     master_port: str = "12345"
     gradient_clipping_max_norm: Optional[float] = None
+    # B200 addition: replay the whole step (forward, backward, all-reduce, optimizer) as ONE CUDA graph once the
+    # batch shape has been seen `graph_warmup_steps` times — the step is ~10^3 kernel launches and host-bound otherwise
+    use_cuda_graph: bool = False
+    graph_warmup_steps: int = 3
     beta_schedule: Optional[list] = field(default=None)
 
     def __post_init__(self):
@@ -122,6 +126,7 @@ class BaseTrainer:
         self.model.to(self.device)
         self.model.device = self.device
         self.flat = FlatGrads(self.model.parameters())
+        self._graphs = {}
         self.set_optimizer()
         self._broadcast_parameters()
 
@@ -154,6 +159,8 @@ class BaseTrainer:
         kw = dict(cfg.optimizer_params or {})
         if self.device.type == "cuda" and cfg.optimizer_cls in ("Adam", "AdamW", "SGD"):
             kw.setdefault("fused", True)
+        if self.device.type == "cuda" and cfg.use_cuda_graph and cfg.optimizer_cls in ("Adam", "AdamW"):
+            kw.setdefault("capturable", True)  # step counter on the device
         self.optimizer = cls([p for p in self.model.parameters() if p.requires_grad], lr=cfg.learning_rate, **kw)
 
     def local_batches(self):
@@ -186,15 +193,50 @@ class BaseTrainer:
             self.flat.allreduce_mean()
         self.optimizer.step()
 
-    def step_batch(self, inputs, epoch=1, batch_ratio=0.0, n_batches=1):
-        """One batch of train_step (base_trainer.py:704-728) without the host read-back."""
-        inputs = self._to_device(inputs)
+    def _eager_step(self, inputs, epoch, batch_ratio):
         sched = self.training_config.beta_schedule
         beta_epoch = sched[epoch - 1] if sched is not None else 1
         out = self.model(inputs, epoch=epoch, dataset_size=len(self.train_dataset), uses_ddp=self.distributed,
                          batch_ratio=batch_ratio, beta=beta_epoch)
         self._optimizers_step(out)
         return out
+
+    def step_batch(self, inputs, epoch=1, batch_ratio=0.0, n_batches=1, allow_graph=True):
+        """One batch of train_step (base_trainer.py:704-728) without the host read-back."""
+        cfg = self.training_config
+        if not (cfg.use_cuda_graph and allow_graph and self.device.type == "cuda"):
+            return self._eager_step(self._to_device(inputs), epoch, batch_ratio)
+        return self._graph_step(inputs, epoch, batch_ratio)
+
+    # ---- CUDA-graph replay of the step ------------------------------------------------------------
+    def _graph_step(self, inputs, epoch, batch_ratio):
+        """Eager for the first `graph_warmup_steps` occurrences of a batch signature, then capture once and replay.
+        The signature includes every Python scalar the models read per step (epoch, batch_ratio), so a model whose
+        arithmetic depends on them (MVAE's KL warm-up) is re-captured only when they change."""
+        has_masks = hasattr(inputs, "masks")
+        sig = (tuple((m, tuple(t.shape), t.dtype) for m, t in inputs.data.items()), has_masks,
+               epoch if getattr(self.model, "step_depends_on_epoch", False) else None,
+               batch_ratio if getattr(self.model, "step_depends_on_epoch", False) else None)
+        st = self._graphs.setdefault(sig, {"seen": 0})
+        if "graph" not in st:
+            if st["seen"] < self.training_config.graph_warmup_steps or has_masks:
+                st["seen"] += 1
+                return self._eager_step(self._to_device(inputs), epoch, batch_ratio)
+            static = DatasetOutput(data={m: torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                                         for m, t in inputs.data.items()})
+            for m, t in inputs.data.items():
+                static.data[m].copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()   # hand the eager pool's blocks to the graph's private pool
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._eager_step(static, epoch, batch_ratio)
+            st.update(graph=graph, static=static, out=out)
+        else:
+            for m, t in inputs.data.items():
+                st["static"].data[m].copy_(t, non_blocking=True)
+        st["graph"].replay()
+        return st["out"]
 
     # base_trainer.py:682-750
     def train_step(self, epoch):

@@ -108,4 +108,18 @@ def smoke_check():
     assert torch.cuda.is_available(), "smoke() needs a GPU"
     torch.cuda.set_device(0)
     e = check_case("mmvaeplus_dreg", verbose=True)
-    print("smoke ok:", e)
+    # the north-star model (ResNet encoders/decoders): library-network fp32 path and the tcgen05 decoder path (bf16
+    # operands) against the fp32 CPU oracle, plus one backward through the native decoders
+    import bench
+    dev = torch.device("cuda", 0)
+    r32 = bench.elbo_rel_err(dev)
+    r16 = bench.elbo_rel_err(dev, torch.bfloat16)
+    assert r32 <= 1e-4, r32
+    assert r16 <= 2e-2, r16
+    model = bench.north_star_model(dev)
+    model.compute_dtype = torch.bfloat16
+    out = model(mb.MultimodalBaseDataset(data={k: v.to(dev) for k, v in bench.synthetic_batch(2).items()}), K=2)
+    out.loss.backward()
+    g = model.decoders["m0"].resnet[4].conv_layers[0].weight.grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
+    print("smoke ok:", e, "north-star ELBO rel err fp32 path", r32, "bf16 tensor path", r16)
