@@ -164,6 +164,10 @@ int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
  *   dW fp32 [T, N, Cin], must be initialised by the caller (zeros, or a running gradient). */
 int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
              const int* tap_off, int64_t P, float* dW, void* stream);
+/* same, for a slice of N columns [n_offset, n_offset + N) of a layer with N_total output channels: G points at the
+ * slice's first column, dW is the full [T, N_total, Cin] tensor */
+int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
+                   const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, void* stream);
 
 /* HBM-bound helpers of the shared-halo layout (all tensors bf16 unless noted):
  *   mv_upsample2x_fwd  nn.Upsample(scale_factor=2) (models/nn/mmnist.py:345): in (H x W, C ch) -> out (2H x 2W, C ch)
@@ -176,6 +180,13 @@ int mv_upsample2x_bwd(const void* g_out, const void* act, void* g_in, void* g_pr
                       float slope, void* stream);
 int mv_head_grad_pack(const void* g, const void* y_out, void* out, int n_img, int H, int W, int ch, float slope, void* stream);
 int mv_colsum(const void* G, int64_t P, int ld, int N, float* out, void* stream);
+/*   mv_avgpool3s2_fwd  nn.AvgPool2d(3, stride=2, padding=1) of the ResNet encoder (models/nn/mmnist.py:278): (H x W) -> (H/2 x W/2)
+ *   mv_avgpool3s2_bwd  its gradient (+ optional g_pre = alpha*g_in*lrelu'(act), like mv_upsample2x_bwd)
+ *   mv_scale_dact      out = alpha * g * lrelu'(act) on [P, C] matrices */
+int mv_avgpool3s2_fwd(const void* in, void* out, int n_img, int H, int W, int C, void* stream);
+int mv_avgpool3s2_bwd(const void* g_out, const void* act, void* g_in, void* g_pre, int n_img, int H, int W, int C, float alpha,
+                      float slope, void* stream);
+int mv_scale_dact(const void* g, const void* act, void* out, int64_t P, int C, float alpha, float slope, void* stream);
 
 #ifdef __cplusplus
 }

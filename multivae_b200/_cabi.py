@@ -55,6 +55,11 @@ _PROTOS = {
     "mv_upsample2x_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
     "mv_head_grad_pack": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "mv_colsum": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
+    "mv_avgpool3s2_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "mv_avgpool3s2_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
+    "mv_scale_dact": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p],
+    "mv_wgrad_slice": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
+                       c_int64, c_void_p, c_int, c_int, c_void_p],
     "mv_wgrad": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                  c_int64, c_void_p, c_void_p],
     "mv_poe_bwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +

@@ -42,12 +42,18 @@ template <typename T, int DIST>
 __global__ void __launch_bounds__(128) lpx_fwd_kernel(const T* __restrict__ recon, const float* __restrict__ x,
                                                       float* __restrict__ lpx, int C, int K, int B, int64_t D,
                                                       float mul, float add_per_elem, float rescale,
-                                                      const uint8_t* __restrict__ mask, int accumulate, int nchunks) {
+                                                      const uint8_t* __restrict__ mask, int accumulate, int nchunks,
+                                                      int ksplit) {
   constexpr int VE = Vec<T>::N;
   constexpr int NV = kChunkElems / (32 * VE);
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= int64_t(C) * B * nchunks) return;
+  int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= int64_t(C) * B * nchunks * ksplit) return;
+  // the K importance samples of a (c, b, chunk) are split over `ksplit` warps when there are too few rows to fill the GPU
+  const int ks = int(warp % ksplit);
+  warp /= ksplit;
+  const int kper = (K + ksplit - 1) / ksplit;
+  const int k_begin = ks * kper, k_end = min(K, k_begin + kper);
   const int chunk = int(warp % nchunks);
   const int64_t cb = warp / nchunks;
   const int b = int(cb % B), c = int(cb / B);
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(128) lpx_fwd_kernel(const T* __restrict__ reco
   }
   int64_t n_here = nvec - int64_t(chunk) * NV * 32;
   n_here = (n_here > NV * 32 ? NV * 32 : n_here) * VE;
-  for (int k = 0; k < K; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     const int64_t row = (int64_t(c) * K + k) * B + b;
     float acc = 0.f;
     if (live) {
@@ -130,12 +136,16 @@ __global__ void __launch_bounds__(128) lpx_bwd_kernel(const T* __restrict__ reco
                                                       const float* __restrict__ coef, const float* __restrict__ g_loss,
                                                       T* __restrict__ g_recon, int C, int K, int B, int64_t D,
                                                       float inv_s, float rescale, const uint8_t* __restrict__ mask,
-                                                      int nchunks) {
+                                                      int nchunks, int ksplit) {
   constexpr int VE = Vec<T>::N;
   constexpr int NV = kChunkElems / (32 * VE);
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (warp >= int64_t(C) * B * nchunks) return;
+  int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= int64_t(C) * B * nchunks * ksplit) return;
+  const int ks = int(warp % ksplit);
+  warp /= ksplit;
+  const int kper = (K + ksplit - 1) / ksplit;
+  const int k_begin = ks * kper, k_end = min(K, k_begin + kper);
   const int chunk = int(warp % nchunks);
   const int64_t cb = warp / nchunks;
   const int b = int(cb % B), c = int(cb / B);
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(128) lpx_bwd_kernel(const T* __restrict__ reco
       }
     }
   }
-  for (int k = 0; k < K; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     const int64_t row = (int64_t(c) * K + k) * B + b;
     const float cf = live ? coef[row] * gl : 0.f;
     const T* rp = recon + row * D;
@@ -417,6 +427,15 @@ static void lp_consts(int dist, float s, float* mul, float* add) {
   }
 }
 
+// split the K samples of a (c, b, chunk) over several warps until ~24 warps per SM are in flight (HBM latency
+// hiding): the smallest divisor of K that reaches that, else K itself
+static int pick_ksplit(int64_t base_warps, int K) {
+  const int64_t want = int64_t(148) * 24;
+  for (int ks = 1; ks <= K; ++ks)
+    if (K % ks == 0 && base_warps * ks >= want) return ks;
+  return K;
+}
+
 template <typename T>
 static int launch_lpx_fwd(const void* recon, const float* x, float* lpx, int C, int K, int B, int64_t D, int dist,
                           float s, float rescale, const uint8_t* mask, int accumulate, cudaStream_t st) {
@@ -429,9 +448,10 @@ static int launch_lpx_fwd(const void* recon, const float* x, float* lpx, int C, 
   if (vec_ok) {
     const int nchunks = int((D + kChunkElems - 1) / kChunkElems);
     if (nchunks > 1 && !accumulate) cudaMemsetAsync(lpx, 0, sizeof(float) * size_t(C) * K * B, st);
-    const int64_t warps = int64_t(C) * B * nchunks;
+    const int ksplit = pick_ksplit(int64_t(C) * B * nchunks, K);
+    const int64_t warps = int64_t(C) * B * nchunks * ksplit;
     const int blocks = int((warps + 3) / 4);
-#define L_(DI) lpx_fwd_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, lpx, C, K, B, D, mul, add, rescale, mask, accumulate, nchunks)
+#define L_(DI) lpx_fwd_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, lpx, C, K, B, D, mul, add, rescale, mask, accumulate, nchunks, ksplit)
     if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
     else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
     else L_(MV_DIST_BERNOULLI);
@@ -462,9 +482,10 @@ static int launch_lpx_bwd(const void* recon, const float* x, const float* coef, 
                       (reinterpret_cast<uintptr_t>(x) % 16 == 0);
   if (vec_ok) {
     const int nchunks = int((D + kChunkElems - 1) / kChunkElems);
-    const int64_t warps = int64_t(C) * B * nchunks;
+    const int ksplit = pick_ksplit(int64_t(C) * B * nchunks, K);
+    const int64_t warps = int64_t(C) * B * nchunks * ksplit;
     const int blocks = int((warps + 3) / 4);
-#define L_(DI) lpx_bwd_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, coef, g_loss, g, C, K, B, D, inv_s, rescale, mask, nchunks)
+#define L_(DI) lpx_bwd_kernel<T, DI><<<blocks, 128, 0, st>>>(r, x, coef, g_loss, g, C, K, B, D, inv_s, rescale, mask, nchunks, ksplit)
     if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
     else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
     else L_(MV_DIST_BERNOULLI);

@@ -105,6 +105,93 @@ __global__ void __launch_bounds__(256) head_grad_pack_kernel(const bf16* __restr
   }
 }
 
+// nn.AvgPool2d(3, stride=2, padding=1) (count_include_pad: divisor 9): in (H x W) -> out (H/2 x W/2).  The zero halo of
+// the layout IS the padding, so the nine taps are read without bounds checks.
+__global__ void __launch_bounds__(256) avgpool3s2_fwd_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, HaloGeom gi,
+                                                            HaloGeom go, int C) {
+  const int vec_per_row = C >> 3;
+  const int64_t total = int64_t(go.P) * vec_per_row;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int img, y, x;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (decode_row(go, row, img, y, x)) {
+      // centre of the window in the input: (2(y-1), 2x) in image coordinates = halo row 1 + 2(y-1)
+      const int64_t centre = int64_t(img) * gi.S + int64_t(1 + 2 * (y - 1)) * gi.Wp + 2 * x;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int64_t src = centre + dy * gi.Wp + dx;
+          if (src >= 0) {
+            float f[8];
+            unpack8f(ld_stream(in + src * C + v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += f[e];
+          }
+        }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] *= (1.f / 9.f);
+    }
+    st_stream(out + int64_t(row) * C + v * 8, pack8f(s));
+  }
+}
+
+// gradient of the pooling: g_in(Y, X) = 1/9 * sum of g_out(y, x) over the windows that contain (Y, X);
+// optionally g_pre = alpha * g_in * lrelu'(act) (residual-branch gradient of the ResnetBlock below)
+__global__ void __launch_bounds__(256) avgpool3s2_bwd_kernel(const bf16* __restrict__ g_out, const bf16* __restrict__ act,
+                                                            bf16* __restrict__ g_in, bf16* __restrict__ g_pre, HaloGeom gi,
+                                                            HaloGeom go, int C, float alpha, float slope) {
+  const int vec_per_row = C >> 3;
+  const int64_t total = int64_t(gi.P) * vec_per_row;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int img, y, x;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (decode_row(gi, row, img, y, x)) {
+      const int Y = y - 1;  // image coordinates
+      // windows centred at 2*yo: contain Y iff |Y - 2 yo| <= 1
+      const int yo0 = (Y + 1) >> 1, ny = (Y & 1) ? 2 : 1;          // Y odd: yo in {(Y-1)/2, (Y+1)/2}; even: {Y/2}
+      const int xo0 = (x + 1) >> 1, nx = (x & 1) ? 2 : 1;
+      for (int a = 0; a < ny; ++a) {
+        const int yo = (Y & 1) ? ((Y - 1) >> 1) + a : yo0;
+        if (yo >= go.H) continue;
+        for (int b = 0; b < nx; ++b) {
+          const int xo = (x & 1) ? ((x - 1) >> 1) + b : xo0;
+          if (xo >= go.W) continue;
+          float f[8];
+          unpack8f(ld_stream(g_out + (int64_t(img) * go.S + int64_t(1 + yo) * go.Wp + xo) * C + v * 8), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s[e] += f[e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] *= (1.f / 9.f);
+      if (g_pre) {
+        float aa[8];
+        unpack8f(ld_stream(act + int64_t(row) * C + v * 8), aa);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pre[e] = alpha * s[e] * (aa[e] > 0.f ? 1.f : slope);
+      }
+    }
+    st_stream(g_in + int64_t(row) * C + v * 8, pack8f(s));
+    if (g_pre) st_stream(g_pre + int64_t(row) * C + v * 8, pack8f(pre));
+  }
+}
+
+// out = alpha * g * lrelu'(act)   (all [P, C] bf16; halo rows of g are zero, so they stay zero)
+__global__ void __launch_bounds__(256) scale_dact_kernel(const bf16* __restrict__ g, const bf16* __restrict__ act, bf16* __restrict__ out,
+                                                        int64_t nvec, float alpha, float slope) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float f[8], a[8];
+    unpack8f(ld_stream(g + i * 8), f);
+    unpack8f(ld_stream(act + i * 8), a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = alpha * f[e] * (a[e] > 0.f ? 1.f : slope);
+    st_stream(out + i * 8, pack8f(f));
+  }
+}
+
 // out[n] += sum_p G[p, n]   (N <= 256, N % 8 == 0)
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ G, int64_t P, int ld, int N, float* __restrict__ out) {
   __shared__ float red[256 * 8];
@@ -170,6 +257,41 @@ extern "C" int mv_head_grad_pack(const void* g, const void* y_out, void* out, in
   head_grad_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(y_out),
                                                                                static_cast<bf16*>(out), gg, ch, slope);
   MV_CHECK_LAUNCH("mv_head_grad_pack");
+  return MV_OK;
+}
+
+extern "C" int mv_avgpool3s2_fwd(const void* in, void* out, int n_img, int H, int W, int C, void* stream) {
+  MV_CHECK_ARG(in && out && n_img > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "mv_avgpool3s2_fwd: bad arguments");
+  const HaloGeom gi = make_geom(n_img, H, W), go = make_geom(n_img, H / 2, W / 2);
+  const int64_t total = int64_t(go.P) * (C / 8);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  avgpool3s2_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(in), static_cast<bf16*>(out),
+                                                                               gi, go, C);
+  MV_CHECK_LAUNCH("mv_avgpool3s2_fwd");
+  return MV_OK;
+}
+
+extern "C" int mv_avgpool3s2_bwd(const void* g_out, const void* act, void* g_in, void* g_pre, int n_img, int H, int W, int C,
+                                 float alpha, float slope, void* stream) {
+  MV_CHECK_ARG(g_out && g_in && n_img > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "mv_avgpool3s2_bwd: bad arguments");
+  MV_CHECK_ARG(!g_pre || act, "mv_avgpool3s2_bwd: g_pre needs the saved activation");
+  const HaloGeom gi = make_geom(n_img, H, W), go = make_geom(n_img, H / 2, W / 2);
+  const int64_t total = int64_t(gi.P) * (C / 8);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  avgpool3s2_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(g_out), static_cast<const bf16*>(act), static_cast<bf16*>(g_in), static_cast<bf16*>(g_pre), gi, go, C,
+      alpha, slope);
+  MV_CHECK_LAUNCH("mv_avgpool3s2_bwd");
+  return MV_OK;
+}
+
+extern "C" int mv_scale_dact(const void* g, const void* act, void* out, int64_t P, int C, float alpha, float slope, void* stream) {
+  MV_CHECK_ARG(g && act && out && P > 0 && C % 8 == 0, "mv_scale_dact: bad arguments");
+  const int64_t nvec = P * (C / 8);
+  const int blocks = int(std::min<int64_t>((nvec + 255) / 256, int64_t(num_sms()) * 16));
+  scale_dact_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(act),
+                                                                           static_cast<bf16*>(out), nvec, alpha, slope);
+  MV_CHECK_LAUNCH("mv_scale_dact");
   return MV_OK;
 }
 

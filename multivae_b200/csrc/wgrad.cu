@@ -161,8 +161,9 @@ constexpr size_t kWgSmemLimit = 232448;
 
 using namespace mv;
 
-extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
-                        int T, const int* tap_off, int64_t P, float* dW, void* stream) {
+extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
+                              int T, const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, void* stream) {
+  MV_CHECK_ARG(N_total >= N && n_offset >= 0 && n_offset + N <= N_total, "mv_wgrad: bad column slice");
   MV_CHECK_ARG(X && G && dW && tap_off, "mv_wgrad: null pointer");
   MV_CHECK_ARG(Cin % 64 == 0 && Cin >= 64 && Cin <= 256, "mv_wgrad: Cin must be 64/128/192/256, got %d", Cin);
   MV_CHECK_ARG(N == 16 || N == 64 || N == 128, "mv_wgrad: N must be 16, 64 or 128, got %d", N);
@@ -181,8 +182,8 @@ extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   p.N = N;
   p.Ncols = N < 32 ? 32 : N;
   p.Cin = Cin;
-  p.N_total_out = N;
-  p.dW = dW;
+  p.N_total_out = N_total;
+  p.dW = dW + size_t(n_offset) * Cin;
   p.n_ktiles = int((P + 127) / 128);
   // +8 rows of slack: the padding block of an odd tap count may read a few rows past the window
   p.x_chunk_bytes = (uint32_t(p.R + 8) * 128u + 1023u) & ~1023u;
@@ -263,4 +264,9 @@ extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   wgrad_kernel<<<dim3(gx, passes), kWgThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmX, tmG, p);
   MV_CHECK_LAUNCH("mv_wgrad");
   return MV_OK;
+}
+
+extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
+                        int T, const int* tap_off, int64_t P, float* dW, void* stream) {
+  return mv_wgrad_slice(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, N, 0, stream);
 }

@@ -102,8 +102,15 @@ def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None):
         dW = torch.zeros(T, N, Cin, device=X.device, dtype=torch.float32)
     offs = (ctypes.c_int32 * 9)(*[int(o) for o in tap_off])
     kw = {} if tag is None else {"tag": tag}
-    C.check(lib.mv_wgrad(X.data_ptr(), X.shape[0], X.stride(0), Cin, G.data_ptr(), G.shape[0], G.stride(0), N, T, offs, P,
-                         dW.data_ptr(), C.stream(), **kw), "mv_wgrad")
+    if N <= 128:
+        C.check(lib.mv_wgrad(X.data_ptr(), X.shape[0], X.stride(0), Cin, G.data_ptr(), G.shape[0], G.stride(0), N, T, offs, P,
+                             dW.data_ptr(), C.stream(), **kw), "mv_wgrad")
+    else:  # wide layers: 128-column slices of G, each into its rows of dW
+        assert N % 128 == 0
+        for n0 in range(0, N, 128):
+            Gs = G[:, n0:n0 + 128]
+            C.check(lib.mv_wgrad_slice(X.data_ptr(), X.shape[0], X.stride(0), Cin, Gs.data_ptr(), G.shape[0], G.stride(0), 128, T,
+                                       offs, P, dW.data_ptr(), N, n0, C.stream(), **kw), "mv_wgrad_slice")
     return dW
 
 

@@ -117,6 +117,9 @@ class EncoderResnetMMNIST(BaseEncoder):
         return NF.linear_heads(h, [getattr(self, f"fc_mu_{tag}"), getattr(self, f"fc_lv_{tag}")])
 
     def forward(self, x):
+        from . import resnet_native as RN
+        if RN.use_native(x):
+            return RN.encoder_forward(self, x)
         mu, lv = self._branch(x, "u")
         out = ModelOutput(embedding=mu, log_covariance=lv)
         if self.multiple_latent:

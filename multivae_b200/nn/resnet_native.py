@@ -28,9 +28,7 @@ def use_native(x):
 
 
 def status(which):
-    if which == "decoder":
-        return "native sm_100a: tcgen05 tap-GEMM conv fwd/dgrad + tcgen05 wgrad + halo kernels (fc: cuBLAS)"
-    return "torch (cuDNN/cuBLAS library calls)"
+    return "native sm_100a: tcgen05 tap-GEMM conv fwd/dgrad + tcgen05 wgrad + halo kernels (fc: cuBLAS)"
 
 
 # ---- low-level wrappers over the helper kernels -------------------------------------------------
@@ -53,7 +51,31 @@ def _upsample_bwd(g_out, act, g, c, alpha):
 def _colsum(G, P, n, out=None):
     if out is None:
         out = torch.zeros(n, device=G.device, dtype=torch.float32)
-    C.check(C.lib().mv_colsum(G.data_ptr(), P, G.stride(0), n, out.data_ptr(), C.stream()), "mv_colsum")
+    C.check(C.lib().mv_colsum(G.data_ptr(), min(P, G.shape[0]), G.stride(0), n, out.data_ptr(), C.stream()), "mv_colsum")
+    return out
+
+
+def _avgpool_fwd(x, g, c):
+    go = HL.Geom(g.n_img, g.H // 2, g.W // 2)
+    out = torch.empty(go.P, c, device=x.device, dtype=torch.bfloat16)
+    C.check(C.lib().mv_avgpool3s2_fwd(x.data_ptr(), out.data_ptr(), g.n_img, g.H, g.W, c, C.stream()), "mv_avgpool3s2_fwd")
+    return out, go
+
+
+def _avgpool_bwd(g_out, act, g, c, alpha):
+    """g: fine (input) geometry.  Returns (g_in, g_pre = alpha * g_in * lrelu'(act))."""
+    g_in = torch.empty(g.P, c, device=g_out.device, dtype=torch.bfloat16)
+    g_pre = torch.empty_like(g_in)
+    C.check(C.lib().mv_avgpool3s2_bwd(g_out.data_ptr(), act.data_ptr(), g_in.data_ptr(), g_pre.data_ptr(), g.n_img, g.H, g.W, c,
+                                      float(alpha), _LRELU, C.stream()), "mv_avgpool3s2_bwd")
+    return g_in, g_pre
+
+
+def _pack_image(x_bf16, g, y_out=None):
+    """dense NCHW bf16 [n, ch<=16, H, W] (optionally times lrelu'(y_out)) -> halo matrix [P, 16]."""
+    out = torch.empty(g.P, 16, device=x_bf16.device, dtype=torch.bfloat16)
+    C.check(C.lib().mv_head_grad_pack(x_bf16.data_ptr(), None if y_out is None else y_out.data_ptr(), out.data_ptr(), g.n_img, g.H,
+                                      g.W, x_bf16.shape[1], _LRELU, C.stream()), "mv_head_grad_pack")
     return out
 
 
@@ -230,5 +252,109 @@ def decoder_forward(dec, z, out_dtype=None):
     return ModelOutput(reconstruction=recon)
 
 
+class EncoderStackFn(torch.autograd.Function):
+    """One branch (shared `u` or private `w`) of EncoderResnetMMNIST up to the flatten: x [n, 3, 28, 28] ->
+    halo matrix [n*64, 256] at 7x7 (mmnist.py:254-300): conv_img, ResnetBlock(64,64), AvgPool, ResnetBlock(64,128),
+    AvgPool, ResnetBlock(128,256)."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        (wi, bi, w10, b10, w11, b11, w20, b20, w21, b21, wsc2, w30, b30, w31, b31, wsc3) = params
+        n_img = x.shape[0]
+        g28 = HL.Geom(n_img, 28, 28)
+        x16 = _pack_image(x.detach().to(torch.bfloat16).contiguous(), g28)
+        wip = torch.zeros(wi.shape[0], 16, 3, 3, device=x.device, dtype=wi.dtype)
+        wip[:, : wi.shape[1]] = wi.detach()
+        a0 = HL.tapgemm(x16, HL.pack_conv_weight(wip), 9, g28.taps3x3(), wi.shape[0], g28.P, bias=bi.detach().float().contiguous(),
+                        geom=g28, tag="e.img")
+        B1 = _Block(w10, b10, w11, b11, None)
+        B2 = _Block(w20, b20, w21, b21, wsc2)
+        B3 = _Block(w30, b30, w31, b31, wsc3)
+        o1, h1, d1 = _block_fwd(a0, g28, B1, "e1")
+        x2, g14 = _avgpool_fwd(o1, g28, B1.cout)
+        o2, h2, d2 = _block_fwd(x2, g14, B2, "e2")
+        x3, g7 = _avgpool_fwd(o2, g14, B2.cout)
+        o3, h3, d3 = _block_fwd(x3, g7, B3, "e3")
+        ctx.save_for_backward(x16, a0, h1, d1, x2, h2, d2, x3, h3, d3)
+        ctx.packs = (B1, B2, B3)
+        ctx.n_img, ctx.cin_img = n_img, wi.shape[1]
+        return o3[: n_img * 64]
+
+    @staticmethod
+    def backward(ctx, g_o3):
+        x16, a0, h1, d1, x2, h2, d2, x3, h3, d3 = ctx.saved_tensors
+        B1, B2, B3 = ctx.packs
+        n_img = ctx.n_img
+        g28 = HL.Geom(n_img, 28, 28)
+        g14, g7 = HL.Geom(n_img, 14, 14), HL.Geom(n_img, 7, 7)
+        lib = C.lib()
+        g3 = torch.zeros(g7.P, B3.cout, device=x16.device, dtype=torch.bfloat16)
+        g3[: n_img * 64].copy_(g_o3)
+        g_d3pre = torch.empty_like(g3)
+        C.check(lib.mv_scale_dact(g3.data_ptr(), d3.data_ptr(), g_d3pre.data_ptr(), g7.P, B3.cout, 0.1, _LRELU, C.stream()),
+                "mv_scale_dact")
+        g_x3, dW30, db30, dW31, db31, dWsc3 = _block_bwd(g3, g_d3pre, x3, h3, g7, B3, "e3")
+        g_o2, g_d2pre = _avgpool_bwd(g_x3, d2, g14, B2.cout, 0.1)
+        g_x2, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_d2pre, x2, h2, g14, B2, "e2")
+        g_o1, g_d1pre = _avgpool_bwd(g_x2, d1, g28, B1.cout, 0.1)
+        g_a0, dW10, db10, dW11, db11, _ = _block_bwd(g_o1, g_d1pre, a0, h1, g28, B1, "e1")
+        # conv_img (3 -> 64): weight gradient with the operand roles swapped (the 16-channel image is the N side),
+        # dWs[t, c, n] = sum_p x[p + off_t, c] * g_a0[p, n]
+        dWs = HL.wgrad(g_a0, x16, 9, [-o for o in g28.taps3x3()], g28.P, tag="e.img")       # [9, 16, 64]
+        dWi = dWs.view(3, 3, 16, dWs.shape[2]).permute(3, 2, 0, 1)[:, : ctx.cin_img]
+        dbi = _colsum(g_a0, g28.P, dWs.shape[2])
+        u = HL.unpack_conv_wgrad
+        return (None, dWi, dbi, u(dW10, 3, 3), db10, u(dW11, 3, 3), db11, u(dW20, 3, 3), db20, u(dW21, 3, 3), db21,
+                u(dWsc2, 1, 1), u(dW30, 3, 3), db30, u(dW31, 3, 3), db31, u(dWsc3, 1, 1))
+
+
+class FcFromHaloFn(torch.autograd.Function):
+    """The two Linear heads (mu, log-variance) on the flattened 7x7x256 activation kept in halo order: the weight
+    columns are gathered into halo order (zeros at halo positions) — library GEMMs, 0.4 % of the encoder's flops."""
+
+    @staticmethod
+    def forward(ctx, h, w_mu, b_mu, w_lv, b_lv):
+        gather, scatter = _fc_perm(h.device)
+        n_img = h.shape[0] // 64
+        w = torch.cat([w_mu.detach(), w_lv.detach()], 0)
+        wp = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).to(torch.bfloat16)[:, gather].contiguous()   # [2L, 16384]
+        h2 = h.reshape(n_img, 64 * 256)
+        out = (h2 @ wp.t()).float() + torch.cat([b_mu.detach(), b_lv.detach()]).float()
+        ctx.save_for_backward(h2, wp)
+        ctx.scatter, ctx.split = scatter, w_mu.shape[0]
+        return out[:, : w_mu.shape[0]].contiguous(), out[:, w_mu.shape[0]:].contiguous()
+
+    @staticmethod
+    def backward(ctx, g_mu, g_lv):
+        h2, wp = ctx.saved_tensors
+        g = torch.cat([g_mu, g_lv], 1)
+        gb = g.float().sum(0)
+        g16 = g.to(torch.bfloat16)
+        gw = (g16.t() @ h2).float()[:, ctx.scatter]
+        gh = (g16 @ wp).reshape(-1, 256)
+        k = ctx.split
+        return gh, gw[:k], gb[:k], gw[k:], gb[k:]
+
+
+def encoder_params(enc, tag):
+    r = getattr(enc, f"resnet_{tag}")
+    b1, b2, b3 = r[0], r[2], r[4]
+    ci = getattr(enc, f"conv_img_{tag}")
+    return (ci.weight, ci.bias,
+            b1.conv_layers[0].weight, b1.conv_layers[0].bias, b1.conv_layers[2].weight, b1.conv_layers[2].bias,
+            b2.conv_layers[0].weight, b2.conv_layers[0].bias, b2.conv_layers[2].weight, b2.conv_layers[2].bias,
+            b2.shortcut_layer.weight,
+            b3.conv_layers[0].weight, b3.conv_layers[0].bias, b3.conv_layers[2].weight, b3.conv_layers[2].bias,
+            b3.shortcut_layer.weight)
+
+
 def encoder_forward(enc, x):
-    raise NotImplementedError("the ResNet encoder runs on the library path in this round")
+    out = ModelOutput()
+    for tag, keys in (("u", ("embedding", "log_covariance")), ("w", ("style_embedding", "style_log_covariance"))):
+        if tag == "w" and not enc.multiple_latent:
+            continue
+        h = EncoderStackFn.apply(x, *encoder_params(enc, tag))
+        mu, lv = FcFromHaloFn.apply(h, getattr(enc, f"fc_mu_{tag}").weight, getattr(enc, f"fc_mu_{tag}").bias,
+                                    getattr(enc, f"fc_lv_{tag}").weight, getattr(enc, f"fc_lv_{tag}").bias)
+        out[keys[0]], out[keys[1]] = mu, lv
+    return out
