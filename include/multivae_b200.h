@@ -161,13 +161,14 @@ int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
  * Replaces the weight-gradient half of autograd's convolution_backward / addmm backward for the layers above
  * (the reference reaches it through loss.backward(), trainers/base/base_trainer.py:359).
  *   X bf16 [x_rows, x_ld] (Cin = 64 / 128 / 256 columns used), G bf16 [g_rows, g_ld] (N = 16 / 64 / 128 columns),
- *   dW fp32 [T, N, Cin], must be initialised by the caller (zeros, or a running gradient). */
+ *   dW fp32 [T, N, Cin], must be initialised by the caller (zeros, or a running gradient).
+ *   db (optional, fp32 [N]): bias gradient db[n] += sum_p G[p, n], computed from the same shared-memory tiles. */
 int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
-             const int* tap_off, int64_t P, float* dW, void* stream);
+             const int* tap_off, int64_t P, float* dW, float* db, void* stream);
 /* same, for a slice of N columns [n_offset, n_offset + N) of a layer with N_total output channels: G points at the
  * slice's first column, dW is the full [T, N_total, Cin] tensor */
 int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
-                   const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, void* stream);
+                   const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, float* db, void* stream);
 
 /* HBM-bound helpers of the shared-halo layout (all tensors bf16 unless noted):
  *   mv_upsample2x_fwd  nn.Upsample(scale_factor=2) (models/nn/mmnist.py:345): in (H x W, C ch) -> out (2H x 2W, C ch)

@@ -109,6 +109,61 @@ __global__ void __launch_bounds__(128) lpx_fwd_kernel(const T* __restrict__ reco
   }
 }
 
+// High-occupancy forward variant: one block per (c, b) stages the fp32 target row in shared memory once; its four
+// warps walk the K importance samples, streaming `recon` with 128-bit loads (4 in flight per lane).  ~40 registers,
+// so 12+ blocks are resident per SM and the HBM stream stays saturated (the register-cached variant above holds
+// 80 target floats per lane and tops out at 3 blocks per SM).
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_fwd_smem_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                           float* __restrict__ lpx, int C, int K, int B, int64_t D, float mul,
+                                                           float add_per_elem, float rescale, const uint8_t* __restrict__ mask,
+                                                           int accumulate) {
+  constexpr int VE = Vec<T>::N;
+  extern __shared__ float xs[];
+  const int b = blockIdx.x % B, c = blockIdx.x / B;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = mask == nullptr || mask[b] != 0;
+  if (live) {
+    const float4* xp = reinterpret_cast<const float4*>(x + int64_t(b) * D);
+    for (int i = threadIdx.x; i < int(D / 4); i += 128) reinterpret_cast<float4*>(xs)[i] = __ldg(xp + i);
+  }
+  __syncthreads();
+  const int nvec = int(D / VE);
+  for (int k = warp; k < K; k += 4) {
+    const int64_t row = (int64_t(c) * K + k) * B + b;
+    float acc = 0.f;
+    if (live) {
+      const T* rp = recon + row * D;
+      int v = lane;
+      for (; v + 96 < nvec; v += 128) {
+        uint4 rv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rv[j] = ld_stream(rp + int64_t(v + 32 * j) * VE);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r[VE];
+          Vec<T>::unpack(rv[j], r);
+          const float* xv = xs + (v + 32 * j) * VE;
+#pragma unroll
+          for (int e = 0; e < VE; ++e) acc += lp_term<DIST>(xv[e], r[e]);
+        }
+      }
+      for (; v < nvec; v += 32) {
+        float r[VE];
+        Vec<T>::unpack(ld_stream(rp + int64_t(v) * VE), r);
+        const float* xv = xs + v * VE;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) acc += lp_term<DIST>(xv[e], r[e]);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float val = live ? rescale * (acc * mul + add_per_elem * float(D)) : 0.f;
+      lpx[row] = accumulate ? lpx[row] + val : val;
+    }
+  }
+}
+
 // scalar fallback for rows whose byte length is not a multiple of 16 (e.g. D = 10)
 template <typename T, int DIST>
 __global__ void __launch_bounds__(128) lpx_fwd_scalar_kernel(const T* __restrict__ recon, const float* __restrict__ x,
@@ -430,7 +485,7 @@ static void lp_consts(int dist, float s, float* mul, float* add) {
 // split the K samples of a (c, b, chunk) over several warps until ~24 warps per SM are in flight (HBM latency
 // hiding): the smallest divisor of K that reaches that, else K itself
 static int pick_ksplit(int64_t base_warps, int K) {
-  const int64_t want = int64_t(148) * 24;
+  const int64_t want = int64_t(148) * 12;  // each extra split re-reads the fp32 target row (2x a bf16 recon row)
   for (int ks = 1; ks <= K; ++ks)
     if (K % ks == 0 && base_warps * ks >= want) return ks;
   return K;
@@ -445,7 +500,15 @@ static int launch_lpx_fwd(const void* recon, const float* x, float* lpx, int C, 
   const T* r = static_cast<const T*>(recon);
   const bool vec_ok = (D % VE == 0) && (reinterpret_cast<uintptr_t>(recon) % 16 == 0) &&
                       (D % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0);
-  if (vec_ok) {
+  if (vec_ok && D * 4 <= 48 * 1024) {
+    const int blocks = C * B;
+    const size_t smem = size_t(D) * 4;
+#define L_(DI) lpx_fwd_smem_kernel<T, DI><<<blocks, 128, smem, st>>>(r, x, lpx, C, K, B, D, mul, add, rescale, mask, accumulate)
+    if (dist == MV_DIST_NORMAL) L_(MV_DIST_NORMAL);
+    else if (dist == MV_DIST_LAPLACE) L_(MV_DIST_LAPLACE);
+    else L_(MV_DIST_BERNOULLI);
+#undef L_
+  } else if (vec_ok) {
     const int nchunks = int((D + kChunkElems - 1) / kChunkElems);
     if (nchunks > 1 && !accumulate) cudaMemsetAsync(lpx, 0, sizeof(float) * size_t(C) * K * B, st);
     const int ksplit = pick_ksplit(int64_t(C) * B * nchunks, K);

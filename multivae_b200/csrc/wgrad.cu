@@ -47,6 +47,7 @@ struct WgradParams {
   WgAcc acc[48];
   int Cin, N_total_out;         // dW is [T][N_total_out][Cin] fp32
   float* dW;
+  float* db;                    // optional bias gradient: db[n] += sum_p G[p, n] (fused column sums of the G tiles)
   int tmem_cols;
 };
 
@@ -59,13 +60,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   uint64_t* empty = bars + kWgMaxStages;
   uint64_t* done = empty + kWgMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);   // 128 x 8 partial column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pass = blockIdx.y;
+  const bool do_db = p.db != nullptr && pass == 0;   // the bias gradient is independent of the pass: pass 0 owns it
   const int nacc = p.n_acc[pass];
   const WgAcc* accs = p.acc + p.acc_begin[pass];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], do_db ? 5 : 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmX);
@@ -127,6 +130,40 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     if (tc::elect_one()) tc::umma_commit(done);
     __syncwarp();
   } else {
+    // ================= bias gradient: column sums of the G tiles while the MMAs run =================
+    if (do_db) {
+      const int et = threadIdx.x - 64;                       // 0..127
+      const int groups = p.N >> 3;                           // 16-byte column groups: 2 / 8 / 16
+      const int cj = et % groups, rg = et / groups;          // this thread: column group cj, rows rg*rpt .. +rpt-1
+      const int rpt = 128 / (128 / groups);                  // rows per thread = groups
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int s = 0, ph = 0;
+      for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x) {
+        tc::mbar_wait(&full[s], ph);
+        const uint8_t* gt = smem + size_t(s) * p.stage_bytes + g_off;
+        for (int i = 0; i < rpt; ++i) {
+          const int row = rg * rpt + i;
+          uint32_t off;
+          if (p.g_row_bytes == 128) off = uint32_t(cj >> 3) * 16384u + uint32_t(row) * 128u + uint32_t(((cj & 7) ^ (row & 7)) << 4);
+          else off = uint32_t(row) * p.g_row_bytes + uint32_t((cj ^ ((row >> 2) & 1)) << 4);   // SWIZZLE_32B
+          const uint4 v = *reinterpret_cast<const uint4*>(gt + off);
+          acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+          acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[et * 8 + e] = acc[e];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < p.N) {
+        const int g2 = et >> 3, e = et & 7;
+        float sum = 0.f;
+        for (int r2 = 0; r2 < 128 / groups; ++r2) sum += red[(r2 * groups + g2) * 8 + e];
+        atomicAdd(p.db + et, sum);
+      }
+    }
     // ================= epilogue: partial dW -> global fp32 reductions =================
     const int q = warp & 3;
     tc::mbar_wait(done, 0);
@@ -162,7 +199,8 @@ constexpr size_t kWgSmemLimit = 232448;
 using namespace mv;
 
 extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
-                              int T, const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, void* stream) {
+                              int T, const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, float* db,
+                              void* stream) {
   MV_CHECK_ARG(N_total >= N && n_offset >= 0 && n_offset + N <= N_total, "mv_wgrad: bad column slice");
   MV_CHECK_ARG(X && G && dW && tap_off, "mv_wgrad: null pointer");
   MV_CHECK_ARG(Cin % 64 == 0 && Cin >= 64 && Cin <= 256, "mv_wgrad: Cin must be 64/128/192/256, got %d", Cin);
@@ -184,6 +222,7 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   p.Cin = Cin;
   p.N_total_out = N_total;
   p.dW = dW + size_t(n_offset) * Cin;
+  p.db = db ? db + n_offset : nullptr;
   p.n_ktiles = int((P + 127) / 128);
   // +8 rows of slack: the padding block of an odd tap count may read a few rows past the window
   p.x_chunk_bytes = (uint32_t(p.R + 8) * 128u + 1023u) & ~1023u;
@@ -239,7 +278,7 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   for (int i = 0; i < passes; ++i) max_acc = p.n_acc[i] > max_acc ? p.n_acc[i] : max_acc;
   int cols = max_acc * p.Ncols;
   p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
-  const size_t fixed = 2048 + (2 * kWgMaxStages + 1) * 8 + 16;
+  const size_t fixed = 2048 + (2 * kWgMaxStages + 1) * 8 + 16 + 128 * 8 * 4;
   p.stages = int((kWgSmemLimit - fixed) / p.stage_bytes);
   if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   MV_CHECK_ARG(p.stages >= 1, "mv_wgrad: stage does not fit shared memory");
@@ -267,6 +306,6 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
 }
 
 extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
-                        int T, const int* tap_off, int64_t P, float* dW, void* stream) {
-  return mv_wgrad_slice(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, N, 0, stream);
+                        int T, const int* tap_off, int64_t P, float* dW, float* db, void* stream) {
+  return mv_wgrad_slice(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, N, 0, db, stream);
 }

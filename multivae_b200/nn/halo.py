@@ -91,8 +91,9 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
     return out
 
 
-def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None):
-    """dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]  (fp32 [T, N, Cin]); see mv_wgrad."""
+def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=False):
+    """dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]  (fp32 [T, N, Cin]); see mv_wgrad.
+    want_db: also return db[n] = sum_p G[p, n] (bias gradient), fused into the same kernel."""
     import ctypes
     lib = C.lib()
     Cin = X.shape[1] if Cin is None else Cin
@@ -102,16 +103,18 @@ def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None):
         dW = torch.zeros(T, N, Cin, device=X.device, dtype=torch.float32)
     offs = (ctypes.c_int32 * 9)(*[int(o) for o in tap_off])
     kw = {} if tag is None else {"tag": tag}
+    db = torch.zeros(N, device=X.device, dtype=torch.float32) if want_db else None
+    dbp = None if db is None else db.data_ptr()
     if N <= 128:
         C.check(lib.mv_wgrad(X.data_ptr(), X.shape[0], X.stride(0), Cin, G.data_ptr(), G.shape[0], G.stride(0), N, T, offs, P,
-                             dW.data_ptr(), C.stream(), **kw), "mv_wgrad")
+                             dW.data_ptr(), dbp, C.stream(), **kw), "mv_wgrad")
     else:  # wide layers: 128-column slices of G, each into its rows of dW
         assert N % 128 == 0
         for n0 in range(0, N, 128):
             Gs = G[:, n0:n0 + 128]
             C.check(lib.mv_wgrad_slice(X.data_ptr(), X.shape[0], X.stride(0), Cin, Gs.data_ptr(), G.shape[0], G.stride(0), 128, T,
-                                       offs, P, dW.data_ptr(), N, n0, C.stream(), **kw), "mv_wgrad_slice")
-    return dW
+                                       offs, P, dW.data_ptr(), N, n0, dbp, C.stream(), **kw), "mv_wgrad_slice")
+    return (dW, db) if want_db else dW
 
 
 def unpack_conv_wgrad(dW, kh, kw):

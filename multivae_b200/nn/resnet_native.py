@@ -107,11 +107,9 @@ def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True):
     """g_out: gradient of the block output; g_dpre = 0.1 * g_out * lrelu'(d) (produced upstream).
     Returns (g_x, dW0, db0, dW1, db1, dWsc)."""
     taps = g.taps3x3()
-    dW1 = HL.wgrad(h, g_dpre, 9, taps, g.P, tag=f"{tag}.c1")
-    db1 = _colsum(g_dpre, g.P, blk.cout)
+    dW1, db1 = HL.wgrad(h, g_dpre, 9, taps, g.P, tag=f"{tag}.c1", want_db=True)
     g_hpre = HL.tapgemm(g_dpre, blk.w1d, 9, taps, blk.hid, g.P, dact1=h, slope1=_LRELU, geom=g, tag=f"{tag}.c1d")
-    dW0 = HL.wgrad(x, g_hpre, 9, taps, g.P, tag=f"{tag}.c0")
-    db0 = _colsum(g_hpre, g.P, blk.hid)
+    dW0, db0 = HL.wgrad(x, g_hpre, 9, taps, g.P, tag=f"{tag}.c0", want_db=True)
     dWsc = None
     g_short = g_out
     if blk.wsc is not None:
@@ -165,8 +163,7 @@ class DecoderStackFn(torch.autograd.Function):
         gh = torch.empty(g28.P, 16, device=h0.device, dtype=torch.bfloat16)
         C.check(lib.mv_head_grad_pack(g_recon.data_ptr(), recon.data_ptr(), gh.data_ptr(), n_img, 28, 28, n_ch, _LRELU, C.stream()),
                 "mv_head_grad_pack")
-        dWh = HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head")
-        dbh = _colsum(gh, g28.P, 16)
+        dWh, dbh = HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head", want_db=True)
         g_dpre3 = torch.empty(g28.P, B3.cout, device=h0.device, dtype=torch.bfloat16)
         g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, dact2=d3, slope2=_LRELU, geom=g28,
                           tag="head.d")

@@ -10,6 +10,14 @@ _DEC_LAYERS = {
 }
 
 
+# encoder layer tags: one branch of one modality, n_img = B images
+_ENC_LAYERS = {
+    "e.img": (28, 3, 64, 9), "e1.c0": (28, 64, 64, 9), "e1.c1": (28, 64, 64, 9),
+    "e2.sc": (14, 64, 128, 1), "e2.c0": (14, 64, 64, 9), "e2.c1": (14, 64, 128, 9),
+    "e3.sc": (7, 128, 256, 1), "e3.c0": (7, 128, 128, 9), "e3.c1": (7, 128, 256, 9),
+}
+
+
 def _layer(tag):
     base = tag[:-1] if tag.endswith("d") and tag[:-1] in _DEC_LAYERS else tag   # "b3.c1d" = data gradient of b3.c1
     if tag == "head.d":
@@ -24,6 +32,12 @@ def describe(name, *, B, M, K, D, L, LW):
     if sym in ("mv_tapgemm", "mv_wgrad") and _layer(tag):
         H, cin, cout, taps = _layer(tag)
         return {"bound": "tensor", "work": 2.0 * rows * H * H * cin * cout * taps, "layer": (H, cin, cout, taps)}
+    etag = tag[:-1] if tag.endswith("d") and tag[:-1] in _ENC_LAYERS else tag
+    if sym in ("mv_tapgemm", "mv_wgrad", "mv_wgrad_slice") and etag in _ENC_LAYERS:
+        H, cin, cout, taps = _ENC_LAYERS[etag]
+        if sym == "mv_wgrad_slice":
+            cout = 128
+        return {"bound": "tensor", "work": 2.0 * B * H * H * cin * cout * taps, "layer": (H, cin, cout, taps)}
     if sym == "mv_moe_lpx_fwd":
         # read recon (bf16) once + targets (fp32) once, write lpx
         return {"bound": "hbm", "work": rows * D * 2 + B * D * 4 + rows * 4}

@@ -22,7 +22,9 @@ def test_conv_weight_gradient(n_img, H, cin, cout, k):
     X, g = HL.to_halo(x)
     G, _ = HL.to_halo(gy)
     taps = g.taps3x3() if k == 3 else [0]
-    dW = HL.wgrad(X, G, k * k, taps, g.P)
+    dW, db = HL.wgrad(X, G, k * k, taps, g.P, want_db=True)
+    ref_db = gy.float().sum((0, 2, 3))
+    assert float((db - ref_db).abs().max()) / float(ref_db.abs().max()) < 2e-3
     w = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
     F.conv2d(x.float(), w, padding=k // 2).backward(gy.float())
     got = HL.unpack_conv_wgrad(dW, k, k)
