@@ -1,0 +1,483 @@
+// 3x3 / stride-1 / pad-1 convolution with 64 output channels on tcgen05, "three taps per MMA" formulation
+// (the dominant shape of the PolyMNIST ResNet decoders/encoders: ResnetBlock(64, 64) at 28x28 and the 64-channel
+// convolutions at 14x14; forward and data gradient — reference models/nn/mmnist.py:229-241).
+//
+// mv_tapgemm issues one M=128 x N=64 x K=16 MMA per (tap, 16 channels): 36 MMAs per 64-channel chunk, and every one of
+// them re-reads its 128 x 16 A tile (4 KB) from shared memory.  Measured on B200 (tests/cuda/mma_rate.cu) an SS-mode
+// MMA costs max(N/2, (4 KB + N*32 B) / 128 B per cycle) cycles, i.e. 51 cycles at N = 64 where the math needs 32:
+// the shape is bound by the shared-memory operand fetch.  Here the three taps of one filter ROW share the A tile:
+//
+//   E_s[q, n] = sum_r sum_c A[q + (r-1)*Wp, c] * W[r, s, n, c]        one MMA of N = 3 x 64 = 192 per (r, 16 channels)
+//   out[p, n] = E_0[p-1, n] + E_1[p, n] + E_2[p+1, n]                   +-1 row shift-add in the epilogue
+//
+// 12 MMAs of 96 cycles (math-bound) instead of 36 of 51, and 44 % less operand traffic.  The +-1 row shift crosses
+// TMEM lanes: inside a warp's lane quarter it is a warp shuffle, across quarters the boundary rows travel through a
+// small shared-memory exchange, and across tiles the tiles simply overlap by one row on each side (a tile of 128 MMA
+// rows owns 126 output rows).  Side inputs (residual / activation-derivative source) arrive as TMA tiles through their own
+// ring, outputs leave through a swizzled staging tile and ONE 126-row TMA store per output: a thread owns one row, so
+// direct global accesses would touch 32 different 128-byte lines per warp instruction (measured: one extra 32-byte
+// access per thread costs ~750 cycles per tile in the L1 pipeline).
+//
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocation, warp 3 side-tile TMA producer,
+// warps 4-19 epilogue
+// (TMEM lane quarter = warp % 4; the four warps of a quarter take 16 output columns each).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace mv {
+
+using bf16 = __nv_bfloat16;
+int num_sms();
+
+__device__ long long g_c3_clk[4];   // experiment counter: cycles / tiles of CTA 0's MMA warp (MV_TG_DBG != 0)
+
+constexpr int kC3Threads = 640;
+constexpr int kC3EpiWarps = 16;
+constexpr int kC3OutRows = 126;
+constexpr int kC3MaxStages = 4;
+constexpr int kC3MaxSide = 3;
+constexpr int kC3N = 192;
+constexpr uint32_t kC3WBox = 192u * 128u;   // one filter row of weights: 3 taps x 64 output channels x 64 input channels
+
+enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_GENERIC = 0x80000000u };
+
+struct Conv3Params {
+  int P, m_tiles, n_kc, row_shift, R;
+  int in_stages;
+  uint32_t in_stage_bytes, w_bytes;
+  const float* bias;
+  float neg, alpha, slope1;
+  int side_stages, n_out;
+  int img_stride, Wp, W, n_img;
+  uint32_t flags;
+  int dbg;
+};
+
+template <uint32_t F>
+__device__ __forceinline__ bool c3_has(const Conv3Params& p, uint32_t bit) {
+  return (F & C3_GENERIC) ? (p.flags & bit) != 0 : (F & bit) != 0;
+}
+
+__device__ __forceinline__ int c3_fast_div(int a, int d, float inv_d) {
+  int q = int(float(a) * inv_d);
+  int r = a - q * d;
+  q += (r >= d) - (r < 0);
+  r = a - q * d;
+  q += (r >= d) - (r < 0);
+  return q;
+}
+
+struct U8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ U8 ldg32(const void* p) {   // 256-bit read-once load
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg32(void* p, const U8& r) {   // 256-bit streaming store
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+
+template <uint32_t F>
+__global__ void __launch_bounds__(kC3Threads, 1)
+conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
+             const __grid_constant__ CUtensorMap tmS, const __grid_constant__ Conv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* in_base = smem;
+  uint8_t* w_base = in_base + size_t(p.in_stages) * p.in_stage_bytes;
+  uint8_t* stg_base = w_base + p.w_bytes;                        // n_out staging tiles of 128 rows x 128 B (SWIZZLE_128B)
+  uint8_t* side_base = stg_base + size_t(p.n_out) * 16384;      // side_stages tiles of 128 rows x 128 B
+  float* xchg = reinterpret_cast<float*>(side_base + size_t(p.side_stages) * 16384);   // [2 parities][4 quarters][2][64]
+  float* s_bias = xchg + 2 * 4 * 2 * 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint64_t* in_full = bars;
+  uint64_t* in_empty = in_full + kC3MaxStages;
+  uint64_t* w_full = in_empty + kC3MaxStages;
+  uint64_t* tm_full = w_full + 1;
+  uint64_t* tm_empty = tm_full + 2;
+  uint64_t* side_full = tm_empty + 2;
+  uint64_t* side_empty = side_full + kC3MaxSide;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + kC3MaxSide);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
+    tc::mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kC3EpiWarps); }
+    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], kC3EpiWarps); }
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmW);
+  }
+  if (threadIdx.x >= 128 && threadIdx.x < 192) {
+    const int j = threadIdx.x - 128;
+    s_bias[j] = (p.flags & C3_BIAS) ? p.bias[j] : 0.f;
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(w_full, p.w_bytes);
+      for (int kc = 0; kc < p.n_kc; ++kc)
+        for (int r = 0; r < 3; ++r)
+          tc::tma_load_2d(w_base + size_t(kc * 3 + r) * kC3WBox, &tmW, w_full, kc * 64, r * kC3N);
+    }
+    __syncwarp();
+    int is = 0, iph = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      const int p0 = tile * kC3OutRows - 1;
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        tc::mbar_wait(&in_empty[is], iph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * 128u);
+          tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], kc * 64, p0 - p.row_shift);
+        }
+        __syncwarp();
+        if (++is == p.in_stages) { is = 0; iph ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= TMA producer: side-input tiles (rows [p0, p0 + 128) x 64 columns), their own ring =================
+    if (p.side_stages > 0) {
+      int ss = 0, sph = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        tc::mbar_wait(&side_empty[ss], sph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&side_full[ss], 16384u);
+          tc::tma_load_2d(side_base + size_t(ss) * 16384, &tmS, &side_full[ss], 0, tile * kC3OutRows - 1);
+        }
+        __syncwarp();
+        if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: 3 filter rows x 4 K steps per 64-channel chunk, N = 192 =================
+    const uint32_t idesc = tc::idesc_bf16(128, kC3N, 0, 0);
+    const uint64_t desc0 = tc::smem_desc(0, 16, 1024, tc::SW_128);
+    const uint32_t desc_hi = uint32_t(desc0 >> 32);
+    const uint32_t desc_lo = uint32_t(desc0);
+    const uint32_t a_rstep = (uint32_t(p.row_shift) * 128u) >> 4;
+    const uint32_t w_lo0 = desc_lo | ((tc::smem_u32(w_base) & 0x3FFFFu) >> 4);
+    tc::mbar_wait(w_full, 0);
+    tc::fence_after_sync();
+    int is = 0, iph = 0, it = 0;
+    const long long clk0 = clock64();
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1, acc_ph = (it >> 1) & 1;
+      tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
+      tc::fence_after_sync();
+      const uint32_t tmem_d = tmem_base + uint32_t(acc * 256);
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        tc::mbar_wait(&in_full[is], iph);
+        tc::fence_after_sync();
+        const uint32_t a_lo0 = desc_lo | ((tc::smem_u32(in_base + size_t(is) * p.in_stage_bytes) & 0x3FFFFu) >> 4);
+        const uint32_t b_lo0 = w_lo0 + uint32_t(kc * 3) * (kC3WBox >> 4);
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo0 + uint32_t(r) * a_rstep + 2u * k);
+              const uint64_t bd = (uint64_t(desc_hi) << 32) | (b_lo0 + uint32_t(r) * (kC3WBox >> 4) + 2u * k);
+              tc::umma_bf16(tmem_d, ad, bd, idesc, (kc | r | k) != 0);
+            }
+          }
+          tc::umma_commit(&in_empty[is]);
+        }
+        __syncwarp();
+        if (++is == p.in_stages) { is = 0; iph ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit(&tm_full[acc]);
+      __syncwarp();
+    }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { g_c3_clk[0] = clock64() - clk0; g_c3_clk[1] = it; }
+  } else if (warp >= 4) {
+    // ================= epilogue (warps 4..19) =================
+    // 16 warps: TMEM lane quarter q = warp % 4, column chunk cc = 16 output columns.  Many warps with little work each:
+    // the epilogue is a dependent chain (TMEM load -> shuffle -> add -> activation -> pack -> store), so the issue slots
+    // are filled by thread-level parallelism, not by unrolling.
+    const int ew = warp - 4;
+    const int q = ew & 3;
+    const int c0 = (ew >> 2) * 16;
+    const bool has_side = c3_has<F>(p, C3_RES) || c3_has<F>(p, C3_DACT1);
+    const uint32_t xchg_s = tc::smem_u32(xchg);
+    // alpha and the bias are folded into one FMA per element: alpha * act(acc + b) = act(alpha * acc + alpha * b) for alpha > 0
+    float ab[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) ab[e] = c3_has<F>(p, C3_BIAS) ? p.alpha * s_bias[c0 + e] : 0.f;
+    // Row geometry without divisions in the tile loop: this thread's row advances by a constant number of rows per tile,
+    // so (row mod S) and (row mod Wp) are carried incrementally (S is a multiple of Wp, so the wrap of the first does not
+    // disturb the second).
+    const int rloc = q * 32 + lane;
+    const bool inner = rloc >= 1 && rloc <= kC3OutRows;   // rows 0 and 127 of the MMA tile belong to the neighbouring tiles
+    int row = int(blockIdx.x) * kC3OutRows - 1 + rloc;
+    const int S = p.img_stride > 0 ? p.img_stride : 1, Wp = p.img_stride > 0 ? p.Wp : 1;
+    const int d_row = int(gridDim.x) * kC3OutRows;
+    const int d_S = d_row % S, d_W = d_row % Wp;
+    int rS = ((row % S) + S) % S, rW = ((row % Wp) + Wp) % Wp;
+    const float inv_alpha = 1.f / p.alpha;
+    const int row_end = p.img_stride > 0 ? (p.n_img * p.img_stride < p.P ? p.n_img * p.img_stride : p.P) : p.P;
+    // staging tile addressing: owned row rloc (1..126) sits in staging row rloc - 1, so that ONE 126-row TMA store per
+    // output moves the tile; 16-byte chunk j of a row r lands at chunk j ^ (r & 7) (SWIZZLE_128B)
+    const int srow = rloc - 1;
+    const uint32_t stg_s = tc::smem_u32(stg_base);
+    const uint32_t o_off0 = uint32_t(srow & 127) * 128u + (uint32_t(((c0 >> 3) + 0) ^ (srow & 7)) << 4);
+    const uint32_t o_off1 = uint32_t(srow & 127) * 128u + (uint32_t(((c0 >> 3) + 1) ^ (srow & 7)) << 4);
+    const uint32_t s_off0 = uint32_t(rloc) * 128u + (uint32_t(((c0 >> 3) + 0) ^ (rloc & 7)) << 4);   // side tiles: row rloc
+    const uint32_t s_off1 = uint32_t(rloc) * 128u + (uint32_t(((c0 >> 3) + 1) ^ (rloc & 7)) << 4);
+    const uint32_t side_s = tc::smem_u32(side_base);
+    const bool leader = threadIdx.x == 128;   // issues the TMA stores
+    int it = 0, ss = 0, sph = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1, acc_ph = (it >> 1) & 1;
+      const bool valid = p.img_stride > 0 ? (inner && row < row_end && rS >= Wp && rW < p.W) : (inner && row < p.P);
+      const uint32_t xw = xchg_s + uint32_t(it & 1) * 2048u;   // [4 quarters][2: E0 of lane 31 | E2 of lane 0][64 columns] floats
+      tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + uint32_t(acc * 256) + (uint32_t(q * 32) << 16) + uint32_t(c0);
+      uint32_t e0[16], e1[16], e2[16];
+      tc::tmem_ld_32x16(taddr, e0);
+      tc::tmem_ld_32x16(taddr + 64, e1);
+      tc::tmem_ld_32x16(taddr + 128, e2);
+      tc::tmem_ld_wait();
+      // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
+      // rows the neighbouring lane quarters need: E0 of lane 31 (for the quarter below), E2 of lane 0 (for the one above)
+      if (lane == 31) {
+        const uint32_t dst = xw + uint32_t((q * 2 + 0) * 64 + c0) * 4u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e0[4 * g]), "r"(e0[4 * g + 1]), "r"(e0[4 * g + 2]),
+                       "r"(e0[4 * g + 3]) : "memory");
+      }
+      if (lane == 0) {
+        const uint32_t dst = xw + uint32_t((q * 2 + 1) * 64 + c0) * 4u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e2[4 * g]), "r"(e2[4 * g + 1]), "r"(e2[4 * g + 2]),
+                       "r"(e2[4 * g + 3]) : "memory");
+      }
+      // the previous tile's TMA stores must have finished READING the staging tiles before they are rewritten below
+      if (leader && it > 0) tc::tma_store_wait_read<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kC3EpiWarps) : "memory");
+      float y[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[e]), 1);
+        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[e]), 1);
+        y[e] = (up + __uint_as_float(e1[e])) + dn;
+      }
+      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+        // boundary lanes: the shuffled-in term came from the lane itself; replace it by the neighbouring quarter's row
+        const uint32_t src = lane == 0 ? xw + uint32_t(((q - 1) * 2 + 0) * 64 + c0) * 4u : xw + uint32_t(((q + 1) * 2 + 1) * 64 + c0) * 4u;
+        const uint32_t* own = lane == 0 ? e0 : e2;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t a, b, c, d;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src + 16u * g) : "memory");
+          y[4 * g + 0] += __uint_as_float(a) - __uint_as_float(own[4 * g + 0]);
+          y[4 * g + 1] += __uint_as_float(b) - __uint_as_float(own[4 * g + 1]);
+          y[4 * g + 2] += __uint_as_float(c) - __uint_as_float(own[4 * g + 2]);
+          y[4 * g + 3] += __uint_as_float(d) - __uint_as_float(own[4 * g + 3]);
+        }
+      }
+      // side input of this row: 16 columns from the TMA tile
+      uint32_t sv[8];
+      if (has_side) {
+        tc::mbar_wait(&side_full[ss], uint32_t(sph));
+        const uint32_t sb = side_s + uint32_t(ss) * 16384u;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]) : "r"(sb + s_off0) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]), "=r"(sv[7]) : "r"(sb + s_off1) : "memory");
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&side_empty[ss]);
+        if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sv[e] = 0u;
+      }
+      const float vz = valid ? 1.f : 0.f;   // halo positions: the layout invariant is zeros
+      const float al = valid ? p.alpha : 0.f;
+      uint32_t o[8], o2[8];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        y[e] = fmaf(al, y[e], vz * ab[e]);
+        y[e] = fmaxf(y[e], p.neg * y[e]);   // none / relu / leaky-relu as one max: slope `neg` is 1 / 0 / 0.2
+      }
+      if (c3_has<F>(p, C3_DACT1)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          y[2 * i] *= bf16lo(sv[i]) > 0.f ? 1.f : p.slope1;
+          y[2 * i + 1] *= bf16hi(sv[i]) > 0.f ? 1.f : p.slope1;
+        }
+      }
+      if (c3_has<F>(p, C3_OUT2)) {
+        // second output = the un-scaled activation y / alpha (the saved `d` of the ResnetBlock)
+        const float ia = valid ? inv_alpha : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o2[i] = pack_bf16(ia * y[2 * i], ia * y[2 * i + 1]);
+      }
+      if (c3_has<F>(p, C3_RES)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i] + vz * bf16lo(sv[i]), y[2 * i + 1] + vz * bf16hi(sv[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i], y[2 * i + 1]);
+      }
+      if (inner) {
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + o_off0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + o_off1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+        if (c3_has<F>(p, C3_OUT2)) {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + 16384u + o_off0), "r"(o2[0]), "r"(o2[1]), "r"(o2[2]), "r"(o2[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + 16384u + o_off1), "r"(o2[4]), "r"(o2[5]), "r"(o2[6]), "r"(o2[7]) : "memory");
+        }
+      }
+      tc::fence_proxy_async();
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kC3EpiWarps) : "memory");
+      if (leader) {
+        tc::tma_store_2d(&tmO, stg_base, 0, tile * kC3OutRows);
+        if (c3_has<F>(p, C3_OUT2)) tc::tma_store_2d(&tmO2, stg_base + 16384, 0, tile * kC3OutRows);
+        tc::tma_store_commit();
+      }
+      row += d_row;
+      rS += d_S; rS -= rS >= S ? S : 0;
+      rW += d_W; rW -= rW >= Wp ? Wp : 0;
+    }
+    if (leader) tc::tma_store_wait_all<0>();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+
+constexpr size_t kC3SmemLimit = 232448;
+
+// Launches the three-taps-per-MMA kernel when the call is a 3x3 convolution with 64 output channels in the halo
+// layout (see the eligibility tests); returns MV_OK with *handled = false otherwise.
+int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
+  *handled = false;
+  if (getenv("MV_NO_CONV3")) return MV_OK;
+  if (a->T != 9 || a->N_total != 64 || a->BN != 64 || (a->Cin != 64 && a->Cin != 128) || a->out_mode != 0) return MV_OK;
+  if (a->img_stride <= 0 || a->Wp < 2) return MV_OK;
+  for (int r = 0; r < 3; ++r)
+    for (int s2 = 0; s2 < 3; ++s2)
+      if (a->tap_off[3 * r + s2] != (r - 1) * a->Wp + (s2 - 1)) return MV_OK;
+  if (a->act == MV_ACT_SIGMOID || !(a->alpha > 0.f)) return MV_OK;   // alpha is folded through the (positively homogeneous) activation
+  if (a->out2 && !a->out2_pre) return MV_OK;
+  if (a->res && a->dact1) return MV_OK;
+  if (a->dact2) return MV_OK;
+  auto tma_ok = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 8 == 0); };
+  if (!tma_ok(a->out, a->out_ld) || (a->out2 && !tma_ok(a->out2, a->out2_ld))) return MV_OK;
+  if (a->res && !tma_ok(a->res, a->res_ld)) return MV_OK;
+  if (a->dact1 && !tma_ok(a->dact1, a->dact1_ld)) return MV_OK;
+  if (a->a_ld % 8 != 0 || a->P <= 0 || a->P >= (int64_t(1) << 31) - 256) return MV_OK;
+
+  Conv3Params p{};
+  p.P = int(a->P);
+  p.m_tiles = int((a->P + kC3OutRows - 1) / kC3OutRows);
+  p.n_kc = a->Cin / 64;
+  p.row_shift = a->Wp;
+  p.R = 128 + 2 * a->Wp;
+  if (p.R > 256) return MV_OK;
+  p.in_stage_bytes = (uint32_t(p.R) * 128u + 1023u) & ~1023u;
+  p.w_bytes = uint32_t(p.n_kc) * 3u * kC3WBox;
+  const size_t fixed = 1024 + 2 * 4 * 2 * 64 * 4 + 64 * 4 + (2 * kC3MaxStages + 5 + 2 * kC3MaxSide) * 8 + 16;
+  p.n_out = a->out2 ? 2 : 1;
+  const bool has_side = a->res || a->dact1;
+  // shared-memory plan: weights + staging are fixed; the input ring keeps 3 stages if at all possible, the side ring
+  // takes what is left (2 or 3 tiles)
+  const size_t base = fixed + p.w_bytes + size_t(p.n_out) * 16384;
+  p.side_stages = 0;
+  if (has_side) {
+    p.side_stages = kC3MaxSide;
+    while (p.side_stages > 2 && base + size_t(p.side_stages) * 16384 + 3 * size_t(p.in_stage_bytes) > kC3SmemLimit) --p.side_stages;
+  }
+  if (base + size_t(p.side_stages) * 16384 + 2 * size_t(p.in_stage_bytes) > kC3SmemLimit) return MV_OK;
+  p.in_stages = int((kC3SmemLimit - base - size_t(p.side_stages) * 16384) / p.in_stage_bytes);
+  if (p.in_stages > kC3MaxStages) p.in_stages = kC3MaxStages;
+  if (const char* e = getenv("MV_TG_IN_STAGES")) {
+    int v = atoi(e);
+    if (v >= 1 && v <= p.in_stages) p.in_stages = v;
+  }
+  p.bias = a->bias;
+  p.neg = a->act == MV_ACT_LRELU02 ? 0.2f : (a->act == MV_ACT_RELU ? 0.f : 1.f);
+  p.alpha = a->alpha;
+  p.slope1 = a->slope1;
+  p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.n_img = a->n_img;
+  p.flags = (a->bias ? C3_BIAS : 0u) | (a->res ? C3_RES : 0u) | (a->dact1 ? C3_DACT1 : 0u) | (a->out2 ? C3_OUT2 : 0u);
+  if (const char* e = getenv("MV_TG_DBG")) p.dbg = atoi(e);
+
+  CUtensorMap tmA, tmW;
+  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.R), 64,
+                             CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !tc::make_tmap_2d_bf16(&tmW, a->Wt, uint64_t(9) * 64, uint64_t(a->Cin), uint64_t(a->Cin) * 2, kC3N, 64,
+                             CU_TENSOR_MAP_SWIZZLE_128B)) {
+    mv::set_error("mv_tapgemm(conv3): cuTensorMapEncodeTiled failed");
+    return MV_ERR_CUDA;
+  }
+  CUtensorMap tmO, tmO2 = tmA, tmS = tmA;
+  bool ok = tc::make_tmap_2d_bf16(&tmO, a->out, uint64_t(a->P), 64, uint64_t(a->out_ld) * 2, kC3OutRows, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (ok && a->out2)
+    ok = tc::make_tmap_2d_bf16(&tmO2, a->out2, uint64_t(a->P), 64, uint64_t(a->out2_ld) * 2, kC3OutRows, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (ok && has_side)
+    ok = tc::make_tmap_2d_bf16(&tmS, a->res ? a->res : a->dact1, uint64_t(a->P), 64, uint64_t(a->res ? a->res_ld : a->dact1_ld) * 2, 128,
+                               64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!ok) {
+    mv::set_error("mv_tapgemm(conv3): cuTensorMapEncodeTiled failed for the outputs / side input");
+    return MV_ERR_CUDA;
+  }
+  const size_t smem = base + size_t(p.side_stages) * 16384 + size_t(p.in_stages) * p.in_stage_bytes;
+  const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MV_C3_LAUNCH(FLAGS)                                                                                          \
+  do {                                                                                                               \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      cudaFuncSetAttribute(conv3_kernel<(FLAGS)>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kC3SmemLimit));   \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+    conv3_kernel<(FLAGS)><<<grid, kC3Threads, smem, st>>>(tmA, tmW, tmO, tmO2, tmS, p);                                              \
+  } while (0)
+  switch (p.flags) {
+    case C3_BIAS: MV_C3_LAUNCH(C3_BIAS); break;
+    case C3_BIAS | C3_RES | C3_OUT2: MV_C3_LAUNCH(C3_BIAS | C3_RES | C3_OUT2); break;
+    case C3_DACT1: MV_C3_LAUNCH(C3_DACT1); break;
+    case C3_RES: MV_C3_LAUNCH(C3_RES); break;
+    default: MV_C3_LAUNCH(C3_GENERIC); break;
+  }
+#undef MV_C3_LAUNCH
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    mv::set_error("mv_tapgemm(conv3): CUDA error %s", cudaGetErrorString(e));
+    return MV_ERR_CUDA;
+  }
+  mv::count_launch();
+  *handled = true;
+  return MV_OK;
+}
+
+}  // namespace mv
+
+extern "C" int mv_debug_c3_clk(long long* cycles, long long* tiles) {
+  long long h[4];
+  if (cudaMemcpyFromSymbol(h, mv::g_c3_clk, sizeof(h)) != cudaSuccess) return MV_ERR_CUDA;
+  *cycles = h[0];
+  *tiles = h[1];
+  return MV_OK;
+}

@@ -28,9 +28,12 @@ namespace mv {
 
 using bf16 = __nv_bfloat16;
 
+__device__ long long g_tg_clk[4];   // experiment: SM cycles the MMA warp of CTA 0 spent in its tile loop
+
 constexpr int kMaxTaps = 9;
 constexpr int kMaxInStages = 3;
 constexpr int kMaxWStages = 20;
+constexpr int kMaxSideStages = 3;
 constexpr int kBM = 128;
 
 struct TapGemmParams {
@@ -64,6 +67,9 @@ struct TapGemmParams {
   uint32_t epi_flags;       // EF_* bits describing which epilogue terms are present
   int side_tma;             // the primary side input (res, else dact1, else dact2) arrives as TMA tiles in shared memory
   int side_kind;            // 0 res, 1 dact1, 2 dact2
+  int n_out;                // staged outputs (1 or 2)
+  int side_stages;          // ring depth of the side-input tiles (0: no TMA side input)
+  int dbg;                  // experiment switches (MV_TG_DBG): 1 skip epilogue body, 2 skip MMA issue, 4 skip TMA stores
 };
 
 
@@ -81,8 +87,10 @@ __device__ __forceinline__ uint4 ldg16(const bf16* p) {
   return r;
 }
 
-constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter, interleaved over column chunks
-constexpr int kThreads = 64 + 32 * kEpiWarps;     // producer warp + MMA warp + epilogue warps
+// Warp roles (256 threads): warp 0 input/weight TMA producer, warp 1 MMA issuer, warp 2 side-input TMA producer,
+// warp 3 owns the TMEM allocation, warps 4-7 epilogue (warp % 4 = TMEM lane quarter).
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 256;
 
 // Epilogue variants are compile-time flag sets (the runtime-flag version cost ~90 instructions per column).
 enum : uint32_t {
@@ -100,6 +108,17 @@ struct RowCtx {
   int img, y, x;
 };
 
+// a / d for 0 <= a < 2^31, d > 0 with a float reciprocal estimate and an exact correction (no integer division
+// in the per-tile path)
+__device__ __forceinline__ int fast_div(int a, int d, float inv_d) {
+  int q = int(float(a) * inv_d);
+  int r = a - q * d;
+  q += (r >= d) - (r < 0);
+  r = a - q * d;
+  q += (r >= d) - (r < 0);
+  return q;
+}
+
 // Side inputs (residual / activation-derivative sources).  The primary one arrives as TMA tiles in shared
 // memory with the same swizzled layout as the output staging tile; others are read from global memory.
 __device__ __forceinline__ uint32_t tile_off(int col, int rloc) {
@@ -107,6 +126,7 @@ __device__ __forceinline__ uint32_t tile_off(int col, int rloc) {
 }
 __device__ __forceinline__ uint4 side_vec(const TapGemmParams& p, const uint8_t* side_tile, int kind, int col, int n,
                                           const RowCtx& r) {
+  if (p.dbg & 64) return make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
   if (side_tile && p.side_kind == kind) return *reinterpret_cast<const uint4*>(side_tile + tile_off(col, r.rloc));
   const bf16* base = kind == 0 ? p.res + size_t(r.row) * p.res_ld
                                : (kind == 1 ? p.dact1 + size_t(r.row) * p.dact1_ld : p.dact2 + size_t(r.row) * p.dact2_ld);
@@ -184,8 +204,10 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
     } else if (st_out) {
       // staging tile: 64-column boxes of 128 rows x 128 B, SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7))
       const uint32_t off = tile_off(cb + g * 8, r.rloc);
-      *reinterpret_cast<uint4*>(st_out + off) = pack8(o);
-      if (two) *reinterpret_cast<uint4*>(st_out2 + off) = pack8(o2);
+      if (!(p.dbg & 128) || o[0] == 123.456f) {
+        *reinterpret_cast<uint4*>(st_out + off) = pack8(o);
+        if (two) *reinterpret_cast<uint4*>(st_out2 + off) = pack8(o2);
+      }
     } else if (r.row < p.P) {
       *reinterpret_cast<uint4*>(p.out + size_t(r.row) * p.out_ld + nn) = pack8(o);
       if (two) *reinterpret_cast<uint4*>(p.out2 + size_t(r.row) * p.out2_ld + nn) = pack8(o2);
@@ -193,49 +215,32 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
   }
 }
 
-// The epilogue of one tile for one warp (its TMEM lane quarter, every second column chunk).
+// The epilogue of one tile for one warp: its TMEM lane quarter (32 rows), all BN columns in chunks of CW.
 template <int BN, uint32_t F>
-__device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half,
-                                         uint32_t taddr, uint64_t* full_bar, uint32_t full_parity, float neg, uint8_t* stg_base,
-                                         int et, const uint8_t* side_tile, uint64_t* side_full, uint32_t side_parity) {
+__device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, uint32_t taddr,
+                                         float neg, uint8_t* st_out, uint8_t* st_out2, const uint8_t* side_tile) {
   constexpr int CW = BN >= 32 ? 32 : 16;
   constexpr int NCH = BN / CW;
-  tc::mbar_wait(full_bar, full_parity);
-  tc::fence_after_sync();
-  if (side_tile) tc::mbar_wait(side_full, side_parity);
-  uint8_t* st_out = nullptr;
-  uint8_t* st_out2 = nullptr;
-  if (p.use_tma_store) {
-    // the previous tile's TMA store must have finished READING the staging tile before it is rewritten
-    if (et == 0) tc::tma_store_wait_read<0>();
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-    st_out = stg_base;
-    st_out2 = stg_base + p.stage_out_bytes;
-  }
 #pragma unroll
-  for (int ch = half; ch < NCH; ch += 2) {
+  for (int ch = 0; ch < NCH; ++ch) {
     uint32_t v[32];
-    if (CW == 32) tc::tmem_ld_32x32(taddr + ch * CW, v);
-    else tc::tmem_ld_32x16(taddr + ch * CW, v);
-    tc::tmem_ld_wait();
+    if (p.dbg & 256) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = 0x3f800000u + e;
+    } else {
+      if (CW == 32) tc::tmem_ld_32x32(taddr + ch * CW, v);
+      else tc::tmem_ld_32x16(taddr + ch * CW, v);
+      tc::tmem_ld_wait();
+    }
     epi_apply<CW, F>(p, v, side_tile, s_bias, ch * CW, n0 + ch * CW, r, neg, st_out, st_out2);
   }
-}
-
-// rarely used flag combinations: one out-of-line copy so that its register needs do not tax the hot variants
-template <int BN>
-__device__ __noinline__ void epi_tile_generic(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half,
-                                              uint32_t taddr, uint64_t* full_bar, uint32_t full_parity, float neg,
-                                              uint8_t* stg_base, int et, const uint8_t* side_tile, uint64_t* side_full,
-                                              uint32_t side_parity) {
-  epi_tile<BN, EF_GENERIC>(p, r, s_bias, n0, half, taddr, full_bar, full_parity, neg, stg_base, et, side_tile, side_full, side_parity);
 }
 
 template <int CK, int BN, int TT>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
-               const __grid_constant__ CUtensorMap tmS, const TapGemmParams p) {
+               const __grid_constant__ CUtensorMap tmS, const __grid_constant__ TapGemmParams p) {
   constexpr uint32_t ROWB = CK * 2;            // bytes per shared-memory row (one pixel, CK channels)
   constexpr int KSTEPS = CK / 16;              // UMMA K = 16 for bf16
   constexpr uint32_t SWZ = CK == 64 ? tc::SW_128 : tc::SW_32;
@@ -245,8 +250,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* in_base = smem;
   uint8_t* w_base = smem + size_t(p.in_stages) * p.in_stage_bytes;
   uint8_t* stg_base = w_base + ((size_t(p.w_stages) * p.w_stage_bytes + 1023) & ~size_t(1023));
-  uint8_t* side_base = stg_base + (p.use_tma_store ? 2 * size_t(p.stage_out_bytes) : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(side_base + (p.side_tma ? 2 * size_t(p.stage_out_bytes) : 0));
+  uint8_t* side_base = stg_base + (p.use_tma_store ? size_t(p.n_out) * p.stage_out_bytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_base + size_t(p.side_stages) * p.stage_out_bytes);
   uint64_t* in_full = bars;
   uint64_t* in_empty = in_full + kMaxInStages;
   uint64_t* w_full = in_empty + kMaxInStages;
@@ -254,9 +259,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tm_full = w_empty + kMaxWStages;
   uint64_t* tm_empty = tm_full + 2;
   uint64_t* side_full = tm_empty + 2;
-  uint64_t* side_empty = side_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  uint64_t* side_empty = side_full + kMaxSideStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + kMaxSideStages);
+  float* s_bias_all = reinterpret_cast<float*>(tmem_slot + 4);   // one private copy of the tile's bias slice per epilogue warp
   const int T = TT > 0 ? TT : p.T;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,12 +269,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < p.w_stages; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kEpiWarps); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], kEpiWarps); }
+    for (int i = 0; i < kMaxSideStages; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], kEpiWarps); }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 3) tc::tmem_alloc(tmem_slot, p.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -277,7 +282,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles_total = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer: input windows + weights =================
     // The whole warp runs the loop (warp-uniform control flow keeps addresses and coordinates in uniform
     // registers); one elected lane arms the barrier and issues the copy.
     int is = 0, iph = 0, ws = 0, wph = 0;
@@ -291,23 +296,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
     }
-    int pit = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++pit) {
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
-      if (p.side_tma) {
-        // side-input tile of this output tile (consumed by the epilogue two tiles behind the producer at most)
-        const int ss = pit & 1, sph = (pit >> 1) & 1;
-        tc::mbar_wait(&side_empty[ss], sph ^ 1);
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(&side_full[ss], p.stage_out_bytes);
-#pragma unroll
-          for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b)
-            tc::tma_load_2d(side_base + size_t(ss) * p.stage_out_bytes + b * 16384, &tmS, &side_full[ss], n0 + b * 64, p0);
-        }
-        __syncwarp();
-      }
       for (int kc = 0; kc < p.n_kc; ++kc) {
-        tc::mbar_wait(&in_empty[is], iph ^ 1);
+        if (p.dbg & 16) tc::mbar_wait_relaxed(&in_empty[is], iph ^ 1); else tc::mbar_wait(&in_empty[is], iph ^ 1);
         if (tc::elect_one()) {
           tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * ROWB);
           tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], kc * CK, p0 - p.halo_lo);
@@ -327,6 +319,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (warp == 2) {
+    // ================= TMA producer: side-input tiles (their own ring, decoupled from the input prefetch) =====
+    if (p.side_stages > 0) {
+      int ss = 0, sph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+        if (p.dbg & 16) tc::mbar_wait_relaxed(&side_empty[ss], sph ^ 1); else tc::mbar_wait(&side_empty[ss], sph ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&side_full[ss], p.stage_out_bytes);
+#pragma unroll
+          for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b)
+            tc::tma_load_2d(side_base + size_t(ss) * p.stage_out_bytes + b * 16384, &tmS, &side_full[ss], n0 + b * 64, p0);
+        }
+        __syncwarp();
+        if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
+      }
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     // Warp-uniform loop, one elected lane issues.  The 64-bit shared-memory descriptors differ only in
@@ -341,6 +350,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int t = 0; t < TU; ++t) tap_lo[t] = uint32_t(int(p.halo_lo + p.tap_off[t]) * int(ROWB)) >> 4;
     int is = 0, iph = 0, ws = 0, wph = 0, it = 0;
+    const long long clk0 = clock64();
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
       tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
@@ -357,7 +367,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           const uint32_t b_lo0 = desc_lo_const | ((tc::smem_u32(w_base + size_t(kc * T) * p.w_stage_bytes) & 0x3FFFFu) >> 4);
           const uint32_t b_step = p.w_stage_bytes >> 4;
-          if (tc::elect_one()) {
+          if (tc::elect_one() && !(p.dbg & 2)) {
             if (TT > 0) {
 #pragma unroll
               for (int t = 0; t < TU; ++t) {
@@ -412,18 +422,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tc::elect_one()) tc::umma_commit(&tm_full[acc]);
       __syncwarp();
     }
-  } else {
-    // ================= epilogue (warps 2..9) =================
-    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter split the tile's column
-    // chunks.  The CTA uses (almost) all shared memory, so there is no L1 and every global load is an L2
-    // round trip: bias sits in shared memory and the side inputs of a chunk are fetched one chunk ahead
-    // (the first one before the wait on the accumulator barrier), so their latency hides behind the MMAs.
-    // Outputs go to a swizzled staging tile and leave with one TMA store per 64-column box.
+    if (p.dbg && blockIdx.x == 0 && lane == 0) { g_tg_clk[0] = clock64() - clk0; g_tg_clk[1] = it; }
+  } else if (warp >= 4) {
+    // ================= epilogue (warps 4..7) =================
+    // Each warp owns one TMEM lane quarter = 32 rows of the tile and is self-contained: its own copy of the bias
+    // slice, its own 32-row slab of the (swizzled) staging tile and its own TMA stores / bulk groups, so the four
+    // warps never meet at a CTA barrier.  The CTA uses (almost) all shared memory, so there is no L1: side inputs
+    // arrive as TMA tiles, bias sits in shared memory.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;             // 0 or 1
-    const int et = threadIdx.x - 64;
+    float* s_bias = s_bias_all + q * (BN < 32 ? 32 : BN);
     const float neg = p.act == MV_ACT_LRELU02 ? 0.2f : (p.act == MV_ACT_RELU ? 0.f : 1.f);
-    int it = 0;
+    const float inv_S = p.img_stride > 0 ? 1.f / float(p.img_stride) : 0.f;
+    const float inv_Wp = p.Wp > 0 ? 1.f / float(p.Wp) : 0.f;
+    const bool two = (p.epi_flags & (EF_OUT2_PRE | EF_OUT2_POST)) != 0;
+    uint8_t* st_out = p.use_tma_store ? stg_base : nullptr;
+    uint8_t* st_out2 = p.use_tma_store ? stg_base + p.stage_out_bytes : nullptr;
+    int it = 0, ss = 0, sph = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
@@ -433,63 +447,70 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       r.valid = r.row < p.P;
       r.img = 0; r.y = 0; r.x = 0;
       if (p.img_stride > 0) {
-        r.img = r.row / p.img_stride;
+        r.img = fast_div(r.row, p.img_stride, inv_S);
         const int rr = r.row - r.img * p.img_stride;
-        r.y = rr / p.Wp;
+        r.y = fast_div(rr, p.Wp, inv_Wp);
         r.x = rr - r.y * p.Wp;
         r.valid = r.valid && r.img < p.n_img && r.y >= 1 && r.x < p.W;
       }
       if ((p.epi_flags & EF_BIAS) && (it == 0 || p.n_tiles > 1)) {
-        if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        if (et < BN) s_bias[et] = p.bias[n0 + et];
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        __syncwarp();
+        for (int j = lane; j < BN; j += 32) s_bias[j] = p.bias[n0 + j];
+        __syncwarp();
       }
       const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
-      const uint8_t* side_tile = p.side_tma ? side_base + size_t(acc) * p.stage_out_bytes : nullptr;
-#define MV_EPI(FLAGS)                                                                                                 \
-  epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et, side_tile, \
-                        &side_full[acc], uint32_t(acc_ph))
-      switch (p.epi_flags) {
-        case 0u: MV_EPI(0u); break;
-        case EF_BIAS: MV_EPI(EF_BIAS); break;
-        case EF_BIAS | EF_RES | EF_OUT2_PRE: MV_EPI(EF_BIAS | EF_RES | EF_OUT2_PRE); break;
-        case EF_DACT1: MV_EPI(EF_DACT1); break;
-        case EF_RES: MV_EPI(EF_RES); break;
-        case EF_OUT2_POST | EF_DACT2: MV_EPI(EF_OUT2_POST | EF_DACT2); break;
-        case EF_BIAS | EF_NCHW: MV_EPI(EF_BIAS | EF_NCHW); break;
-        default:
-          epi_tile_generic<BN>(p, r, s_bias, n0, half, taddr, &tm_full[acc], uint32_t(acc_ph), neg, stg_base, et, side_tile,
-                               &side_full[acc], uint32_t(acc_ph));
-          break;
+      const uint8_t* side_tile = p.side_stages > 0 ? side_base + size_t(ss) * p.stage_out_bytes : nullptr;
+      if (p.dbg & 16) tc::mbar_wait_relaxed(&tm_full[acc], uint32_t(acc_ph)); else tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
+      tc::fence_after_sync();
+      if (side_tile) tc::mbar_wait(&side_full[ss], uint32_t(sph));
+      if (p.use_tma_store && it > 0) {
+        // this warp's previous TMA stores must have finished READING its staging slab before it is rewritten
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
       }
+      if (!(p.dbg & 1)) {
+#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, taddr, neg, st_out, st_out2, side_tile)
+        switch (p.epi_flags) {
+          case 0u: MV_EPI(0u); break;
+          case EF_BIAS: MV_EPI(EF_BIAS); break;
+          case EF_BIAS | EF_RES | EF_OUT2_PRE: MV_EPI(EF_BIAS | EF_RES | EF_OUT2_PRE); break;
+          case EF_DACT1: MV_EPI(EF_DACT1); break;
+          case EF_RES: MV_EPI(EF_RES); break;
+          case EF_OUT2_POST | EF_DACT2: MV_EPI(EF_OUT2_POST | EF_DACT2); break;
+          case EF_BIAS | EF_NCHW: MV_EPI(EF_BIAS | EF_NCHW); break;
+          default: MV_EPI(EF_GENERIC); break;
+        }
 #undef MV_EPI
-      // accumulator drained: hand the TMEM buffer (and the side tile) back before the stores go out
+      }
+      // accumulator drained and side tile consumed: hand both back before the stores go out
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(&tm_empty[acc]);
-        if (p.side_tma) tc::mbar_arrive(&side_empty[acc]);
+        if (side_tile) tc::mbar_arrive(&side_empty[ss]);
       }
-      if (p.use_tma_store) {
+      if (side_tile && ++ss == p.side_stages) { ss = 0; sph ^= 1; }
+      if (p.use_tma_store && !(p.dbg & 5)) {
         tc::fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        if (et == 0) {
+        __syncwarp();
+        if (lane == 0) {
 #pragma unroll
           for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b) {
-            tc::tma_store_2d(&tmO, stg_base + b * 16384, n0 + b * 64, p0);
-            if (p.epi_flags & (EF_OUT2_PRE | EF_OUT2_POST))
-              tc::tma_store_2d(&tmO2, stg_base + p.stage_out_bytes + b * 16384, n0 + b * 64, p0);
+            tc::tma_store_2d(&tmO, st_out + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
+            if (two) tc::tma_store_2d(&tmO2, st_out2 + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
           }
           tc::tma_store_commit();
         }
       }
     }
-    if (p.use_tma_store && et == 0) tc::tma_store_wait_all<0>();
+    if (p.use_tma_store && lane == 0) tc::tma_store_wait_all<0>();
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 3) tc::tmem_dealloc(tmem_base, p.tmem_cols);
 }
+
+int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled);
 
 static int g_num_sms = 0;
 int num_sms() {
@@ -508,6 +529,14 @@ constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 
 using namespace mv;
 
+extern "C" int mv_debug_tg_clk(long long* cycles, long long* tiles) {
+  long long h[4];
+  if (cudaMemcpyFromSymbol(h, g_tg_clk, sizeof(h)) != cudaSuccess) return MV_ERR_CUDA;
+  *cycles = h[0];
+  *tiles = h[1];
+  return MV_OK;
+}
+
 extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   MV_CHECK_ARG(a && a->A && a->Wt && a->out, "mv_tapgemm: null pointer");
   MV_CHECK_ARG(a->P > 0 && a->Cin > 0 && a->N_total > 0, "mv_tapgemm: bad sizes");
@@ -516,6 +545,12 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   MV_CHECK_ARG(a->Cin % CK == 0 && (CK == 64 || a->Cin == 16), "mv_tapgemm: Cin must be 16 or a multiple of 64, got %d", a->Cin);
   MV_CHECK_ARG(a->BN == 16 || a->BN == 32 || a->BN == 64 || a->BN == 128, "mv_tapgemm: BN must be 16/32/64/128");
   MV_CHECK_ARG(a->N_total % a->BN == 0, "mv_tapgemm: N_total %% BN != 0");
+  {
+    // 3x3 convolutions with 64 output channels: three-taps-per-MMA kernel (tapconv3.cu)
+    bool handled = false;
+    const int rc = mv::conv3_try_launch(a, stream, &handled);
+    if (rc != MV_OK || handled) return rc;
+  }
   MV_CHECK_ARG(a->a_ld % 8 == 0 && (a->out_ld % 8 == 0 || a->out_mode == 1), "mv_tapgemm: leading dimensions must be multiples of 8");
   TapGemmParams p{};
   p.P = int(a->P);
@@ -541,36 +576,53 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
     uint32_t v = uint32_t(atoi(e));
     if (v >= p.in_stage_bytes) p.in_stage_bytes = v & ~1023u;
   }
-  const size_t fixed = 2048 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 8) * 8 + 16 + 128 * 4;
+  const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 4 + 2 * kMaxSideStages) * 8 + 16 +
+                       size_t(kEpiWarps) * (a->BN < 32 ? 32 : a->BN) * 4 /*bias copies*/;
   const int w_tiles = p.T * p.n_kc;
   p.use_tma_store = (a->out_mode == 0 && a->BN >= 64 && a->out_ld % 8 == 0 && (!a->out2 || a->out2_ld % 8 == 0)) ? 1 : 0;
   p.stage_out_bytes = uint32_t(a->BN / 64) * 16384u;
+  p.n_out = a->out2 ? 2 : 1;
   const void* side_ptr = a->res ? a->res : (a->dact1 ? a->dact1 : ((a->out2 && !a->out2_pre) ? a->dact2 : nullptr));
   const int side_ld = a->res ? a->res_ld : (a->dact1 ? a->dact1_ld : a->dact2_ld);
   p.side_kind = a->res ? 0 : (a->dact1 ? 1 : 2);
   p.side_tma = (side_ptr && a->BN >= 64 && side_ld % 8 == 0) ? 1 : 0;
-  const size_t stg = (p.use_tma_store ? 2 * size_t(p.stage_out_bytes) + 1024 : 0) + (p.side_tma ? 2 * size_t(p.stage_out_bytes) : 0);
-  const size_t budget = kSmemLimit - fixed - stg;
-  // weights resident for the whole kernel if they fit next to >= 2 input stages
-  p.w_resident = (p.n_tiles == 1 && w_tiles <= kMaxWStages &&
-                  size_t(w_tiles) * p.w_stage_bytes + 2 * size_t(p.in_stage_bytes) <= budget) ? 1 : 0;
-  if (p.w_resident) {
-    p.w_stages = w_tiles;
-    size_t left = budget - size_t(w_tiles) * p.w_stage_bytes;
-    p.in_stages = int(left / p.in_stage_bytes);
-  } else {
-    p.in_stages = p.n_kc >= 2 ? 3 : 2;
-    size_t left = budget - size_t(p.in_stages) * p.in_stage_bytes;
-    p.w_stages = int(left / p.w_stage_bytes);
-    if (p.w_stages > 8) p.w_stages = 8;
-    MV_CHECK_ARG(p.w_stages >= 2, "mv_tapgemm: not enough shared memory for the weight ring");
+  const size_t out_stg = p.use_tma_store ? size_t(p.n_out) * p.stage_out_bytes : 0;
+  auto round1k = [](size_t v) { return (v + 1023) & ~size_t(1023); };
+  // shared-memory plan: try the deepest side ring first; the input ring keeps 3 stages whenever possible
+  int side_try = p.side_tma ? kMaxSideStages : 0;
+  if (const char* e = getenv("MV_TG_SIDE_STAGES")) {
+    int v = atoi(e);
+    if (p.side_tma && v >= 1 && v <= kMaxSideStages) side_try = v;
   }
+  for (;; --side_try) {
+    const size_t stg = out_stg + size_t(side_try) * p.stage_out_bytes;
+    const size_t budget = kSmemLimit - fixed - stg;
+    // weights resident for the whole kernel if they fit next to the input ring
+    const size_t w_res = round1k(size_t(w_tiles) * p.w_stage_bytes);
+    const bool res_ok = p.n_tiles == 1 && w_tiles <= kMaxWStages && w_res + 2 * size_t(p.in_stage_bytes) <= budget;
+    if (res_ok) {
+      p.w_resident = 1;
+      p.w_stages = w_tiles;
+      p.in_stages = int((budget - w_res) / p.in_stage_bytes);
+    } else {
+      p.w_resident = 0;
+      p.in_stages = p.n_kc >= 2 ? 3 : 2;
+      const size_t in_b = size_t(p.in_stages) * p.in_stage_bytes;
+      p.w_stages = budget > in_b + 1024 ? int((budget - in_b - 1024) / p.w_stage_bytes) : 0;
+      if (p.w_stages > 8) p.w_stages = 8;
+    }
+    const bool deep_enough = p.w_resident ? p.in_stages >= 3 : p.w_stages >= 4;
+    if (deep_enough || side_try <= (p.side_tma ? 2 : 0)) break;
+  }
+  p.side_stages = side_try;
+  MV_CHECK_ARG(p.w_resident || p.w_stages >= 2, "mv_tapgemm: not enough shared memory for the weight ring");
   if (p.in_stages > kMaxInStages) p.in_stages = kMaxInStages;
   if (const char* e = getenv("MV_TG_IN_STAGES")) {
     int v = atoi(e);
     if (v >= 1 && v <= p.in_stages) p.in_stages = v;
   }
   MV_CHECK_ARG(p.in_stages >= 1, "mv_tapgemm: not enough shared memory for one input stage");
+  if (const char* e = getenv("MV_TG_DBG")) p.dbg = atoi(e);
   p.acc_stride = a->BN < 32 ? 32 : a->BN;
   p.tmem_cols = 2 * p.acc_stride;  // 64 / 128 / 256: powers of two
   p.bias = a->bias; p.act = a->act; p.alpha = a->alpha;
@@ -596,10 +648,11 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   }
   CUtensorMap tmO = tmA, tmO2 = tmA;  // placeholders when the direct-store path is used
   if (p.use_tma_store) {
-    bool ok = tc::make_tmap_2d_bf16(&tmO, a->out, uint64_t(a->P), uint64_t(a->N_total), uint64_t(a->out_ld) * 2, 128, 64,
+    // each epilogue warp stores its own 32-row slab
+    bool ok = tc::make_tmap_2d_bf16(&tmO, a->out, uint64_t(a->P), uint64_t(a->N_total), uint64_t(a->out_ld) * 2, 32, 64,
                                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (ok && a->out2)
-      ok = tc::make_tmap_2d_bf16(&tmO2, a->out2, uint64_t(a->P), uint64_t(a->N_total), uint64_t(a->out2_ld) * 2, 128, 64,
+      ok = tc::make_tmap_2d_bf16(&tmO2, a->out2, uint64_t(a->P), uint64_t(a->N_total), uint64_t(a->out2_ld) * 2, 32, 64,
                                  CU_TENSOR_MAP_SWIZZLE_128B);
     if (!ok) {
       mv::set_error("mv_tapgemm: cuTensorMapEncodeTiled failed for the output (out %p ld %d)", a->out, a->out_ld);
@@ -613,7 +666,9 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
     mv::set_error("mv_tapgemm: cuTensorMapEncodeTiled failed for the side input");
     return MV_ERR_CUDA;
   }
-  const size_t smem = fixed + stg + size_t(p.in_stages) * p.in_stage_bytes + size_t(p.w_stages) * p.w_stage_bytes;
+  const size_t smem = fixed + out_stg + size_t(p.side_stages) * p.stage_out_bytes + size_t(p.in_stages) * p.in_stage_bytes +
+                      round1k(size_t(p.w_stages) * p.w_stage_bytes);
+  MV_CHECK_ARG(smem <= kSmemLimit, "mv_tapgemm: shared-memory plan exceeds the limit (%zu bytes)", smem);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);

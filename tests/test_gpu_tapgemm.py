@@ -57,6 +57,38 @@ def test_conv3x3_dgrad_with_activation_derivative(n_img, H, cin, cout):
     _close(HL.from_halo(out, g), ref)
 
 
+@pytest.mark.parametrize("n_img,H,cin", [(37, 28, 64), (301, 28, 64), (23, 14, 128), (9, 14, 64), (5, 7, 64)])
+@pytest.mark.parametrize("variant", ["bias_lrelu", "dact1", "res", "none"])
+def test_conv3x3_cout64_single_side_variants(n_img, H, cin, variant):
+    """The three-taps-per-MMA kernel (csrc/tapconv3.cu) behind mv_tapgemm for 3x3 convolutions with 64 outputs."""
+    from multivae_b200.nn import halo as HL
+    cout = 64
+    x = _rnd(n_img, cin, H, H, seed=21).bfloat16()
+    w = _rnd(cout, cin, 3, 3, seed=22, scale=cin ** -0.5).bfloat16()
+    b = _rnd(cout, seed=23)
+    s = _rnd(n_img, cout, H, H, seed=24).bfloat16()
+    A, g = HL.to_halo(x)
+    S_, _ = HL.to_halo(s)
+    conv = F.conv2d(x.float(), w.float(), padding=1)
+    if variant == "bias_lrelu":
+        out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), cout, g.P, bias=b, act="lrelu", geom=g)
+        ref = F.leaky_relu(conv + b.view(1, -1, 1, 1), 0.2)
+    elif variant == "dact1":
+        out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), cout, g.P, dact1=S_, geom=g)
+        ref = conv * torch.where(s.float() > 0, 1.0, 0.2)
+    elif variant == "res":
+        out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), cout, g.P, res=S_, geom=g)
+        ref = conv + s.float()
+    else:
+        out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), cout, g.P, geom=g)
+        ref = conv
+    _close(HL.from_halo(out, g), ref)
+    mask = torch.ones(g.P, dtype=torch.bool, device="cuda")
+    v = mask[: n_img * g.S].view(n_img, H + 1, g.Wp)
+    v[:, 1:, :H] = False
+    assert float(out[mask].abs().max()) == 0.0
+
+
 def test_conv1x1_and_two_outputs():
     from multivae_b200.nn import halo as HL
     n_img, H, cin, cout = 29, 14, 128, 64
