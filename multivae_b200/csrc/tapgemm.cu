@@ -88,9 +88,10 @@ __device__ __forceinline__ uint4 ldg16(const bf16* p) {
 }
 
 // Warp roles (256 threads): warp 0 input/weight TMA producer, warp 1 MMA issuer, warp 2 side-input TMA producer,
-// warp 3 owns the TMEM allocation, warps 4-7 epilogue (warp % 4 = TMEM lane quarter).
-constexpr int kEpiWarps = 4;
-constexpr int kThreads = 256;
+// warp 3 owns the TMEM allocation, warps 4-11 epilogue (warp % 4 = TMEM lane quarter; the two warps of a quarter split
+// the tile's columns — the epilogue is a latency-bound dependent chain, so it wants warps, not unrolling).
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 384;
 
 // Epilogue variants are compile-time flag sets (the runtime-flag version cost ~90 instructions per column).
 enum : uint32_t {
@@ -126,7 +127,6 @@ __device__ __forceinline__ uint32_t tile_off(int col, int rloc) {
 }
 __device__ __forceinline__ uint4 side_vec(const TapGemmParams& p, const uint8_t* side_tile, int kind, int col, int n,
                                           const RowCtx& r) {
-  if (p.dbg & 64) return make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
   if (side_tile && p.side_kind == kind) return *reinterpret_cast<const uint4*>(side_tile + tile_off(col, r.rloc));
   const bf16* base = kind == 0 ? p.res + size_t(r.row) * p.res_ld
                                : (kind == 1 ? p.dact1 + size_t(r.row) * p.dact1_ld : p.dact2 + size_t(r.row) * p.dact2_ld);
@@ -204,10 +204,8 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
     } else if (st_out) {
       // staging tile: 64-column boxes of 128 rows x 128 B, SWIZZLE_128B (16-byte chunk j of row r at j ^ (r & 7))
       const uint32_t off = tile_off(cb + g * 8, r.rloc);
-      if (!(p.dbg & 128) || o[0] == 123.456f) {
-        *reinterpret_cast<uint4*>(st_out + off) = pack8(o);
-        if (two) *reinterpret_cast<uint4*>(st_out2 + off) = pack8(o2);
-      }
+      *reinterpret_cast<uint4*>(st_out + off) = pack8(o);
+      if (two) *reinterpret_cast<uint4*>(st_out2 + off) = pack8(o2);
     } else if (r.row < p.P) {
       *reinterpret_cast<uint4*>(p.out + size_t(r.row) * p.out_ld + nn) = pack8(o);
       if (two) *reinterpret_cast<uint4*>(p.out2 + size_t(r.row) * p.out2_ld + nn) = pack8(o2);
@@ -215,24 +213,22 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
   }
 }
 
-// The epilogue of one tile for one warp: its TMEM lane quarter (32 rows), all BN columns in chunks of CW.
+// The epilogue of one tile for one warp: its TMEM lane quarter (32 rows) and its half of the BN columns, in chunks of CW.
 template <int BN, uint32_t F>
-__device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, uint32_t taddr,
+__device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half, uint32_t taddr,
                                          float neg, uint8_t* st_out, uint8_t* st_out2, const uint8_t* side_tile) {
-  constexpr int CW = BN >= 32 ? 32 : 16;
-  constexpr int NCH = BN / CW;
+  constexpr int WC = BN >= 32 ? BN / 2 : BN;    // columns per warp (BN = 16: the second warp of a quarter idles)
+  constexpr int CW = WC >= 32 ? 32 : 16;
+  constexpr int NCH = WC / CW;
+  if (BN < 32 && half != 0) return;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
+    const int cb = half * WC + ch * CW;
     uint32_t v[32];
-    if (p.dbg & 256) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = 0x3f800000u + e;
-    } else {
-      if (CW == 32) tc::tmem_ld_32x32(taddr + ch * CW, v);
-      else tc::tmem_ld_32x16(taddr + ch * CW, v);
-      tc::tmem_ld_wait();
-    }
-    epi_apply<CW, F>(p, v, side_tile, s_bias, ch * CW, n0 + ch * CW, r, neg, st_out, st_out2);
+    if (CW == 32) tc::tmem_ld_32x32(taddr + cb, v);
+    else tc::tmem_ld_32x16(taddr + cb, v);
+    tc::tmem_ld_wait();
+    epi_apply<CW, F>(p, v, side_tile, s_bias, cb, n0 + cb, r, neg, st_out, st_out2);
   }
 }
 
@@ -424,13 +420,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (p.dbg && blockIdx.x == 0 && lane == 0) { g_tg_clk[0] = clock64() - clk0; g_tg_clk[1] = it; }
   } else if (warp >= 4) {
-    // ================= epilogue (warps 4..7) =================
-    // Each warp owns one TMEM lane quarter = 32 rows of the tile and is self-contained: its own copy of the bias
-    // slice, its own 32-row slab of the (swizzled) staging tile and its own TMA stores / bulk groups, so the four
-    // warps never meet at a CTA barrier.  The CTA uses (almost) all shared memory, so there is no L1: side inputs
-    // arrive as TMA tiles, bias sits in shared memory.
+    // ================= epilogue (warps 4..11) =================
+    // A warp owns one TMEM lane quarter = 32 rows of the tile and half of its columns, with its own copy of the bias
+    // slice.  Outputs go to a swizzled staging tile and leave as 32-row TMA stores: per warp when its columns are a
+    // whole 64-column box (BN = 128), per pair of warps otherwise (named barrier of 64 threads) — never a CTA barrier.
+    // The CTA uses (almost) all shared memory, so there is no L1: side inputs arrive as TMA tiles.
     const int q = warp & 3;
-    float* s_bias = s_bias_all + q * (BN < 32 ? 32 : BN);
+    const int half = (warp - 4) >> 2;
+    const bool pair_store = BN == 64;                         // the two warps of a quarter share one 64-column box
+    const bool store_leader = lane == 0 && (BN == 128 || half == 0);
+    float* s_bias = s_bias_all + (warp - 4) * (BN < 32 ? 32 : BN);
     const float neg = p.act == MV_ACT_LRELU02 ? 0.2f : (p.act == MV_ACT_RELU ? 0.f : 1.f);
     const float inv_S = p.img_stride > 0 ? 1.f / float(p.img_stride) : 0.f;
     const float inv_Wp = p.Wp > 0 ? 1.f / float(p.Wp) : 0.f;
@@ -464,12 +463,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::fence_after_sync();
       if (side_tile) tc::mbar_wait(&side_full[ss], uint32_t(sph));
       if (p.use_tma_store && it > 0) {
-        // this warp's previous TMA stores must have finished READING its staging slab before it is rewritten
-        if (lane == 0) tc::tma_store_wait_read<0>();
-        __syncwarp();
+        // the previous TMA stores of this slab must have finished READING it before it is rewritten
+        if (store_leader) tc::tma_store_wait_read<0>();
+        if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        else __syncwarp();
       }
       if (!(p.dbg & 1)) {
-#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, taddr, neg, st_out, st_out2, side_tile)
+#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, neg, st_out, st_out2, side_tile)
         switch (p.epi_flags) {
           case 0u: MV_EPI(0u); break;
           case EF_BIAS: MV_EPI(EF_BIAS); break;
@@ -492,18 +492,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (side_tile && ++ss == p.side_stages) { ss = 0; sph ^= 1; }
       if (p.use_tma_store && !(p.dbg & 5)) {
         tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b) {
-            tc::tma_store_2d(&tmO, st_out + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
-            if (two) tc::tma_store_2d(&tmO2, st_out2 + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
-          }
+        if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        else __syncwarp();
+        if (store_leader) {
+          const int b = BN == 128 ? half : 0;   // this leader's 64-column box
+          tc::tma_store_2d(&tmO, st_out + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
+          if (two) tc::tma_store_2d(&tmO2, st_out2 + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
           tc::tma_store_commit();
         }
       }
     }
-    if (p.use_tma_store && lane == 0) tc::tma_store_wait_all<0>();
+    if (p.use_tma_store && store_leader) tc::tma_store_wait_all<0>();
   }
   tc::fence_before_sync();
   __syncthreads();
