@@ -320,7 +320,7 @@ def run_gpu(args):
         "elbo_rel_err": rel, "elbo_rel_err_bf16_tensor_path": rel16,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    EMIT(json.dumps(line))
 
 
 def measured_peaks():
@@ -395,7 +395,25 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _claim_stdout():
+    """Everything but the final JSON line goes to stderr (NCCL and torch print banners on fd 1): returns a writer for the
+    real stdout."""
+    real = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+    def emit(line):
+        os.write(real, (line + "\n").encode())
+    return emit
+
+
+EMIT = print
+
+
 def main():
+    global EMIT
+    EMIT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

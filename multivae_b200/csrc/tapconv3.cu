@@ -37,7 +37,7 @@ constexpr int kC3Threads = 640;
 constexpr int kC3EpiWarps = 16;
 constexpr int kC3OutRows = 126;
 constexpr int kC3MaxStages = 4;
-constexpr int kC3MaxSide = 3;
+constexpr int kC3MaxSide = 4;
 constexpr int kC3N = 192;
 constexpr uint32_t kC3WBox = 192u * 128u;   // one filter row of weights: 3 taps x 64 output channels x 64 input channels
 
@@ -49,7 +49,7 @@ struct Conv3Params {
   uint32_t in_stage_bytes, w_bytes;
   const float* bias;
   float neg, alpha, slope1;
-  int side_stages, n_out;
+  int side_stages, n_stg;   // side-tile ring depth; staging tiles per epilogue group (outputs not written in place)
   int img_stride, Wp, W, n_img;
   uint32_t flags;
   int dbg;
@@ -85,7 +85,7 @@ __device__ __forceinline__ void stg32(void* p, const U8& r) {   // 256-bit strea
                : "memory");
 }
 
-template <uint32_t F>
+template <uint32_t F, int G>
 __global__ void __launch_bounds__(kC3Threads, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
@@ -94,8 +94,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* in_base = smem;
   uint8_t* w_base = in_base + size_t(p.in_stages) * p.in_stage_bytes;
-  uint8_t* stg_base = w_base + p.w_bytes;                        // n_out staging tiles of 128 rows x 128 B (SWIZZLE_128B)
-  uint8_t* side_base = stg_base + size_t(p.n_out) * 16384;      // side_stages tiles of 128 rows x 128 B
+  uint8_t* stg_base = w_base + p.w_bytes;                        // per group n_stg staging tiles of 128 rows x 128 B (SWIZZLE_128B)
+  uint8_t* side_base = stg_base + size_t(G) * size_t(p.n_stg) * 16384;   // side_stages tiles of 128 rows x 128 B
   float* xchg = reinterpret_cast<float*>(side_base + size_t(p.side_stages) * 16384);   // [2 parities][4 quarters][2][64]
   float* s_bias = xchg + 2 * 4 * 2 * 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
@@ -112,8 +112,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
     tc::mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kC3EpiWarps); }
-    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], kC3EpiWarps); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kC3EpiWarps / G); }
+    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], G == 2 ? 1 : kC3EpiWarps); }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
@@ -151,14 +151,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 3) {
-    // ================= TMA producer: side-input tiles (rows [p0, p0 + 128) x 64 columns), their own ring =================
+    // ================= TMA producer: side-input tiles (the tile's 126 owned rows (+2) x 64 columns), their own ring ==========
     if (p.side_stages > 0) {
       int ss = 0, sph = 0;
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         tc::mbar_wait(&side_empty[ss], sph ^ 1);
         if (tc::elect_one()) {
           tc::mbar_expect_tx(&side_full[ss], 16384u);
-          tc::tma_load_2d(side_base + size_t(ss) * 16384, &tmS, &side_full[ss], 0, tile * kC3OutRows - 1);
+          tc::tma_load_2d(side_base + size_t(ss) * 16384, &tmS, &side_full[ss], 0, tile * kC3OutRows);
         }
         __syncwarp();
         if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
@@ -207,152 +207,195 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (p.dbg && blockIdx.x == 0 && lane == 0) { g_c3_clk[0] = clock64() - clk0; g_c3_clk[1] = it; }
   } else if (warp >= 4) {
     // ================= epilogue (warps 4..19) =================
-    // 16 warps: TMEM lane quarter q = warp % 4, column chunk cc = 16 output columns.  Many warps with little work each:
-    // the epilogue is a dependent chain (TMEM load -> shuffle -> add -> activation -> pack -> store), so the issue slots
-    // are filled by thread-level parallelism, not by unrolling.
+    // 16 warps in G groups.  G = 1: all warps work on the same tile, 16 output columns each.  G = 2: group g takes the
+    // tiles whose accumulator is buffer g (every second tile of this CTA), 8 warps x 32 columns, so that the two groups
+    // are in different phases of the (latency-bound: TMEM load -> exchange -> shuffle -> activation -> pack -> store)
+    // chain at any time and fill each other's issue slots.  A group synchronises with named barriers of its own.
+    constexpr int GW = kC3EpiWarps / G;          // warps per group
+    constexpr int NCHUNK = G;                    // 16-column chunks per warp
     const int ew = warp - 4;
-    const int q = ew & 3;
-    const int c0 = (ew >> 2) * 16;
+    const int grp = ew / GW;
+    const int q = ew & 3;                        // TMEM lane quarter (= warp % 4)
+    const int cw0 = ((ew % GW) >> 2) * 16 * NCHUNK;   // first output column of this warp
     const bool has_side = c3_has<F>(p, C3_RES) || c3_has<F>(p, C3_DACT1);
-    const uint32_t xchg_s = tc::smem_u32(xchg);
-    // alpha and the bias are folded into one FMA per element: alpha * act(acc + b) = act(alpha * acc + alpha * b) for alpha > 0
+    // G = 2 writes the first output IN PLACE over the side tile (its staging would not fit twice); the tile is then released by
+    // the group leader once the TMA store has read it.  G = 1 keeps a separate staging tile and every warp releases the side
+    // tile as soon as it has read its part (a longer-held ring of 3 tiles costs more than the staging tile).
+    constexpr bool kInPlace = G == 2;
+    const uint32_t xw = tc::smem_u32(xchg) + uint32_t(grp) * 2048u;   // [4 quarters][2: E0 of lane 31 | E2 of lane 0][64 columns] floats
+    const int bar_a = 1 + grp, bar_b = 3 + grp;
+    // G = 1: alpha * bias of this warp's 16 columns lives in registers (G = 2 has 32 columns per warp: shared memory)
     float ab[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) ab[e] = c3_has<F>(p, C3_BIAS) ? p.alpha * s_bias[c0 + e] : 0.f;
+    for (int e = 0; e < 16; ++e) ab[e] = (G == 1 && c3_has<F>(p, C3_BIAS)) ? p.alpha * s_bias[cw0 + e] : 0.f;
     // Row geometry without divisions in the tile loop: this thread's row advances by a constant number of rows per tile,
     // so (row mod S) and (row mod Wp) are carried incrementally (S is a multiple of Wp, so the wrap of the first does not
     // disturb the second).
     const int rloc = q * 32 + lane;
     const bool inner = rloc >= 1 && rloc <= kC3OutRows;   // rows 0 and 127 of the MMA tile belong to the neighbouring tiles
-    int row = int(blockIdx.x) * kC3OutRows - 1 + rloc;
+    int row = (int(blockIdx.x) + grp * int(gridDim.x)) * kC3OutRows - 1 + rloc;
     const int S = p.img_stride > 0 ? p.img_stride : 1, Wp = p.img_stride > 0 ? p.Wp : 1;
-    const int d_row = int(gridDim.x) * kC3OutRows;
+    const int d_row = int(gridDim.x) * kC3OutRows * G;
     const int d_S = d_row % S, d_W = d_row % Wp;
     int rS = ((row % S) + S) % S, rW = ((row % Wp) + Wp) % Wp;
     const float inv_alpha = 1.f / p.alpha;
     const int row_end = p.img_stride > 0 ? (p.n_img * p.img_stride < p.P ? p.n_img * p.img_stride : p.P) : p.P;
-    // staging tile addressing: owned row rloc (1..126) sits in staging row rloc - 1, so that ONE 126-row TMA store per
-    // output moves the tile; 16-byte chunk j of a row r lands at chunk j ^ (r & 7) (SWIZZLE_128B)
-    const int srow = rloc - 1;
-    const uint32_t stg_s = tc::smem_u32(stg_base);
-    const uint32_t o_off0 = uint32_t(srow & 127) * 128u + (uint32_t(((c0 >> 3) + 0) ^ (srow & 7)) << 4);
-    const uint32_t o_off1 = uint32_t(srow & 127) * 128u + (uint32_t(((c0 >> 3) + 1) ^ (srow & 7)) << 4);
-    const uint32_t s_off0 = uint32_t(rloc) * 128u + (uint32_t(((c0 >> 3) + 0) ^ (rloc & 7)) << 4);   // side tiles: row rloc
-    const uint32_t s_off1 = uint32_t(rloc) * 128u + (uint32_t(((c0 >> 3) + 1) ^ (rloc & 7)) << 4);
+    // Staging: owned row rloc (1..126) sits in tile row rloc - 1, so that ONE 126-row TMA store per output moves the tile;
+    // 16-byte chunk j of a row r lands at chunk j ^ (r & 7) (SWIZZLE_128B).  With a side input the first output is written
+    // IN PLACE over the side tile (same thread, same address) and stored from there.
+    const int srow = (rloc - 1) & 127;
+    const uint32_t row_off = uint32_t(srow) * 128u;
+    const uint32_t stg_s = tc::smem_u32(stg_base) + uint32_t(grp) * uint32_t(p.n_stg) * 16384u;
     const uint32_t side_s = tc::smem_u32(side_base);
-    const bool leader = threadIdx.x == 128;   // issues the TMA stores
-    int it = 0, ss = 0, sph = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+    const bool leader = (ew % GW) == 0 && lane == 0;   // issues the group's TMA stores
+    int ss = grp % (p.side_stages > 0 ? p.side_stages : 1), sph = 0, prev_ss = -1, k = 0;
+    for (int it = grp; int(blockIdx.x) + it * int(gridDim.x) < p.m_tiles; it += G, ++k) {
+      const int tile = int(blockIdx.x) + it * int(gridDim.x);
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
       const bool valid = p.img_stride > 0 ? (inner && row < row_end && rS >= Wp && rW < p.W) : (inner && row < p.P);
-      const uint32_t xw = xchg_s + uint32_t(it & 1) * 2048u;   // [4 quarters][2: E0 of lane 31 | E2 of lane 0][64 columns] floats
-      tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
-      tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + uint32_t(acc * 256) + (uint32_t(q * 32) << 16) + uint32_t(c0);
-      uint32_t e0[16], e1[16], e2[16];
-      tc::tmem_ld_32x16(taddr, e0);
-      tc::tmem_ld_32x16(taddr + 64, e1);
-      tc::tmem_ld_32x16(taddr + 128, e2);
-      tc::tmem_ld_wait();
-      // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
-      // rows the neighbouring lane quarters need: E0 of lane 31 (for the quarter below), E2 of lane 0 (for the one above)
-      if (lane == 31) {
-        const uint32_t dst = xw + uint32_t((q * 2 + 0) * 64 + c0) * 4u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e0[4 * g]), "r"(e0[4 * g + 1]), "r"(e0[4 * g + 2]),
-                       "r"(e0[4 * g + 3]) : "memory");
-      }
-      if (lane == 0) {
-        const uint32_t dst = xw + uint32_t((q * 2 + 1) * 64 + c0) * 4u;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e2[4 * g]), "r"(e2[4 * g + 1]), "r"(e2[4 * g + 2]),
-                       "r"(e2[4 * g + 3]) : "memory");
-      }
-      // the previous tile's TMA stores must have finished READING the staging tiles before they are rewritten below
-      if (leader && it > 0) tc::tma_store_wait_read<0>();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kC3EpiWarps) : "memory");
-      float y[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[e]), 1);
-        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[e]), 1);
-        y[e] = (up + __uint_as_float(e1[e])) + dn;
-      }
-      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
-        // boundary lanes: the shuffled-in term came from the lane itself; replace it by the neighbouring quarter's row
-        const uint32_t src = lane == 0 ? xw + uint32_t(((q - 1) * 2 + 0) * 64 + c0) * 4u : xw + uint32_t(((q + 1) * 2 + 1) * 64 + c0) * 4u;
-        const uint32_t* own = lane == 0 ? e0 : e2;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t a, b, c, d;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src + 16u * g) : "memory");
-          y[4 * g + 0] += __uint_as_float(a) - __uint_as_float(own[4 * g + 0]);
-          y[4 * g + 1] += __uint_as_float(b) - __uint_as_float(own[4 * g + 1]);
-          y[4 * g + 2] += __uint_as_float(c) - __uint_as_float(own[4 * g + 2]);
-          y[4 * g + 3] += __uint_as_float(d) - __uint_as_float(own[4 * g + 3]);
-        }
-      }
-      // side input of this row: 16 columns from the TMA tile
-      uint32_t sv[8];
-      if (has_side) {
-        tc::mbar_wait(&side_full[ss], uint32_t(sph));
-        const uint32_t sb = side_s + uint32_t(ss) * 16384u;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]) : "r"(sb + s_off0) : "memory");
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]), "=r"(sv[7]) : "r"(sb + s_off1) : "memory");
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&side_empty[ss]);
-        if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sv[e] = 0u;
-      }
       const float vz = valid ? 1.f : 0.f;   // halo positions: the layout invariant is zeros
       const float al = valid ? p.alpha : 0.f;
-      uint32_t o[8], o2[8];
+      const uint32_t side_tile = side_s + uint32_t(ss) * 16384u;
+      const uint32_t out_tile = (kInPlace && has_side) ? side_tile : stg_s;
+      const uint32_t out2_tile = (kInPlace && has_side) ? stg_s : stg_s + 16384u;
+      tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
+      tc::fence_after_sync();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        y[e] = fmaf(al, y[e], vz * ab[e]);
-        y[e] = fmaxf(y[e], p.neg * y[e]);   // none / relu / leaky-relu as one max: slope `neg` is 1 / 0 / 0.2
-      }
-      if (c3_has<F>(p, C3_DACT1)) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          y[2 * i] *= bf16lo(sv[i]) > 0.f ? 1.f : p.slope1;
-          y[2 * i + 1] *= bf16hi(sv[i]) > 0.f ? 1.f : p.slope1;
+      for (int j = 0; j < NCHUNK; ++j) {
+        const int c0 = cw0 + 16 * j;
+        const uint32_t taddr = tmem_base + uint32_t(acc * 256) + (uint32_t(q * 32) << 16) + uint32_t(c0);
+        uint32_t e0[16], e1[16], e2[16];
+        tc::tmem_ld_32x16(taddr, e0);
+        tc::tmem_ld_32x16(taddr + 64, e1);
+        tc::tmem_ld_32x16(taddr + 128, e2);
+        tc::tmem_ld_wait();
+        if (j == NCHUNK - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
         }
-      }
-      if (c3_has<F>(p, C3_OUT2)) {
-        // second output = the un-scaled activation y / alpha (the saved `d` of the ResnetBlock)
-        const float ia = valid ? inv_alpha : 0.f;
+        // rows the neighbouring lane quarters need: E0 of lane 31 (for the quarter below), E2 of lane 0 (for the one above)
+        if (lane == 31) {
+          const uint32_t dst = xw + uint32_t((q * 2 + 0) * 64 + c0) * 4u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o2[i] = pack_bf16(ia * y[2 * i], ia * y[2 * i + 1]);
-      }
-      if (c3_has<F>(p, C3_RES)) {
+          for (int g = 0; g < 4; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e0[4 * g]), "r"(e0[4 * g + 1]),
+                         "r"(e0[4 * g + 2]), "r"(e0[4 * g + 3]) : "memory");
+        }
+        if (lane == 0) {
+          const uint32_t dst = xw + uint32_t((q * 2 + 1) * 64 + c0) * 4u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i] + vz * bf16lo(sv[i]), y[2 * i + 1] + vz * bf16hi(sv[i]));
-      } else {
+          for (int g = 0; g < 4; ++g)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e2[4 * g]), "r"(e2[4 * g + 1]),
+                         "r"(e2[4 * g + 2]), "r"(e2[4 * g + 3]) : "memory");
+        }
+        if (j == 0 && leader && k > 0) {
+          // the group's previous TMA stores must have finished READING their tiles before those are rewritten / recycled
+          tc::tma_store_wait_read<0>();
+          if (kInPlace && has_side) tc::mbar_arrive(&side_empty[prev_ss]);
+        }
+        if (G == 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(32 * GW) : "memory");
+        float y[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i], y[2 * i + 1]);
-      }
-      if (inner) {
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + o_off0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + o_off1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+        for (int e = 0; e < 16; ++e) {
+          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[e]), 1);
+          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[e]), 1);
+          y[e] = (up + __uint_as_float(e1[e])) + dn;
+        }
+        if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+          // boundary lanes: the shuffled-in term came from the lane itself; replace it by the neighbouring quarter's row
+          const uint32_t src = lane == 0 ? xw + uint32_t(((q - 1) * 2 + 0) * 64 + c0) * 4u : xw + uint32_t(((q + 1) * 2 + 1) * 64 + c0) * 4u;
+          const uint32_t* own = lane == 0 ? e0 : e2;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t a, b, c, d;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src + 16u * g) : "memory");
+            y[4 * g + 0] += __uint_as_float(a) - __uint_as_float(own[4 * g + 0]);
+            y[4 * g + 1] += __uint_as_float(b) - __uint_as_float(own[4 * g + 1]);
+            y[4 * g + 2] += __uint_as_float(c) - __uint_as_float(own[4 * g + 2]);
+            y[4 * g + 3] += __uint_as_float(d) - __uint_as_float(own[4 * g + 3]);
+          }
+        }
+        const uint32_t off0 = row_off + (uint32_t(((c0 >> 3) + 0) ^ (srow & 7)) << 4);
+        const uint32_t off1 = row_off + (uint32_t(((c0 >> 3) + 1) ^ (srow & 7)) << 4);
+        // side input of this row: 16 columns from the TMA tile
+        uint32_t sv[8];
+        if (has_side) {
+          if (j == 0) tc::mbar_wait(&side_full[ss], uint32_t(sph));
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3]) : "r"(side_tile + off0) : "memory");
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(sv[4]), "=r"(sv[5]), "=r"(sv[6]), "=r"(sv[7]) : "r"(side_tile + off1) : "memory");
+          if (!kInPlace && j == NCHUNK - 1) {
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&side_empty[ss]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sv[e] = 0u;
+        }
+        // alpha and the bias are folded into one FMA per element: alpha * act(acc + b) = act(alpha * acc + alpha * b), alpha > 0
+        if (G == 1 && c3_has<F>(p, C3_BIAS)) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] = fmaf(al, y[e], vz * ab[e]);
+        } else if (c3_has<F>(p, C3_BIAS)) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+            y[4 * g + 0] = al * (y[4 * g + 0] + b.x); y[4 * g + 1] = al * (y[4 * g + 1] + b.y);
+            y[4 * g + 2] = al * (y[4 * g + 2] + b.z); y[4 * g + 3] = al * (y[4 * g + 3] + b.w);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] *= al;
+        }
+        uint32_t o[8], o2[8];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);   // none / relu / leaky-relu as one max: slope 1 / 0 / 0.2
+        if (c3_has<F>(p, C3_DACT1)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            y[2 * i] *= bf16lo(sv[i]) > 0.f ? 1.f : p.slope1;
+            y[2 * i + 1] *= bf16hi(sv[i]) > 0.f ? 1.f : p.slope1;
+          }
+        }
         if (c3_has<F>(p, C3_OUT2)) {
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + 16384u + o_off0), "r"(o2[0]), "r"(o2[1]), "r"(o2[2]), "r"(o2[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg_s + 16384u + o_off1), "r"(o2[4]), "r"(o2[5]), "r"(o2[6]), "r"(o2[7]) : "memory");
+          // second output = the un-scaled activation y / alpha (the saved `d` of the ResnetBlock)
+          const float ia = valid ? inv_alpha : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o2[i] = pack_bf16(ia * y[2 * i], ia * y[2 * i + 1]);
+        }
+        if (c3_has<F>(p, C3_RES)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i] + vz * bf16lo(sv[i]), y[2 * i + 1] + vz * bf16hi(sv[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i], y[2 * i + 1]);
+        }
+        if (inner) {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_tile + off0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_tile + off1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+          if (c3_has<F>(p, C3_OUT2)) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out2_tile + off0), "r"(o2[0]), "r"(o2[1]), "r"(o2[2]), "r"(o2[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out2_tile + off1), "r"(o2[4]), "r"(o2[5]), "r"(o2[6]), "r"(o2[7]) : "memory");
+          }
         }
       }
       tc::fence_proxy_async();
-      asm volatile("bar.sync 2, %0;" ::"n"(32 * kC3EpiWarps) : "memory");
+      if (G == 1) asm volatile("bar.sync 3, %0;" ::"n"(32 * GW) : "memory");
+      else asm volatile("bar.sync %0, %1;" ::"r"(bar_b), "n"(32 * GW) : "memory");
       if (leader) {
-        tc::tma_store_2d(&tmO, stg_base, 0, tile * kC3OutRows);
-        if (c3_has<F>(p, C3_OUT2)) tc::tma_store_2d(&tmO2, stg_base + 16384, 0, tile * kC3OutRows);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmO), "r"(out_tile), "r"(0),
+                     "r"(tile * kC3OutRows) : "memory");
+        if (c3_has<F>(p, C3_OUT2))
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmO2), "r"(out2_tile), "r"(0),
+                       "r"(tile * kC3OutRows) : "memory");
         tc::tma_store_commit();
+      }
+      prev_ss = ss;
+      if (has_side) {
+        ss += G;
+        if (ss >= p.side_stages) { ss -= p.side_stages; sph ^= 1; }
       }
       row += d_row;
       rS += d_S; rS -= rS >= S ? S : 0;
@@ -398,18 +441,28 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.in_stage_bytes = (uint32_t(p.R) * 128u + 1023u) & ~1023u;
   p.w_bytes = uint32_t(p.n_kc) * 3u * kC3WBox;
   const size_t fixed = 1024 + 2 * 4 * 2 * 64 * 4 + 64 * 4 + (2 * kC3MaxStages + 5 + 2 * kC3MaxSide) * 8 + 16;
-  p.n_out = a->out2 ? 2 : 1;
   const bool has_side = a->res || a->dact1;
-  // shared-memory plan: weights + staging are fixed; the input ring keeps 3 stages if at all possible, the side ring
-  // takes what is left (2 or 3 tiles)
-  const size_t base = fixed + p.w_bytes + size_t(p.n_out) * 16384;
-  p.side_stages = 0;
-  if (has_side) {
-    p.side_stages = kC3MaxSide;
-    while (p.side_stages > 2 && base + size_t(p.side_stages) * 16384 + 3 * size_t(p.in_stage_bytes) > kC3SmemLimit) --p.side_stages;
+  // staging tiles per epilogue group: with a side input the first output is written in place over the side tile
+  const int n_out = a->out2 ? 2 : 1;
+  // shared-memory plan.  Preferred: two epilogue groups (G = 2) with a 3-stage input ring and, if there is a side input,
+  // a side ring of 4 (then 3) tiles; otherwise one group (G = 1) with a side ring of 3 (then 2) tiles.
+  auto n_stg = [&](int G) { return n_out - ((G == 2 && has_side) ? 1 : 0); };
+  auto plan = [&](int G, int side_stages, int in_stages) {
+    return fixed + p.w_bytes + size_t(G) * size_t(n_stg(G)) * 16384 + size_t(side_stages) * 16384 + size_t(in_stages) * p.in_stage_bytes;
+  };
+  int G = 0;
+  // (measured: with a side input the in-place ring of 4 is saturated and two groups gain nothing — one group there)
+  if (!getenv("MV_C3_ONE_GROUP") && p.n_kc == 1 && (!has_side || getenv("MV_C3_TWO_GROUPS"))) {
+    for (int ssn = has_side ? 4 : 0; ssn >= (has_side ? 3 : 0) && !G; --ssn)
+      if (plan(2, ssn, 3) <= kC3SmemLimit) { G = 2; p.side_stages = ssn; }
   }
-  if (base + size_t(p.side_stages) * 16384 + 2 * size_t(p.in_stage_bytes) > kC3SmemLimit) return MV_OK;
-  p.in_stages = int((kC3SmemLimit - base - size_t(p.side_stages) * 16384) / p.in_stage_bytes);
+  if (!G) {
+    for (int ssn = has_side ? 3 : 0; ssn >= (has_side ? 2 : 0) && !G; --ssn)
+      if (plan(1, ssn, p.n_kc == 1 ? 3 : 2) <= kC3SmemLimit) { G = 1; p.side_stages = ssn; }
+  }
+  if (!G) return MV_OK;
+  p.n_stg = n_stg(G);
+  p.in_stages = int((kC3SmemLimit - plan(G, p.side_stages, 0)) / p.in_stage_bytes);
   if (p.in_stages > kC3MaxStages) p.in_stages = kC3MaxStages;
   if (const char* e = getenv("MV_TG_IN_STAGES")) {
     int v = atoi(e);
@@ -442,17 +495,22 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     mv::set_error("mv_tapgemm(conv3): cuTensorMapEncodeTiled failed for the outputs / side input");
     return MV_ERR_CUDA;
   }
-  const size_t smem = base + size_t(p.side_stages) * 16384 + size_t(p.in_stages) * p.in_stage_bytes;
+  const size_t smem = plan(G, p.side_stages, p.in_stages);
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MV_C3_LAUNCH(FLAGS)                                                                                          \
-  do {                                                                                                               \
-    static bool attr_done = false;                                                                                   \
-    if (!attr_done) {                                                                                                \
-      cudaFuncSetAttribute(conv3_kernel<(FLAGS)>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kC3SmemLimit));   \
-      attr_done = true;                                                                                              \
-    }                                                                                                                \
-    conv3_kernel<(FLAGS)><<<grid, kC3Threads, smem, st>>>(tmA, tmW, tmO, tmO2, tmS, p);                                              \
+#define MV_C3_LAUNCH_G(FLAGS, G_)                                                                                        \
+  do {                                                                                                                   \
+    static bool attr_done = false;                                                                                       \
+    if (!attr_done) {                                                                                                    \
+      cudaFuncSetAttribute(conv3_kernel<(FLAGS), G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kC3SmemLimit));   \
+      attr_done = true;                                                                                                  \
+    }                                                                                                                    \
+    conv3_kernel<(FLAGS), G_><<<grid, kC3Threads, smem, st>>>(tmA, tmW, tmO, tmO2, tmS, p);                              \
+  } while (0)
+#define MV_C3_LAUNCH(FLAGS)                    \
+  do {                                         \
+    if (G == 2) MV_C3_LAUNCH_G(FLAGS, 2);      \
+    else MV_C3_LAUNCH_G(FLAGS, 1);             \
   } while (0)
   switch (p.flags) {
     case C3_BIAS: MV_C3_LAUNCH(C3_BIAS); break;
@@ -462,6 +520,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     default: MV_C3_LAUNCH(C3_GENERIC); break;
   }
 #undef MV_C3_LAUNCH
+#undef MV_C3_LAUNCH_G
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     mv::set_error("mv_tapgemm(conv3): CUDA error %s", cudaGetErrorString(e));
