@@ -411,6 +411,244 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 constexpr size_t kC3SmemLimit = 232448;
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Image head: 3x3 convolution 64 -> n_valid <= 16 channels (padded to 16) + bias + activation, scattered to a dense NCHW
+// bf16 image (DecoderResnetMMNIST.conv_img, models/nn/mmnist.py:352-354).  Same three-taps-per-MMA scheme with N = 3 x 16:
+// 12 MMAs per tile instead of the 36 N = 16 MMAs of the generic kernel (which cost as much as N = 64 ones: the A fetch).
+// Warps 4-11 are two epilogue groups of four (one warp per TMEM lane quarter) on alternate tiles.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kH3Threads = 384;
+constexpr int kH3N = 48;
+constexpr uint32_t kH3WBox = 48u * 128u;
+
+struct Head3Params {
+  int P, m_tiles, row_shift, R, in_stages;
+  uint32_t in_stage_bytes;
+  const float* bias;
+  float neg;
+  bf16* out;
+  int img_stride, Wp, W, H, n_img, n_valid;
+};
+
+__global__ void __launch_bounds__(kH3Threads, 1)
+head3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ Head3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* in_base = smem;
+  uint8_t* w_base = in_base + size_t(p.in_stages) * p.in_stage_bytes;
+  float* xchg = reinterpret_cast<float*>(w_base + 3 * kH3WBox);   // [2 groups][4 quarters][2][16]
+  float* s_bias = xchg + 2 * 4 * 2 * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 16);
+  uint64_t* in_full = bars;
+  uint64_t* in_empty = in_full + kC3MaxStages;
+  uint64_t* w_full = in_empty + kC3MaxStages;
+  uint64_t* tm_full = w_full + 1;
+  uint64_t* tm_empty = tm_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
+    tc::mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], 4); }
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmW);
+  }
+  if (threadIdx.x >= 128 && threadIdx.x < 144) s_bias[threadIdx.x - 128] = p.bias ? p.bias[threadIdx.x - 128] : 0.f;
+  if (warp == 2) tc::tmem_alloc(tmem_slot, 128);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx(w_full, 3 * kH3WBox);
+      for (int r = 0; r < 3; ++r) tc::tma_load_2d(w_base + size_t(r) * kH3WBox, &tmW, w_full, 0, r * kH3N);
+    }
+    __syncwarp();
+    int is = 0, iph = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      tc::mbar_wait(&in_empty[is], iph ^ 1);
+      if (tc::elect_one()) {
+        tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * 128u);
+        tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], 0, tile * kC3OutRows - 1 - p.row_shift);
+      }
+      __syncwarp();
+      if (++is == p.in_stages) { is = 0; iph ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = tc::idesc_bf16(128, kH3N, 0, 0);
+    const uint64_t desc0 = tc::smem_desc(0, 16, 1024, tc::SW_128);
+    const uint32_t desc_hi = uint32_t(desc0 >> 32), desc_lo = uint32_t(desc0);
+    const uint32_t a_rstep = (uint32_t(p.row_shift) * 128u) >> 4;
+    const uint32_t w_lo0 = desc_lo | ((tc::smem_u32(w_base) & 0x3FFFFu) >> 4);
+    tc::mbar_wait(w_full, 0);
+    tc::fence_after_sync();
+    int is = 0, iph = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1, acc_ph = (it >> 1) & 1;
+      tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
+      tc::fence_after_sync();
+      const uint32_t tmem_d = tmem_base + uint32_t(acc * 64);
+      tc::mbar_wait(&in_full[is], iph);
+      tc::fence_after_sync();
+      const uint32_t a_lo0 = desc_lo | ((tc::smem_u32(in_base + size_t(is) * p.in_stage_bytes) & 0x3FFFFu) >> 4);
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = (uint64_t(desc_hi) << 32) | (a_lo0 + uint32_t(r) * a_rstep + 2u * k);
+            const uint64_t bd = (uint64_t(desc_hi) << 32) | (w_lo0 + uint32_t(r) * (kH3WBox >> 4) + 2u * k);
+            tc::umma_bf16(tmem_d, ad, bd, idesc, (r | k) != 0);
+          }
+        }
+        tc::umma_commit(&in_empty[is]);
+        tc::umma_commit(&tm_full[acc]);
+      }
+      __syncwarp();
+      if (++is == p.in_stages) { is = 0; iph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const uint32_t xw = tc::smem_u32(xchg) + uint32_t(grp) * 512u;
+    const int rloc = q * 32 + lane;
+    const bool inner = rloc >= 1 && rloc <= kC3OutRows;
+    const int S = p.img_stride, Wp = p.Wp;
+    int row = (int(blockIdx.x) + grp * int(gridDim.x)) * kC3OutRows - 1 + rloc;
+    const int d_row = int(gridDim.x) * kC3OutRows * 2;
+    const int d_S = d_row % S, d_W = d_row % Wp, d_img = d_row / S;
+    int img = row >= 0 ? row / S : -1;
+    int rS = ((row % S) + S) % S, rW = ((row % Wp) + Wp) % Wp;
+    const float inv_Wp = 1.f / float(Wp);
+    float bias[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) bias[e] = s_bias[e];
+    const size_t plane = size_t(p.H) * p.W;
+    for (int it = grp; int(blockIdx.x) + it * int(gridDim.x) < p.m_tiles; it += 2) {
+      const int acc = it & 1, acc_ph = (it >> 1) & 1;
+      const bool valid = inner && row < p.P && img < p.n_img && rS >= Wp && rW < p.W;
+      tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + uint32_t(acc * 64) + (uint32_t(q * 32) << 16);
+      uint32_t e0[16], e1[16], e2[16];
+      tc::tmem_ld_32x16(taddr, e0);
+      tc::tmem_ld_32x16(taddr + 16, e1);
+      tc::tmem_ld_32x16(taddr + 32, e2);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
+      if (lane == 31) {
+        const uint32_t dst = xw + uint32_t((q * 2 + 0) * 16) * 4u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e0[4 * g]), "r"(e0[4 * g + 1]), "r"(e0[4 * g + 2]),
+                       "r"(e0[4 * g + 3]) : "memory");
+      }
+      if (lane == 0) {
+        const uint32_t dst = xw + uint32_t((q * 2 + 1) * 16) * 4u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u * g), "r"(e2[4 * g]), "r"(e2[4 * g + 1]), "r"(e2[4 * g + 2]),
+                       "r"(e2[4 * g + 3]) : "memory");
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      float y[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[e]), 1);
+        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[e]), 1);
+        y[e] = (up + __uint_as_float(e1[e])) + dn;
+      }
+      if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+        const uint32_t src = lane == 0 ? xw + uint32_t(((q - 1) * 2 + 0) * 16) * 4u : xw + uint32_t(((q + 1) * 2 + 1) * 16) * 4u;
+        const uint32_t* own = lane == 0 ? e0 : e2;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t a, b, c, d;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src + 16u * g) : "memory");
+          y[4 * g + 0] += __uint_as_float(a) - __uint_as_float(own[4 * g + 0]);
+          y[4 * g + 1] += __uint_as_float(b) - __uint_as_float(own[4 * g + 1]);
+          y[4 * g + 2] += __uint_as_float(c) - __uint_as_float(own[4 * g + 2]);
+          y[4 * g + 3] += __uint_as_float(d) - __uint_as_float(own[4 * g + 3]);
+        }
+      }
+      // the exchange buffer may be rewritten by the group's next tile only after everybody has read it
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+      if (valid) {
+        const int yy = int(float(rS - rW) * inv_Wp + 0.5f);   // exact: (rS - rW) is a multiple of Wp
+        bf16* dst = p.out + size_t(img) * p.n_valid * plane + size_t(yy - 1) * p.W + rW;
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+          if (ch < p.n_valid) {
+            float v = y[ch] + bias[ch];
+            v = fmaxf(v, p.neg * v);
+            dst[size_t(ch) * plane] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+      row += d_row;
+      img += d_img;
+      rS += d_S;
+      if (rS >= S) { rS -= S; img += 1; }
+      rW += d_W; rW -= rW >= Wp ? Wp : 0;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, 128);
+}
+
+int head3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
+  *handled = false;
+  if (getenv("MV_NO_CONV3") || getenv("MV_NO_HEAD3")) return MV_OK;
+  if (a->T != 9 || a->N_total != 16 || a->BN != 16 || a->Cin != 64 || a->out_mode != 1) return MV_OK;
+  if (a->img_stride <= 0 || a->Wp < 2 || a->n_valid < 1 || a->n_valid > 16) return MV_OK;
+  for (int r = 0; r < 3; ++r)
+    for (int s2 = 0; s2 < 3; ++s2)
+      if (a->tap_off[3 * r + s2] != (r - 1) * a->Wp + (s2 - 1)) return MV_OK;
+  if (a->act == MV_ACT_SIGMOID || a->alpha != 1.f || a->res || a->dact1 || a->dact2 || a->out2) return MV_OK;
+  if (a->a_ld % 8 != 0 || a->P <= 0 || a->P >= (int64_t(1) << 31) - 256) return MV_OK;
+  Head3Params p{};
+  p.P = int(a->P);
+  p.m_tiles = int((a->P + kC3OutRows - 1) / kC3OutRows);
+  p.row_shift = a->Wp;
+  p.R = 128 + 2 * a->Wp;
+  if (p.R > 256) return MV_OK;
+  p.in_stage_bytes = (uint32_t(p.R) * 128u + 1023u) & ~1023u;
+  p.in_stages = kC3MaxStages;
+  p.bias = a->bias;
+  p.neg = a->act == MV_ACT_LRELU02 ? 0.2f : (a->act == MV_ACT_RELU ? 0.f : 1.f);
+  p.out = static_cast<bf16*>(a->out);
+  p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.H = a->H; p.n_img = a->n_img; p.n_valid = a->n_valid;
+  CUtensorMap tmA, tmW;
+  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), 64, uint64_t(a->a_ld) * 2, uint32_t(p.R), 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+      !tc::make_tmap_2d_bf16(&tmW, a->Wt, uint64_t(9) * 16, 64, 128, kH3N, 64, CU_TENSOR_MAP_SWIZZLE_128B)) {
+    mv::set_error("mv_tapgemm(head3): cuTensorMapEncodeTiled failed");
+    return MV_ERR_CUDA;
+  }
+  const size_t smem = 1024 + size_t(p.in_stages) * p.in_stage_bytes + 3 * kH3WBox + 2 * 4 * 2 * 16 * 4 + 16 * 4 + (2 * kC3MaxStages + 5) * 8 + 16;
+  const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(head3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kC3SmemLimit));
+    attr_done = true;
+  }
+  head3_kernel<<<grid, kH3Threads, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmW, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    mv::set_error("mv_tapgemm(head3): CUDA error %s", cudaGetErrorString(e));
+    return MV_ERR_CUDA;
+  }
+  mv::count_launch();
+  *handled = true;
+  return MV_OK;
+}
+
+
 // Launches the three-taps-per-MMA kernel when the call is a 3x3 convolution with 64 output channels in the halo
 // layout (see the eligibility tests); returns MV_OK with *handled = false otherwise.
 int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {

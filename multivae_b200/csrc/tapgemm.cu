@@ -510,6 +510,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled);
+int head3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled);
 
 static int g_num_sms = 0;
 int num_sms() {
@@ -547,7 +548,9 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   {
     // 3x3 convolutions with 64 output channels: three-taps-per-MMA kernel (tapconv3.cu)
     bool handled = false;
-    const int rc = mv::conv3_try_launch(a, stream, &handled);
+    int rc = mv::conv3_try_launch(a, stream, &handled);
+    if (rc != MV_OK || handled) return rc;
+    rc = mv::head3_try_launch(a, stream, &handled);   // 64 -> <= 16 channel image head (NCHW output)
     if (rc != MV_OK || handled) return rc;
   }
   MV_CHECK_ARG(a->a_ld % 8 == 0 && (a->out_ld % 8 == 0 || a->out_mode == 1), "mv_tapgemm: leading dimensions must be multiples of 8");
