@@ -75,6 +75,16 @@ int mv_moe_lpx_bwd(const void* recon, int recon_dtype, const float* x, const flo
                    const float* g_loss, void* g_recon, int C, int K, int B, int64_t D, int dist,
                    float dist_scale, float rescale, const uint8_t* mask_r, void* stream);
 
+/* The same two kernels for ALL reconstructed modalities in one launch (host arrays of n_mod <= 8 device pointers /
+ * per-modality scales; every modality has the same D, element type and distribution family — the PolyMNIST case).
+ * lpx is overwritten with the sum over modalities.  Shapes that do not qualify run as n_mod single launches. */
+int mv_moe_lpx_fwd_multi(int n_mod, const void* const* recon, int recon_dtype, const float* const* x, float* lpx, int C,
+                         int K, int B, int64_t D, int dist, const float* dist_scale, const float* rescale,
+                         const uint8_t* const* mask_r, void* stream);
+int mv_moe_lpx_bwd_multi(int n_mod, const void* const* recon, int recon_dtype, const float* const* x, const float* coef,
+                         const float* g_loss, void* const* g_recon, int C, int K, int B, int64_t D, int dist,
+                         const float* dist_scale, const float* rescale, const uint8_t* const* mask_r, void* stream);
+
 /* Latent terms + importance weights + loss for one batch, and their unit gradients.
  * Replaces _compute_k_lws + _dreg_looser/_iwae_looser (mmvaePlus_model.py:230-363) and
  * compute_k_lws + dreg_looser/iwae_looser (mmvae_model.py:160-292).

@@ -47,6 +47,11 @@ _PROTOS = {
                        c_void_p, c_int, c_void_p],
     "mv_moe_lpx_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int,
                        c_float, c_float, c_void_p, c_void_p],
+    "mv_moe_lpx_fwd_multi": [c_int, ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int64,
+                             c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), ctypes.POINTER(c_void_p), c_void_p],
+    "mv_moe_lpx_bwd_multi": [c_int, ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
+                             ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int, ctypes.POINTER(c_float),
+                             ctypes.POINTER(c_float), ctypes.POINTER(c_void_p), c_void_p],
     "mv_moe_lw_fwd": [c_void_p] * 21 + [c_int] * 7 + [c_float, c_int, c_void_p],
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
@@ -168,6 +173,15 @@ def ptr(t):
     if not t.is_contiguous():
         raise ValueError("non-contiguous tensor passed to a native kernel")
     return t.data_ptr()
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (None -> NULL) for the batched entry points."""
+    return (c_void_p * len(tensors))(*[None if t is None else ptr(t) for t in tensors])
+
+
+def float_array(values):
+    return (c_float * len(values))(*[float(v) for v in values])
 
 
 def stream():

@@ -113,11 +113,22 @@ __global__ void __launch_bounds__(128) lpx_fwd_kernel(const T* __restrict__ reco
 // warps walk the K importance samples, streaming `recon` with 128-bit loads (4 in flight per lane).  ~40 registers,
 // so 12+ blocks are resident per SM and the HBM stream stays saturated (the register-cached variant above holds
 // 80 target floats per lane and tops out at 3 blocks per SM).
+// Per-modality arguments of the batched (one launch for all reconstructed modalities) variants: blockIdx.y = modality.
+constexpr int kMaxBatchMods = 8;
+struct LpxBatch {
+  const void* recon[kMaxBatchMods];
+  const float* x[kMaxBatchMods];
+  void* g[kMaxBatchMods];
+  const uint8_t* mask[kMaxBatchMods];
+  float mul[kMaxBatchMods], add[kMaxBatchMods], inv_s[kMaxBatchMods], rescale[kMaxBatchMods];
+};
+
+// accumulate: 0 store, 1 add (single writer), 2 atomic add (several modalities write the same row concurrently)
 template <typename T, int DIST>
-__global__ void __launch_bounds__(128) lpx_fwd_smem_kernel(const T* __restrict__ recon, const float* __restrict__ x,
-                                                           float* __restrict__ lpx, int C, int K, int B, int64_t D, float mul,
-                                                           float add_per_elem, float rescale, const uint8_t* __restrict__ mask,
-                                                           int accumulate) {
+__device__ __forceinline__ void lpx_fwd_smem_body(const T* __restrict__ recon, const float* __restrict__ x,
+                                                  float* __restrict__ lpx, int C, int K, int B, int64_t D, float mul,
+                                                  float add_per_elem, float rescale, const uint8_t* __restrict__ mask,
+                                                  int accumulate) {
   constexpr int VE = Vec<T>::N;
   extern __shared__ float xs[];
   const int b = blockIdx.x % B, c = blockIdx.x / B;
@@ -159,9 +170,24 @@ __global__ void __launch_bounds__(128) lpx_fwd_smem_kernel(const T* __restrict__
     acc = warp_sum(acc);
     if (lane == 0) {
       const float val = live ? rescale * (acc * mul + add_per_elem * float(D)) : 0.f;
-      lpx[row] = accumulate ? lpx[row] + val : val;
+      if (accumulate == 2) atomicAdd(lpx + row, val);
+      else lpx[row] = accumulate ? lpx[row] + val : val;
     }
   }
+}
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_fwd_smem_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                           float* __restrict__ lpx, int C, int K, int B, int64_t D, float mul,
+                                                           float add_per_elem, float rescale, const uint8_t* __restrict__ mask,
+                                                           int accumulate) {
+  lpx_fwd_smem_body<T, DIST>(recon, x, lpx, C, K, B, D, mul, add_per_elem, rescale, mask, accumulate);
+}
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_fwd_smem_multi_kernel(const __grid_constant__ LpxBatch bt, float* __restrict__ lpx, int C,
+                                                                 int K, int B, int64_t D) {
+  const int m = blockIdx.y;
+  lpx_fwd_smem_body<T, DIST>(static_cast<const T*>(bt.recon[m]), bt.x[m], lpx, C, K, B, D, bt.mul[m], bt.add[m], bt.rescale[m],
+                             bt.mask[m], 2);
 }
 
 // scalar fallback for rows whose byte length is not a multiple of 16 (e.g. D = 10)
@@ -187,11 +213,10 @@ __global__ void __launch_bounds__(128) lpx_fwd_scalar_kernel(const T* __restrict
 }
 
 template <typename T, int DIST>
-__global__ void __launch_bounds__(128) lpx_bwd_kernel(const T* __restrict__ recon, const float* __restrict__ x,
-                                                      const float* __restrict__ coef, const float* __restrict__ g_loss,
-                                                      T* __restrict__ g_recon, int C, int K, int B, int64_t D,
-                                                      float inv_s, float rescale, const uint8_t* __restrict__ mask,
-                                                      int nchunks, int ksplit) {
+__device__ __forceinline__ void lpx_bwd_body(const T* __restrict__ recon, const float* __restrict__ x,
+                                             const float* __restrict__ coef, const float* __restrict__ g_loss,
+                                             T* __restrict__ g_recon, int C, int K, int B, int64_t D, float inv_s, float rescale,
+                                             const uint8_t* __restrict__ mask, int nchunks, int ksplit) {
   constexpr int VE = Vec<T>::N;
   constexpr int NV = kChunkElems / (32 * VE);
   const int lane = threadIdx.x & 31;
@@ -250,6 +275,22 @@ __global__ void __launch_bounds__(128) lpx_bwd_kernel(const T* __restrict__ reco
       }
     }
   }
+}
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_bwd_kernel(const T* __restrict__ recon, const float* __restrict__ x,
+                                                      const float* __restrict__ coef, const float* __restrict__ g_loss,
+                                                      T* __restrict__ g_recon, int C, int K, int B, int64_t D,
+                                                      float inv_s, float rescale, const uint8_t* __restrict__ mask,
+                                                      int nchunks, int ksplit) {
+  lpx_bwd_body<T, DIST>(recon, x, coef, g_loss, g_recon, C, K, B, D, inv_s, rescale, mask, nchunks, ksplit);
+}
+template <typename T, int DIST>
+__global__ void __launch_bounds__(128) lpx_bwd_multi_kernel(const __grid_constant__ LpxBatch bt, const float* __restrict__ coef,
+                                                            const float* __restrict__ g_loss, int C, int K, int B, int64_t D,
+                                                            int nchunks, int ksplit) {
+  const int m = blockIdx.y;
+  lpx_bwd_body<T, DIST>(static_cast<const T*>(bt.recon[m]), bt.x[m], coef, g_loss, static_cast<T*>(bt.g[m]), C, K, B, D, bt.inv_s[m],
+                        bt.rescale[m], bt.mask[m], nchunks, ksplit);
 }
 
 template <typename T, int DIST>
@@ -592,6 +633,101 @@ extern "C" int mv_moe_lpx_bwd(const void* recon, int recon_dtype, const float* x
   if (recon_dtype == MV_BF16) return launch_lpx_bwd<__nv_bfloat16>(recon, x, coef, g_loss, g_recon, C, K, B, D, dist, dist_scale, rescale, mask_r, st);
   mv::set_error("mv_moe_lpx_bwd: unsupported dtype %d", recon_dtype);
   return MV_ERR_UNSUPPORTED;
+}
+
+// ---- all reconstructed modalities in ONE launch (same D / dtype / distribution family): blockIdx.y = modality -------------
+template <typename T>
+static bool lpx_multi_ok(int n_mod, const void* const* recon, const float* const* x, void* const* g, int64_t D) {
+  constexpr int VE = Vec<T>::N;
+  if (n_mod < 1 || n_mod > kMaxBatchMods || D % VE != 0 || D % 4 != 0) return false;
+  for (int m = 0; m < n_mod; ++m) {
+    if (!recon[m] || !x[m] || reinterpret_cast<uintptr_t>(recon[m]) % 16 || reinterpret_cast<uintptr_t>(x[m]) % 16) return false;
+    if (g && (!g[m] || reinterpret_cast<uintptr_t>(g[m]) % 16)) return false;
+  }
+  return true;
+}
+
+extern "C" int mv_moe_lpx_fwd_multi(int n_mod, const void* const* recon, int recon_dtype, const float* const* x, float* lpx, int C,
+                                    int K, int B, int64_t D, int dist, const float* dist_scale, const float* rescale,
+                                    const uint8_t* const* mask_r, void* stream) {
+  MV_CHECK_ARG(recon && x && lpx && dist_scale && rescale && n_mod >= 1, "mv_moe_lpx_fwd_multi: null pointer");
+  MV_CHECK_ARG(C > 0 && K > 0 && B > 0 && D > 0, "mv_moe_lpx_fwd_multi: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool batched = recon_dtype == MV_BF16 ? lpx_multi_ok<__nv_bfloat16>(n_mod, recon, x, nullptr, D)
+                                              : (recon_dtype == MV_F32 && lpx_multi_ok<float>(n_mod, recon, x, nullptr, D));
+  if (!batched || D * 4 > 48 * 1024) {   // general case: one launch per modality, accumulating
+    for (int m = 0; m < n_mod; ++m) {
+      const int rc = mv_moe_lpx_fwd(recon[m], recon_dtype, x[m], lpx, C, K, B, D, dist, dist_scale[m], rescale[m],
+                                    mask_r ? mask_r[m] : nullptr, m > 0 ? 1 : 0, stream);
+      if (rc != MV_OK) return rc;
+    }
+    return MV_OK;
+  }
+  MV_CHECK_ARG(dist >= MV_DIST_NORMAL && dist <= MV_DIST_BERNOULLI, "mv_moe_lpx_fwd_multi: unsupported distribution %d", dist);
+  LpxBatch bt{};
+  for (int m = 0; m < n_mod; ++m) {
+    MV_CHECK_ARG(dist == MV_DIST_BERNOULLI || dist_scale[m] > 0.f, "mv_moe_lpx_fwd_multi: scale must be > 0");
+    bt.recon[m] = recon[m]; bt.x[m] = x[m]; bt.mask[m] = mask_r ? mask_r[m] : nullptr; bt.rescale[m] = rescale[m];
+    lp_consts(dist, dist_scale[m], &bt.mul[m], &bt.add[m]);
+  }
+  cudaMemsetAsync(lpx, 0, sizeof(float) * size_t(C) * K * B, st);
+  const dim3 grid(C * B, n_mod);
+  const size_t smem = size_t(D) * 4;
+#define L_(TT, DI) lpx_fwd_smem_multi_kernel<TT, DI><<<grid, 128, smem, st>>>(bt, lpx, C, K, B, D)
+#define LT_(DI)                                     \
+  do {                                              \
+    if (recon_dtype == MV_BF16) L_(__nv_bfloat16, DI); \
+    else L_(float, DI);                             \
+  } while (0)
+  if (dist == MV_DIST_NORMAL) LT_(MV_DIST_NORMAL);
+  else if (dist == MV_DIST_LAPLACE) LT_(MV_DIST_LAPLACE);
+  else LT_(MV_DIST_BERNOULLI);
+#undef LT_
+#undef L_
+  MV_CHECK_LAUNCH("mv_moe_lpx_fwd_multi");
+  return MV_OK;
+}
+
+extern "C" int mv_moe_lpx_bwd_multi(int n_mod, const void* const* recon, int recon_dtype, const float* const* x, const float* coef,
+                                    const float* g_loss, void* const* g_recon, int C, int K, int B, int64_t D, int dist,
+                                    const float* dist_scale, const float* rescale, const uint8_t* const* mask_r, void* stream) {
+  MV_CHECK_ARG(recon && x && coef && g_loss && g_recon && dist_scale && rescale && n_mod >= 1, "mv_moe_lpx_bwd_multi: null pointer");
+  MV_CHECK_ARG(C > 0 && K > 0 && B > 0 && D > 0, "mv_moe_lpx_bwd_multi: bad sizes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool batched = recon_dtype == MV_BF16 ? lpx_multi_ok<__nv_bfloat16>(n_mod, recon, x, g_recon, D)
+                                              : (recon_dtype == MV_F32 && lpx_multi_ok<float>(n_mod, recon, x, g_recon, D));
+  if (!batched) {
+    for (int m = 0; m < n_mod; ++m) {
+      const int rc = mv_moe_lpx_bwd(recon[m], recon_dtype, x[m], coef, g_loss, g_recon[m], C, K, B, D, dist, dist_scale[m], rescale[m],
+                                    mask_r ? mask_r[m] : nullptr, stream);
+      if (rc != MV_OK) return rc;
+    }
+    return MV_OK;
+  }
+  MV_CHECK_ARG(dist >= MV_DIST_NORMAL && dist <= MV_DIST_BERNOULLI, "mv_moe_lpx_bwd_multi: unsupported distribution %d", dist);
+  LpxBatch bt{};
+  for (int m = 0; m < n_mod; ++m) {
+    MV_CHECK_ARG(dist == MV_DIST_BERNOULLI || dist_scale[m] > 0.f, "mv_moe_lpx_bwd_multi: scale must be > 0");
+    bt.recon[m] = recon[m]; bt.x[m] = x[m]; bt.g[m] = g_recon[m]; bt.mask[m] = mask_r ? mask_r[m] : nullptr;
+    bt.rescale[m] = rescale[m]; bt.inv_s[m] = dist == MV_DIST_BERNOULLI ? 1.f : 1.f / dist_scale[m];
+  }
+  const int nchunks = int((D + kChunkElems - 1) / kChunkElems);
+  const int ksplit = pick_ksplit(int64_t(C) * B * nchunks * n_mod, K);
+  const int64_t warps = int64_t(C) * B * nchunks * ksplit;
+  const dim3 grid(unsigned((warps + 3) / 4), n_mod);
+#define L_(TT, DI) lpx_bwd_multi_kernel<TT, DI><<<grid, 128, 0, st>>>(bt, coef, g_loss, C, K, B, D, nchunks, ksplit)
+#define LT_(DI)                                     \
+  do {                                              \
+    if (recon_dtype == MV_BF16) L_(__nv_bfloat16, DI); \
+    else L_(float, DI);                             \
+  } while (0)
+  if (dist == MV_DIST_NORMAL) LT_(MV_DIST_NORMAL);
+  else if (dist == MV_DIST_LAPLACE) LT_(MV_DIST_LAPLACE);
+  else LT_(MV_DIST_BERNOULLI);
+#undef LT_
+#undef L_
+  MV_CHECK_LAUNCH("mv_moe_lpx_bwd_multi");
+  return MV_OK;
 }
 
 extern "C" int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, const float* sig_u, const float* mu_w,

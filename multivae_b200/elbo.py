@@ -16,6 +16,14 @@ def _f32c(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
 
+def _same_family(recons, xs, recon_meta):
+    """All reconstructed modalities share D, element type and distribution family (and there are 2..8 of them)."""
+    if not 2 <= len(recons) <= 8:
+        return False
+    d0, t0, f0 = xs[0][0].numel(), recons[0].dtype, recon_meta[0][0]
+    return all(x[0].numel() == d0 and r.dtype == t0 and m[0] == f0 for r, x, m in zip(recons, xs, recon_meta))
+
+
 class MoEElboFn(torch.autograd.Function):
     """loss = -sum_b sum_c [ sum_k wk*lw  |  logsumexp_k lw - log K ] / n_mods(b)
 
@@ -39,13 +47,23 @@ class MoEElboFn(torch.autograd.Function):
         lpx = torch.empty(Cn, K, B, device=dev, dtype=torch.float32)
         recons = [r.contiguous() for r in recons]
         xs = meta["x"]
-        for i, (r, x) in enumerate(zip(recons, xs)):
-            dist, scale, rescale, mrow = meta["recon"][i]
-            D = x[0].numel()
-            assert r.shape[:3] == (Cn, K, B) and r[0, 0, 0].numel() == D, (r.shape, x.shape)
-            mask_r = None if masks is None else masks[mrow]
-            C.check(lib.mv_moe_lpx_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, D, dist, scale,
-                                       rescale, C.ptr(mask_r), 1 if i > 0 else 0, C.stream()), "mv_moe_lpx_fwd")
+        for r, x in zip(recons, xs):
+            assert r.shape[:3] == (Cn, K, B) and r[0, 0, 0].numel() == x[0].numel(), (r.shape, x.shape)
+        ctx.batched = _same_family(recons, xs, meta["recon"])
+        if ctx.batched:
+            # one launch over all reconstructed modalities (same D / dtype / distribution family)
+            mrows = [None if masks is None else masks[m[3]] for m in meta["recon"]]
+            C.check(lib.mv_moe_lpx_fwd_multi(len(recons), C.ptr_array(recons), C.dtype_code(recons[0]), C.ptr_array(xs), C.ptr(lpx),
+                                             Cn, K, B, xs[0][0].numel(), meta["recon"][0][0],
+                                             C.float_array([m[1] for m in meta["recon"]]),
+                                             C.float_array([m[2] for m in meta["recon"]]), C.ptr_array(mrows), C.stream()),
+                    "mv_moe_lpx_fwd_multi")
+        else:
+            for i, (r, x) in enumerate(zip(recons, xs)):
+                dist, scale, rescale, mrow = meta["recon"][i]
+                mask_r = None if masks is None else masks[mrow]
+                C.check(lib.mv_moe_lpx_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, x[0].numel(), dist, scale,
+                                           rescale, C.ptr(mask_r), 1 if i > 0 else 0, C.stream()), "mv_moe_lpx_fwd")
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         lw, wk, coef, loss_b = f(Cn, K, B), f(Cn, K, B), f(Cn, K, B), f(B)
         g_u, g_mu_u, g_sig_u = f(Cn, K, B, L), f(Cn, B, L), f(Cn, B, L)
@@ -75,6 +93,15 @@ class MoEElboFn(torch.autograd.Function):
         masks = meta.get("masks")
         g_recons = []
         need = ctx.needs_input_grad
+        if ctx.batched and all(need[8 + i] for i in range(len(recons))):
+            g_recons = [torch.empty_like(r) for r in recons]
+            mrows = [None if masks is None else masks[m[3]] for m in meta["recon"]]
+            C.check(lib.mv_moe_lpx_bwd_multi(len(recons), C.ptr_array(recons), C.dtype_code(recons[0]), C.ptr_array(meta["x"]),
+                                             C.ptr(coef), C.ptr(g_loss), C.ptr_array(g_recons), Cn, K, B, meta["x"][0][0].numel(),
+                                             meta["recon"][0][0], C.float_array([m[1] for m in meta["recon"]]),
+                                             C.float_array([m[2] for m in meta["recon"]]), C.ptr_array(mrows), C.stream()),
+                    "mv_moe_lpx_bwd_multi")
+            recons = []
         for i, r in enumerate(recons):
             if not need[8 + i]:
                 g_recons.append(None)

@@ -44,6 +44,10 @@ def describe(name, *, B, M, K, D, L, LW):
     if sym == "mv_moe_lpx_bwd":
         # read recon + targets + coef, write g_recon (bf16)
         return {"bound": "hbm", "work": rows * D * 2 * 2 + B * D * 4 + rows * 4}
+    if sym == "mv_moe_lpx_fwd_multi":   # all M reconstructed modalities in one launch
+        return {"bound": "hbm", "work": M * (rows * D * 2 + B * D * 4) + rows * 4}
+    if sym == "mv_moe_lpx_bwd_multi":
+        return {"bound": "hbm", "work": M * (rows * D * 2 * 2 + B * D * 4) + rows * 4}
     if sym == "mv_moe_lw_fwd":
         lat = M * K * B * (L + LW) * 4
         return {"bound": "hbm", "work": 2 * lat + 3 * rows * 4 + 4 * M * B * (L + LW) * 4 * 2}
