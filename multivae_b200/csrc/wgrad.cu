@@ -29,14 +29,17 @@ struct WgAcc {
   int row_off;      // window row of block 0 (halo_lo + tap offset)
   int chunk;        // 64-channel chunk buffer of block 0
   uint32_t lbo;     // byte distance from block 0 to block 1 inside the stage
-  int t0, c0;       // output coordinates of block 0: tap, channel chunk
-  int t1, c1;       // ... of block 1 (t1 < 0: block 1 is padding, not stored)
+  int tap[2][2];    // output tap of (M block, N block); < 0: padding, not stored.  N block 1 only exists in pair mode
+  int cch[2];       // output channel chunk of each M block
 };
 
 struct WgradParams {
   int n_ktiles, kt_per_cta_stride;
   int n_chunks;                 // Cin / 64
   int N, Ncols;                 // G columns, TMEM column stride per accumulator
+  int n_mma;                    // MMA N: N, or 2 N in pair mode (the N side is the G tile and the G tile shifted by one row)
+  uint32_t g_lbo;               // byte distance between the 64-column blocks of the N side
+  uint32_t g_rows;              // rows of the G box (128, or 136 in pair mode)
   int halo_lo, R;
   uint32_t x_chunk_bytes;       // bytes of one chunk buffer (R rows x 128 B, 1 KB aligned)
   uint32_t g_bytes, g_row_bytes, g_box_cols;
@@ -92,18 +95,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         for (int c = 0; c < p.n_chunks; ++c) tc::tma_load_2d(st + size_t(c) * p.x_chunk_bytes, &tmX, &full[s], c * 64, kt * 128 - p.halo_lo);
         const int nbox = p.N / int(p.g_box_cols);
         for (int b = 0; b < nbox; ++b)
-          tc::tma_load_2d(st + g_off + size_t(b) * 128 * p.g_row_bytes, &tmG, &full[s], b * int(p.g_box_cols), kt * 128);
+          tc::tma_load_2d(st + g_off + size_t(b) * p.g_rows * p.g_row_bytes, &tmG, &full[s], b * int(p.g_box_cols), kt * 128);
       }
       __syncwarp();
       if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc = tc::idesc_bf16(128, uint32_t(p.N), 1, 1);
+    const uint32_t idesc = tc::idesc_bf16(128, uint32_t(p.n_mma), 1, 1);
     const uint32_t g_sw = p.g_row_bytes == 128 ? tc::SW_128 : tc::SW_32;
     const uint32_t g_kstep = 16 * p.g_row_bytes;                       // 16 pixel rows per UMMA K step
     // G: blocks of 64 columns are separate boxes (128 rows x 128 B) -> LBO = 16 KB; 8-row groups -> SBO
-    const uint64_t g_desc0 = tc::smem_desc(0, 128 * p.g_row_bytes, 8 * p.g_row_bytes, g_sw);
+    const uint64_t g_desc0 = tc::smem_desc(0, p.g_lbo, 8 * p.g_row_bytes, g_sw);
     int s = 0, ph = 0, it = 0;
     for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x, ++it) {
       tc::mbar_wait(&full[s], ph);
@@ -144,7 +147,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         for (int i = 0; i < rpt; ++i) {
           const int row = rg * rpt + i;
           uint32_t off;
-          if (p.g_row_bytes == 128) off = uint32_t(cj >> 3) * 16384u + uint32_t(row) * 128u + uint32_t(((cj & 7) ^ (row & 7)) << 4);
+          if (p.g_row_bytes == 128) off = uint32_t(cj >> 3) * (p.g_rows * 128u) + uint32_t(row) * 128u + uint32_t(((cj & 7) ^ (row & 7)) << 4);
           else off = uint32_t(row) * p.g_row_bytes + uint32_t((cj ^ ((row >> 2) & 1)) << 4);   // SWIZZLE_32B
           const uint4 v = *reinterpret_cast<const uint4*>(gt + off);
           acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
@@ -173,13 +176,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const int blk = m >> 6, ch = m & 63;
     for (int a = 0; a < nacc; ++a) {
       const WgAcc& A = accs[a];
-      const int t = blk == 0 ? A.t0 : A.t1, cc = blk == 0 ? A.c0 : A.c1;
-      for (int n0 = 0; n0 < p.N; n0 += 16) {
+      const int cc = A.cch[blk];
+      for (int n0 = 0; n0 < p.n_mma; n0 += 16) {
+        const int nb = n0 >= p.N ? 1 : 0;          // N block (pair mode: the row-shifted copy of G)
+        const int t = A.tap[blk][nb];
         uint32_t v[16];
         tc::tmem_ld_32x16(tmem_base + uint32_t(a * p.Ncols + n0) + (uint32_t(q * 32) << 16), v);
         tc::tmem_ld_wait();
         if (any && t >= 0) {
-          float* dst = p.dW + (size_t(t) * p.N_total_out + n0) * p.Cin + cc * 64 + ch;
+          float* dst = p.dW + (size_t(t) * p.N_total_out + (n0 - nb * p.N)) * p.Cin + cc * 64 + ch;
 #pragma unroll
           for (int j = 0; j < 16; ++j) atomicAdd(dst + size_t(j) * p.Cin, __uint_as_float(v[j]));
         }
@@ -226,13 +231,44 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   p.n_ktiles = int((P + 127) / 128);
   // +8 rows of slack: the padding block of an odd tap count may read a few rows past the window
   p.x_chunk_bytes = (uint32_t(p.R + 8) * 128u + 1023u) & ~1023u;
+  // Pair mode (Cin = 64, N = 64, a 3x3 tap pattern): the plain scheme issues N = 64 MMAs, which are bound by the operand
+  // fetch (51 cycles against 32 of math, tests/cuda/mma_rate.cu).  Here the N side is the G tile AND the G tile shifted
+  // by one row (N = 128, math-bound), the M side two X shifts per filter row:
+  //   D[(xa, c), (gb, n)] = sum_p X[p + xa, c] G[p + gb, n] = dW at tap offset xa - gb      (the shifted sum covers the same
+  //   rows over all tiles; rows outside the tensors read as zeros)
+  // with xa in {base - 1, base + 1}, gb in {0, 1}: offsets base-1, base-2 (unused), base+1, base -> the three taps of a
+  // filter row from 8 MMAs instead of 12, each twice as efficient.
+  int Wp3 = 0;
+  bool pair = false;
+  if (Cin == 64 && N == 64 && T == 9 && N_total == N && !getenv("MV_WG_NO_PAIR")) {
+    Wp3 = tap_off[7] - tap_off[4];
+    pair = Wp3 >= 2;
+    for (int r = 0; r < 3 && pair; ++r)
+      for (int s2 = 0; s2 < 3; ++s2)
+        if (tap_off[3 * r + s2] != (r - 1) * Wp3 + (s2 - 1)) pair = false;
+  }
   p.g_row_bytes = N >= 64 ? 128u : uint32_t(N) * 2u;
   p.g_box_cols = N >= 64 ? 64u : uint32_t(N);
-  p.g_bytes = 128u * uint32_t(N) * 2u;
+  p.g_rows = pair ? 136u : 128u;
+  p.n_mma = pair ? 2 * N : N;
+  p.g_lbo = pair ? p.g_row_bytes : 128u * p.g_row_bytes;
+  p.Ncols = p.n_mma < 32 ? 32 : p.n_mma;
+  p.g_bytes = p.g_rows * uint32_t(N) * 2u;
   p.stage_bytes = uint32_t(p.n_chunks) * p.x_chunk_bytes + ((p.g_bytes + 1023u) & ~1023u);
   // accumulator table
   int na = 0;
-  if (p.n_chunks == 1) {
+  if (pair) {
+    for (int r = 0; r < 3; ++r) {
+      WgAcc& A = p.acc[na++];
+      const int base = (r - 1) * Wp3;
+      A.row_off = p.halo_lo + base - 1;
+      A.chunk = 0;
+      A.lbo = 2u * 128u;                       // M block 1 = the same window two rows further (base + 1)
+      A.tap[0][0] = 3 * r + 0; A.tap[0][1] = -1;
+      A.tap[1][0] = 3 * r + 2; A.tap[1][1] = 3 * r + 1;
+      A.cch[0] = A.cch[1] = 0;
+    }
+  } else if (p.n_chunks == 1) {
     // pair taps: block 1 is the same buffer shifted to another tap (taps sorted by offset so that LBO > 0)
     int order[9];
     for (int t = 0; t < T; ++t) order[t] = t;
@@ -243,14 +279,15 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
       WgAcc& A = p.acc[na++];
       A.row_off = p.halo_lo + tap_off[order[i]];
       A.chunk = 0;
-      A.t0 = order[i]; A.c0 = 0;
+      A.tap[0][0] = order[i]; A.tap[0][1] = -1; A.tap[1][1] = -1;
+      A.cch[0] = A.cch[1] = 0;
       if (i + 1 < T && tap_off[order[i + 1]] > tap_off[order[i]]) {
         A.lbo = uint32_t(tap_off[order[i + 1]] - tap_off[order[i]]) * 128u;
-        A.t1 = order[i + 1]; A.c1 = 0;
+        A.tap[1][0] = order[i + 1];
         i += 2;
       } else {
         A.lbo = 128u;  // padding block: one row further, never stored
-        A.t1 = -1; A.c1 = 0;
+        A.tap[1][0] = -1;
         i += 1;
       }
     }
@@ -262,7 +299,8 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
         A.row_off = p.halo_lo + tap_off[t];
         A.chunk = c;
         A.lbo = p.x_chunk_bytes;
-        A.t0 = t; A.c0 = c; A.t1 = t; A.c1 = c + 1;
+        A.tap[0][0] = t; A.tap[1][0] = t; A.tap[0][1] = A.tap[1][1] = -1;
+        A.cch[0] = c; A.cch[1] = c + 1;
       }
   }
   const int per_pass_max = 512 / p.Ncols > kWgMaxAcc ? kWgMaxAcc : 512 / p.Ncols;
@@ -285,7 +323,7 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   CUtensorMap tmX, tmG;
   const bool ok = tc::make_tmap_2d_bf16(&tmX, X, uint64_t(x_rows), uint64_t(Cin), uint64_t(x_ld) * 2, uint32_t(p.R), 64,
                                         CU_TENSOR_MAP_SWIZZLE_128B) &&
-                  tc::make_tmap_2d_bf16(&tmG, G, uint64_t(g_rows), uint64_t(N), uint64_t(g_ld) * 2, 128, p.g_box_cols,
+                  tc::make_tmap_2d_bf16(&tmG, G, uint64_t(g_rows), uint64_t(N), uint64_t(g_ld) * 2, p.g_rows, p.g_box_cols,
                                         N >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
   if (!ok) {
     mv::set_error("mv_wgrad: cuTensorMapEncodeTiled failed");

@@ -91,7 +91,7 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
     return out
 
 
-def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=False):
+def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=False, db=None):
     """dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]  (fp32 [T, N, Cin]); see mv_wgrad.
     want_db: also return db[n] = sum_p G[p, n] (bias gradient), fused into the same kernel."""
     import ctypes
@@ -103,7 +103,10 @@ def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=Fals
         dW = torch.zeros(T, N, Cin, device=X.device, dtype=torch.float32)
     offs = (ctypes.c_int32 * 9)(*[int(o) for o in tap_off])
     kw = {} if tag is None else {"tag": tag}
-    db = torch.zeros(N, device=X.device, dtype=torch.float32) if want_db else None
+    if want_db and db is None:
+        db = torch.zeros(N, device=X.device, dtype=torch.float32)
+    if not want_db:
+        db = None
     dbp = None if db is None else db.data_ptr()
     if N <= 128:
         C.check(lib.mv_wgrad(X.data_ptr(), X.shape[0], X.stride(0), Cin, G.data_ptr(), G.shape[0], G.stride(0), N, T, offs, P,
@@ -115,6 +118,24 @@ def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=Fals
             C.check(lib.mv_wgrad_slice(X.data_ptr(), X.shape[0], X.stride(0), Cin, Gs.data_ptr(), G.shape[0], G.stride(0), 128, T,
                                        offs, P, dW.data_ptr(), N, n0, dbp, C.stream(), **kw), "mv_wgrad_slice")
     return (dW, db) if want_db else dW
+
+
+class ZeroArena:
+    """One zero-filled fp32 buffer handed out in slices: the accumulating outputs (dW, db) of all weight-gradient launches
+    of a backward pass share ONE fill kernel instead of one each."""
+
+    def __init__(self, n_floats, device):
+        self.buf = torch.zeros(n_floats, device=device, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 3) // 4 * 4   # keep 16-byte alignment
+        assert self.off <= self.buf.numel(), "ZeroArena too small"
+        return t
 
 
 def unpack_conv_wgrad(dW, kh, kw):

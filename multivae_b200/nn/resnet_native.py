@@ -103,17 +103,26 @@ def _block_fwd(x, g, blk, tag):
     return out, h, d
 
 
-def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True):
+def _block_wgrad_floats(blk):
+    """fp32 elements of a block's weight/bias gradients (ZeroArena sizing; +4 per tensor for alignment)."""
+    n = 9 * blk.cout * blk.hid + blk.cout + 9 * blk.hid * blk.cin + blk.hid + 16
+    if blk.wsc is not None:
+        n += blk.cout * blk.cin + 4
+    return n
+
+
+def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None):
     """g_out: gradient of the block output; g_dpre = 0.1 * g_out * lrelu'(d) (produced upstream).
     Returns (g_x, dW0, db0, dW1, db1, dWsc)."""
     taps = g.taps3x3()
-    dW1, db1 = HL.wgrad(h, g_dpre, 9, taps, g.P, tag=f"{tag}.c1", want_db=True)
+    z = (lambda *s: None) if arena is None else arena.take
+    dW1, db1 = HL.wgrad(h, g_dpre, 9, taps, g.P, tag=f"{tag}.c1", want_db=True, dW=z(9, blk.cout, blk.hid), db=z(blk.cout))
     g_hpre = HL.tapgemm(g_dpre, blk.w1d, 9, taps, blk.hid, g.P, dact1=h, slope1=_LRELU, geom=g, tag=f"{tag}.c1d")
-    dW0, db0 = HL.wgrad(x, g_hpre, 9, taps, g.P, tag=f"{tag}.c0", want_db=True)
+    dW0, db0 = HL.wgrad(x, g_hpre, 9, taps, g.P, tag=f"{tag}.c0", want_db=True, dW=z(9, blk.hid, blk.cin), db=z(blk.hid))
     dWsc = None
     g_short = g_out
     if blk.wsc is not None:
-        dWsc = HL.wgrad(x, g_out, 1, [0], g.P, tag=f"{tag}.sc")
+        dWsc = HL.wgrad(x, g_out, 1, [0], g.P, tag=f"{tag}.sc", dW=z(1, blk.cout, blk.cin))
         g_short = HL.tapgemm(g_out, blk.wscd, 1, [0], blk.cin, g.P, geom=g, tag=f"{tag}.scd") if need_gx else None
     g_x = None
     if need_gx:
@@ -163,16 +172,17 @@ class DecoderStackFn(torch.autograd.Function):
         gh = torch.empty(g28.P, 16, device=h0.device, dtype=torch.bfloat16)
         C.check(lib.mv_head_grad_pack(g_recon.data_ptr(), recon.data_ptr(), gh.data_ptr(), n_img, 28, 28, n_ch, _LRELU, C.stream()),
                 "mv_head_grad_pack")
-        dWh, dbh = HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head", want_db=True)
+        arena = HL.ZeroArena(sum(_block_wgrad_floats(b) for b in (B1, B2, B3)) + 9 * 16 * B3.cout + 32, h0.device)
+        dWh, dbh = HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head", want_db=True, dW=arena.take(9, 16, B3.cout), db=arena.take(16))
         g_dpre3 = torch.empty(g28.P, B3.cout, device=h0.device, dtype=torch.bfloat16)
         g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, dact2=d3, slope2=_LRELU, geom=g28,
                           tag="head.d")
-        g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3")
+        g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3", arena=arena)
         g_o2, g_dpre2 = _upsample_bwd(g_u2, d2, g14, B2.cout, 0.1)
-        g_u1, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_dpre2, u1, h2, g14, B2, "b2")
+        g_u1, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_dpre2, u1, h2, g14, B2, "b2", arena=arena)
         g_o1, g_dpre1 = _upsample_bwd(g_u1, d1, g7, B1.cout, 0.1)
         need_h0 = ctx.needs_input_grad[0]
-        g_h0, dW10, db10, dW11, db11, dWsc1 = _block_bwd(g_o1, g_dpre1, h0, h1, g7, B1, "b1", need_gx=need_h0)
+        g_h0, dW10, db10, dW11, db11, dWsc1 = _block_bwd(g_o1, g_dpre1, h0, h1, g7, B1, "b1", need_gx=need_h0, arena=arena)
         if g_h0 is not None:
             g_h0 = g_h0[: h0.shape[0]]
         u = HL.unpack_conv_wgrad
@@ -225,7 +235,7 @@ class FcHaloFn(torch.autograd.Function):
         g = g.reshape(zb.shape[0], -1).to(torch.bfloat16)
         gz = (g @ wp).float() if ctx.needs_input_grad[0] else None
         gw = (g.t() @ zb).float()[ctx.scatter]
-        gb = g.float().sum(0)[ctx.scatter]
+        gb = g.sum(0, dtype=torch.float32)[ctx.scatter]   # fp32 accumulation straight from the bf16 rows (no fp32 copy of g)
         return gz, gw, gb
 
 
@@ -290,11 +300,12 @@ class EncoderStackFn(torch.autograd.Function):
         g_d3pre = torch.empty_like(g3)
         C.check(lib.mv_scale_dact(g3.data_ptr(), d3.data_ptr(), g_d3pre.data_ptr(), g7.P, B3.cout, 0.1, _LRELU, C.stream()),
                 "mv_scale_dact")
-        g_x3, dW30, db30, dW31, db31, dWsc3 = _block_bwd(g3, g_d3pre, x3, h3, g7, B3, "e3")
+        arena = HL.ZeroArena(sum(_block_wgrad_floats(b) for b in (B1, B2, B3)), x16.device)
+        g_x3, dW30, db30, dW31, db31, dWsc3 = _block_bwd(g3, g_d3pre, x3, h3, g7, B3, "e3", arena=arena)
         g_o2, g_d2pre = _avgpool_bwd(g_x3, d2, g14, B2.cout, 0.1)
-        g_x2, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_d2pre, x2, h2, g14, B2, "e2")
+        g_x2, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_d2pre, x2, h2, g14, B2, "e2", arena=arena)
         g_o1, g_d1pre = _avgpool_bwd(g_x2, d1, g28, B1.cout, 0.1)
-        g_a0, dW10, db10, dW11, db11, _ = _block_bwd(g_o1, g_d1pre, a0, h1, g28, B1, "e1")
+        g_a0, dW10, db10, dW11, db11, _ = _block_bwd(g_o1, g_d1pre, a0, h1, g28, B1, "e1", arena=arena)
         # conv_img (3 -> 64): weight gradient with the operand roles swapped (the 16-channel image is the N side),
         # dWs[t, c, n] = sum_p x[p + off_t, c] * g_a0[p, n]
         dWs = HL.wgrad(g_a0, x16, 9, [-o for o in g28.taps3x3()], g28.P, tag="e.img")       # [9, 16, 64]
@@ -325,7 +336,7 @@ class FcFromHaloFn(torch.autograd.Function):
     def backward(ctx, g_mu, g_lv):
         h2, wp = ctx.saved_tensors
         g = torch.cat([g_mu, g_lv], 1)
-        gb = g.float().sum(0)
+        gb = g.sum(0, dtype=torch.float32)
         g16 = g.to(torch.bfloat16)
         gw = (g16.t() @ h2).float()[:, ctx.scatter]
         gh = (g16 @ wp).reshape(-1, 256)
