@@ -49,6 +49,7 @@ struct Conv3Params {
   uint32_t in_stage_bytes, w_bytes;
   const float* bias;
   float neg, alpha, slope1;
+  int inplace;              // first output written in place over the side tile (released by the group leader after the TMA store)
   int side_stages, n_stg;   // side-tile ring depth; staging tiles per epilogue group (outputs not written in place)
   int img_stride, Wp, W, n_img;
   uint32_t flags;
@@ -113,7 +114,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
     tc::mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kC3EpiWarps / G); }
-    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], G == 2 ? 1 : kC3EpiWarps); }
+    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], p.inplace ? 1 : kC3EpiWarps / G); }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
@@ -221,7 +222,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // G = 2 writes the first output IN PLACE over the side tile (its staging would not fit twice); the tile is then released by
     // the group leader once the TMA store has read it.  G = 1 keeps a separate staging tile and every warp releases the side
     // tile as soon as it has read its part (a longer-held ring of 3 tiles costs more than the staging tile).
-    constexpr bool kInPlace = G == 2;
+    const bool kInPlace = p.inplace != 0;
     const uint32_t xw = tc::smem_u32(xchg) + uint32_t(grp) * 2048u;   // [4 quarters][2: E0 of lane 31 | E2 of lane 0][64 columns] floats
     const int bar_a = 1 + grp, bar_b = 3 + grp;
     // G = 1: alpha * bias of this warp's 16 columns lives in registers (G = 2 has 32 columns per warp: shared memory)
@@ -684,24 +685,32 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   const int n_out = a->out2 ? 2 : 1;
   // shared-memory plan.  Preferred: two epilogue groups (G = 2) with a 3-stage input ring and, if there is a side input,
   // a side ring of 4 (then 3) tiles; otherwise one group (G = 1) with a side ring of 3 (then 2) tiles.
-  auto n_stg = [&](int G) { return n_out - ((G == 2 && has_side) ? 1 : 0); };
-  auto plan = [&](int G, int side_stages, int in_stages) {
-    return fixed + p.w_bytes + size_t(G) * size_t(n_stg(G)) * 16384 + size_t(side_stages) * 16384 + size_t(in_stages) * p.in_stage_bytes;
+  // shared-memory plans, in order of preference:
+  //   no side input:  two epilogue groups, 3-4 input stages
+  //   side input:     two groups, separate staging, side ring of 3, TWO input stages (each stage is a whole tile and the
+  //                   epilogue, not the MMA, sets the pace) - or one group with 3 input stages
+  auto plan = [&](int G, int nstg, int side_stages, int in_stages) {
+    return fixed + p.w_bytes + size_t(G) * size_t(nstg) * 16384 + size_t(side_stages) * 16384 + size_t(in_stages) * p.in_stage_bytes;
   };
-  int G = 0;
-  // (measured: with a side input the in-place ring of 4 is saturated and two groups gain nothing — one group there)
-  if (!getenv("MV_C3_ONE_GROUP") && p.n_kc == 1 && (!has_side || getenv("MV_C3_TWO_GROUPS"))) {
-    for (int ssn = has_side ? 4 : 0; ssn >= (has_side ? 3 : 0) && !G; --ssn)
-      if (plan(2, ssn, 3) <= kC3SmemLimit) { G = 2; p.side_stages = ssn; }
+  int G = 0, in_min = 3;
+  const bool one_group = getenv("MV_C3_ONE_GROUP") != nullptr || p.n_kc != 1;
+  if (!one_group && !has_side && plan(2, n_out, 0, 3) <= kC3SmemLimit) { G = 2; p.n_stg = n_out; p.side_stages = 0; }
+  if (!G && !one_group && has_side && !getenv("MV_C3_SIDE_ONE_GROUP")) {
+    if (getenv("MV_C3_INPLACE") && plan(2, n_out - 1, 4, 3) <= kC3SmemLimit) {
+      G = 2; p.n_stg = n_out - 1; p.side_stages = 4; p.inplace = 1;
+    } else if (plan(2, n_out, 3, 2) <= kC3SmemLimit) {
+      G = 2; p.n_stg = n_out; p.side_stages = 3; in_min = 2;
+    }
   }
   if (!G) {
+    in_min = p.n_kc == 1 ? 3 : 2;
     for (int ssn = has_side ? 3 : 0; ssn >= (has_side ? 2 : 0) && !G; --ssn)
-      if (plan(1, ssn, p.n_kc == 1 ? 3 : 2) <= kC3SmemLimit) { G = 1; p.side_stages = ssn; }
+      if (plan(1, n_out, ssn, in_min) <= kC3SmemLimit) { G = 1; p.n_stg = n_out; p.side_stages = ssn; }
   }
   if (!G) return MV_OK;
-  p.n_stg = n_stg(G);
-  p.in_stages = int((kC3SmemLimit - plan(G, p.side_stages, 0)) / p.in_stage_bytes);
+  p.in_stages = int((kC3SmemLimit - plan(G, p.n_stg, p.side_stages, 0)) / p.in_stage_bytes);
   if (p.in_stages > kC3MaxStages) p.in_stages = kC3MaxStages;
+  if (p.in_stages < in_min) return MV_OK;
   if (const char* e = getenv("MV_TG_IN_STAGES")) {
     int v = atoi(e);
     if (v >= 1 && v <= p.in_stages) p.in_stages = v;
@@ -733,7 +742,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     mv::set_error("mv_tapgemm(conv3): cuTensorMapEncodeTiled failed for the outputs / side input");
     return MV_ERR_CUDA;
   }
-  const size_t smem = plan(G, p.side_stages, p.in_stages);
+  const size_t smem = plan(G, p.n_stg, p.side_stages, p.in_stages);
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define MV_C3_LAUNCH_G(FLAGS, G_)                                                                                        \
