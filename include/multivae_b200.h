@@ -199,6 +199,20 @@ int mv_avgpool3s2_bwd(const void* g_out, const void* act, void* g_in, void* g_pr
                       float slope, void* stream);
 int mv_scale_dact(const void* g, const void* act, void* out, int64_t P, int C, float alpha, float slope, void* stream);
 
+/* All convolution-weight packs of a network in one launch.  Each item turns an fp32 Conv2d weight [N, C, kh, kw] (T = kh*kw)
+ * into the bf16 operand matrices of mv_tapgemm: dst_fwd [T * Npad, Cpad] (row t*Npad + n, column c) for the forward pass and
+ * dst_dgrad [T * Cpad, Npad] (row (T-1-t)*Cpad + c, column n: taps flipped, channel roles swapped) for the data gradient;
+ * either destination may be NULL.  Padding rows / columns (Npad > N, Cpad > C) are written as zeros.  Replaces the per-layer
+ * permute / flip / cast of the reference-side autograd graph (nn.Conv2d weights of models/nn/mmnist.py:229-241,287,352). */
+#define MV_PACK_MAX_ITEMS 24
+typedef struct mv_pack_item {
+  const void* src;      /* fp32 [N, C, T] */
+  void* dst_fwd;        /* bf16 [T * Npad, Cpad] or NULL */
+  void* dst_dgrad;      /* bf16 [T * Cpad, Npad] or NULL */
+  int32_t N, C, T, Npad, Cpad;
+} mv_pack_item;
+int mv_pack_conv_weights(const mv_pack_item* items, int n_items, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,12 @@ class TapGemmArgs(ctypes.Structure):
     ]
 
 
+class PackItem(ctypes.Structure):
+    """mv_pack_item of include/multivae_b200.h."""
+    _fields_ = [("src", c_void_p), ("dst_fwd", c_void_p), ("dst_dgrad", c_void_p), ("N", ctypes.c_int32), ("C", ctypes.c_int32),
+                ("T", ctypes.c_int32), ("Npad", ctypes.c_int32), ("Cpad", ctypes.c_int32)]
+
+
 # symbol -> argtypes, exactly the prototypes in include/multivae_b200.h
 _PROTOS = {
     "mv_version": [ctypes.POINTER(c_int)] * 3,
@@ -63,6 +69,7 @@ _PROTOS = {
     "mv_avgpool3s2_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "mv_avgpool3s2_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
     "mv_scale_dact": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p],
+    "mv_pack_conv_weights": [ctypes.POINTER(PackItem), c_int, c_void_p],
     "mv_wgrad_slice": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                        c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "mv_wgrad": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),

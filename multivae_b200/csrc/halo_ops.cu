@@ -304,3 +304,50 @@ extern "C" int mv_colsum(const void* G, int64_t P, int ld, int N, float* out, vo
   MV_CHECK_LAUNCH("mv_colsum");
   return MV_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight packs of a whole network in ONE launch: fp32 Conv2d weights [N, C, kh, kw] -> bf16 tap-major K-major matrices for
+// the forward pass [T * Npad, Cpad] and (taps flipped, roles swapped) for the data gradient [T * Cpad_d, Npad_d]
+// (what multivae_b200/nn/halo.py pack_conv_weight / pack_conv_weight_dgrad build with ~3 ATen kernels per layer).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace mv {
+struct PackBatch {
+  mv_pack_item it[MV_PACK_MAX_ITEMS];
+};
+__global__ void __launch_bounds__(256) pack_conv_weights_kernel(const __grid_constant__ PackBatch b) {
+  const mv_pack_item& w = b.it[blockIdx.y];
+  const float* __restrict__ src = static_cast<const float*>(w.src);
+  bf16* __restrict__ fwd = static_cast<bf16*>(w.dst_fwd);
+  bf16* __restrict__ dg = static_cast<bf16*>(w.dst_dgrad);
+  const int T = w.T;
+  const int64_t total = int64_t(T) * w.Npad * w.Cpad;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(e % w.Cpad);
+    const int64_t tn = e / w.Cpad;
+    const int n = int(tn % w.Npad), t = int(tn / w.Npad);
+    const float v = (n < w.N && c < w.C) ? src[(int64_t(n) * w.C + c) * T + t] : 0.f;
+    const bf16 h = __float2bfloat16_rn(v);
+    if (fwd) fwd[e] = h;                                                        // [(t * Npad + n), c]
+    if (dg) dg[(int64_t(T - 1 - t) * w.Cpad + c) * w.Npad + n] = h;             // [((T-1-t) * Cpad + c), n]
+  }
+}
+}  // namespace mv
+
+extern "C" int mv_pack_conv_weights(const mv_pack_item* items, int n_items, void* stream) {
+  MV_CHECK_ARG(items && n_items >= 1 && n_items <= MV_PACK_MAX_ITEMS, "mv_pack_conv_weights: 1 <= n_items <= %d", MV_PACK_MAX_ITEMS);
+  mv::PackBatch b{};
+  int64_t biggest = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const mv_pack_item& w = items[i];
+    MV_CHECK_ARG(w.src && (w.dst_fwd || w.dst_dgrad), "mv_pack_conv_weights: null pointer in item %d", i);
+    MV_CHECK_ARG(w.N >= 1 && w.C >= 1 && w.T >= 1 && w.Npad >= w.N && w.Cpad >= w.C, "mv_pack_conv_weights: bad sizes in item %d", i);
+    b.it[i] = w;
+    const int64_t total = int64_t(w.T) * w.Npad * w.Cpad;
+    biggest = total > biggest ? total : biggest;
+  }
+  int gx = int((biggest + 256 * 4 - 1) / (256 * 4));
+  gx = gx < 1 ? 1 : (gx > 1184 ? 1184 : gx);
+  mv::pack_conv_weights_kernel<<<dim3(gx, n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+  MV_CHECK_LAUNCH("mv_pack_conv_weights");
+  return MV_OK;
+}

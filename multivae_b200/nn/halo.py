@@ -52,6 +52,26 @@ def pack_conv_weight_dgrad(w, dtype=torch.bfloat16):
     return w.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(kh * kw * c, n).to(dtype).contiguous()
 
 
+def pack_conv_weights(specs):
+    """All weight packs of a network in ONE kernel (mv_pack_conv_weights).
+    specs: list of (weight [N, C, kh, kw] fp32, Npad, Cpad, want_dgrad) -> list of (fwd [T*Npad, Cpad], dgrad [T*Cpad, Npad] | None),
+    the same matrices as pack_conv_weight / pack_conv_weight_dgrad on the zero-padded weight."""
+    items = (C.PackItem * len(specs))()
+    outs = []
+    for it, (w, npad, cpad, want_d) in zip(items, specs):
+        w = w.detach()
+        assert w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda
+        n, c, kh, kw = w.shape
+        t = kh * kw
+        fwd = torch.empty(t * npad, cpad, device=w.device, dtype=torch.bfloat16)
+        dg = torch.empty(t * cpad, npad, device=w.device, dtype=torch.bfloat16) if want_d else None
+        it.src, it.dst_fwd, it.dst_dgrad = w.data_ptr(), fwd.data_ptr(), None if dg is None else dg.data_ptr()
+        it.N, it.C, it.T, it.Npad, it.Cpad = n, c, t, npad, cpad
+        outs.append((fwd, dg))
+    C.check(C.lib().mv_pack_conv_weights(items, len(specs), C.stream()), "mv_pack_conv_weights")
+    return outs
+
+
 def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act="none", alpha=1.0, res=None, dact1=None,
             slope1=0.2, out=None, out2=None, out2_pre=False, alpha2=1.0, dact2=None, slope2=0.2, geom=None,
             nchw_out=None, n_valid=0, tag=None):

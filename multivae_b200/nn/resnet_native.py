@@ -82,14 +82,30 @@ def _pack_image(x_bf16, g, y_out=None):
 class _Block:
     """bf16 packs of one ResnetBlock's weights (forward and data-gradient orientation)."""
 
-    def __init__(self, w0, b0, w1, b1, wsc):
+    def __init__(self, w0, b0, w1, b1, wsc, packs):
         self.cin, self.hid, self.cout = w0.shape[1], w0.shape[0], w1.shape[0]
-        self.w0, self.w0d = HL.pack_conv_weight(w0), HL.pack_conv_weight_dgrad(w0)
-        self.w1, self.w1d = HL.pack_conv_weight(w1), HL.pack_conv_weight_dgrad(w1)
+        (self.w0, self.w0d), (self.w1, self.w1d) = packs[0], packs[1]
         self.b0, self.b1 = b0.detach().float().contiguous(), b1.detach().float().contiguous()
         self.wsc = self.wscd = None
         if wsc is not None:
-            self.wsc, self.wscd = HL.pack_conv_weight(wsc), HL.pack_conv_weight_dgrad(wsc)
+            self.wsc, self.wscd = packs[2]
+
+
+def _pack_network(blocks, extra):
+    """One mv_pack_conv_weights launch for a whole stack: `blocks` = [(w0, b0, w1, b1, wsc | None)], `extra` = further
+    (weight, Npad, Cpad, want_dgrad) specs.  Returns ([_Block], [packs of the extra specs])."""
+    specs = []
+    for w0, b0, w1, b1, wsc in blocks:
+        specs += [(w0, w0.shape[0], w0.shape[1], True), (w1, w1.shape[0], w1.shape[1], True)]
+        if wsc is not None:
+            specs.append((wsc, wsc.shape[0], wsc.shape[1], True))
+    packs = HL.pack_conv_weights(specs + list(extra))
+    out, i = [], 0
+    for w0, b0, w1, b1, wsc in blocks:
+        n = 2 if wsc is None else 3
+        out.append(_Block(w0, b0, w1, b1, wsc, packs[i:i + n]))
+        i += n
+    return out, packs[i:]
 
 
 def _block_fwd(x, g, blk, tag):
@@ -137,11 +153,8 @@ class DecoderStackFn(torch.autograd.Function):
     def forward(ctx, h0, n_img, *params):
         (w10, b10, w11, b11, wsc1, w20, b20, w21, b21, wsc2, w30, b30, w31, b31, wh, bh) = params
         dev = h0.device
-        B1 = _Block(w10, b10, w11, b11, wsc1)
-        B2 = _Block(w20, b20, w21, b21, wsc2)
-        B3 = _Block(w30, b30, w31, b31, None)
-        whp = torch.zeros(16, wh.shape[1], 3, 3, device=dev, dtype=wh.dtype)
-        whp[: wh.shape[0]] = wh.detach()
+        (B1, B2, B3), ((whf, whd),) = _pack_network([(w10, b10, w11, b11, wsc1), (w20, b20, w21, b21, wsc2), (w30, b30, w31, b31, None)],
+                                                    [(wh, 16, wh.shape[1], True)])   # image head: 3 -> 16 output channels (zeros)
         bhp = torch.zeros(16, device=dev, dtype=torch.float32)
         bhp[: wh.shape[0]] = bh.detach().float()
         g7 = HL.Geom(n_img, 7, 7)
@@ -152,10 +165,9 @@ class DecoderStackFn(torch.autograd.Function):
         o3, h3, d3 = _block_fwd(u2, g28, B3, "b3")
         n_ch = wh.shape[0]
         recon = torch.empty(n_img, n_ch, 28, 28, device=dev, dtype=torch.bfloat16)
-        HL.tapgemm(o3, HL.pack_conv_weight(whp), 9, g28.taps3x3(), 16, g28.P, bias=bhp, act="lrelu", geom=g28, nchw_out=recon,
-                   n_valid=n_ch, tag="head")
+        HL.tapgemm(o3, whf, 9, g28.taps3x3(), 16, g28.P, bias=bhp, act="lrelu", geom=g28, nchw_out=recon, n_valid=n_ch, tag="head")
         ctx.save_for_backward(h0, h1, d1, u1, h2, d2, u2, h3, d3, o3, recon)
-        ctx.packs = (B1, B2, B3, HL.pack_conv_weight_dgrad(whp))
+        ctx.packs = (B1, B2, B3, whd)
         ctx.n_img, ctx.n_ch = n_img, n_ch
         return recon
 
@@ -270,13 +282,9 @@ class EncoderStackFn(torch.autograd.Function):
         n_img = x.shape[0]
         g28 = HL.Geom(n_img, 28, 28)
         x16 = _pack_image(x.detach().to(torch.bfloat16).contiguous(), g28)
-        wip = torch.zeros(wi.shape[0], 16, 3, 3, device=x.device, dtype=wi.dtype)
-        wip[:, : wi.shape[1]] = wi.detach()
-        a0 = HL.tapgemm(x16, HL.pack_conv_weight(wip), 9, g28.taps3x3(), wi.shape[0], g28.P, bias=bi.detach().float().contiguous(),
-                        geom=g28, tag="e.img")
-        B1 = _Block(w10, b10, w11, b11, None)
-        B2 = _Block(w20, b20, w21, b21, wsc2)
-        B3 = _Block(w30, b30, w31, b31, wsc3)
+        (B1, B2, B3), ((wif, _),) = _pack_network([(w10, b10, w11, b11, None), (w20, b20, w21, b21, wsc2), (w30, b30, w31, b31, wsc3)],
+                                                  [(wi, wi.shape[0], 16, False)])   # image conv: 3 -> 16 input channels (zeros)
+        a0 = HL.tapgemm(x16, wif, 9, g28.taps3x3(), wi.shape[0], g28.P, bias=bi.detach().float().contiguous(), geom=g28, tag="e.img")
         o1, h1, d1 = _block_fwd(a0, g28, B1, "e1")
         x2, g14 = _avgpool_fwd(o1, g28, B1.cout)
         o2, h2, d2 = _block_fwd(x2, g14, B2, "e2")

@@ -134,3 +134,19 @@ def test_linear(rows, K, N):
     b = _rnd(N, seed=18)
     out = HL.tapgemm(x, w, 1, [0], N, rows, bias=b, act="relu")
     _close(out, F.relu(F.linear(x.float(), w.float(), b)))
+
+
+def test_pack_conv_weights_kernel_matches_torch_packs():
+    """mv_pack_conv_weights (all packs of a network in one launch) against pack_conv_weight / pack_conv_weight_dgrad."""
+    from multivae_b200.nn import halo as HL
+    ws = [_rnd(64, 64, 3, 3, seed=31), _rnd(128, 256, 1, 1, seed=32), _rnd(3, 64, 3, 3, seed=33), _rnd(64, 3, 3, 3, seed=34)]
+    specs = [(ws[0], 64, 64, True), (ws[1], 128, 256, True), (ws[2], 16, 64, True), (ws[3], 64, 16, False)]
+    packs = HL.pack_conv_weights(specs)
+    for (w, npad, cpad, want_d), (fwd, dg) in zip(specs, packs):
+        wp = torch.zeros(npad, cpad, *w.shape[2:], device="cuda")
+        wp[: w.shape[0], : w.shape[1]] = w
+        assert torch.equal(fwd, HL.pack_conv_weight(wp))
+        if want_d:
+            assert torch.equal(dg, HL.pack_conv_weight_dgrad(wp))
+        else:
+            assert dg is None
