@@ -180,6 +180,12 @@ int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, in
 int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
                    const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, float* db, void* stream);
 
+/* same contraction, accumulated straight into a gradient tensor in the torch Conv2d layout: dW[(n_offset + n), c, t] (fp32
+ * [N_out, Cin, T], e.g. `weight.grad` itself) += ..., only for n < n_valid (output columns beyond are padding); db[n_offset + n]
+ * likewise.  Lets the training step skip the permuted copy and the separate `grad += ...` kernel per parameter. */
+int mv_wgrad_nct(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N, int T,
+                 const int* tap_off, int64_t P, float* dW, int n_offset, int n_valid, float* db, void* stream);
+
 /* HBM-bound helpers of the shared-halo layout (all tensors bf16 unless noted):
  *   mv_upsample2x_fwd  nn.Upsample(scale_factor=2) (models/nn/mmnist.py:345): in (H x W, C ch) -> out (2H x 2W, C ch)
  *   mv_upsample2x_bwd  its gradient: g_in = sum of the 2x2 children of g_out; optional g_pre = alpha*g_in*lrelu'(act)

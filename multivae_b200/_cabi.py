@@ -74,6 +74,8 @@ _PROTOS = {
                        c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "mv_wgrad": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                  c_int64, c_void_p, c_void_p, c_void_p],
+    "mv_wgrad_nct": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
+                     c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "mv_poe_bwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
 }

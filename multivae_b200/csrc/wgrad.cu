@@ -49,6 +49,7 @@ struct WgradParams {
   int acc_begin[8];
   WgAcc acc[48];
   int Cin, N_total_out;         // dW is [T][N_total_out][Cin] fp32
+  int nct, T, n_valid;          // nct: dW is [N][Cin][T] instead (the torch Conv2d layout); output columns >= n_valid are padding
   float* dW;
   float* db;                    // optional bias gradient: db[n] += sum_p G[p, n] (fused column sums of the G tiles)
   int tmem_cols;
@@ -160,7 +161,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
       for (int e = 0; e < 8; ++e) red[et * 8 + e] = acc[e];
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et < p.N) {
+      if (et < p.N && et < p.n_valid) {
         const int g2 = et >> 3, e = et & 7;
         float sum = 0.f;
         for (int r2 = 0; r2 < 128 / groups; ++r2) sum += red[(r2 * groups + g2) * 8 + e];
@@ -184,9 +185,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         tc::tmem_ld_32x16(tmem_base + uint32_t(a * p.Ncols + n0) + (uint32_t(q * 32) << 16), v);
         tc::tmem_ld_wait();
         if (any && t >= 0) {
-          float* dst = p.dW + (size_t(t) * p.N_total_out + (n0 - nb * p.N)) * p.Cin + cc * 64 + ch;
+          const int nn = n0 - nb * p.N;
+          if (p.nct) {
+            float* dst = p.dW + (size_t(nn) * p.Cin + cc * 64 + ch) * p.T + t;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + size_t(j) * p.Cin, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j)
+              if (nn + j < p.n_valid) atomicAdd(dst + size_t(j) * p.Cin * p.T, __uint_as_float(v[j]));
+          } else {
+            float* dst = p.dW + (size_t(t) * p.N_total_out + nn) * p.Cin + cc * 64 + ch;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + size_t(j) * p.Cin, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -203,9 +212,9 @@ constexpr size_t kWgSmemLimit = 232448;
 
 using namespace mv;
 
-extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
-                              int T, const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, float* db,
-                              void* stream) {
+static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
+                        int T, const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, float* db, int nct, int n_valid,
+                        void* stream) {
   MV_CHECK_ARG(N_total >= N && n_offset >= 0 && n_offset + N <= N_total, "mv_wgrad: bad column slice");
   MV_CHECK_ARG(X && G && dW && tap_off, "mv_wgrad: null pointer");
   MV_CHECK_ARG(Cin % 64 == 0 && Cin >= 64 && Cin <= 256, "mv_wgrad: Cin must be 64/128/192/256, got %d", Cin);
@@ -226,7 +235,10 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   p.Ncols = N < 32 ? 32 : N;
   p.Cin = Cin;
   p.N_total_out = N_total;
-  p.dW = dW + size_t(n_offset) * Cin;
+  p.nct = nct;
+  p.T = T;
+  p.n_valid = n_valid;
+  p.dW = dW + size_t(n_offset) * Cin * (nct ? T : 1);
   p.db = db ? db + n_offset : nullptr;
   p.n_ktiles = int((P + 127) / 128);
   // +8 rows of slack: the padding block of an odd tap count may read a few rows past the window
@@ -240,7 +252,7 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   // filter row from 8 MMAs instead of 12, each twice as efficient.
   int Wp3 = 0;
   bool pair = false;
-  if (Cin == 64 && N == 64 && T == 9 && N_total == N && !getenv("MV_WG_NO_PAIR")) {
+  if (Cin == 64 && N == 64 && T == 9 && (N_total == N || nct) && !getenv("MV_WG_NO_PAIR")) {
     Wp3 = tap_off[7] - tap_off[4];
     pair = Wp3 >= 2;
     for (int r = 0; r < 3 && pair; ++r)
@@ -343,7 +355,20 @@ extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, 
   return MV_OK;
 }
 
+extern "C" int mv_wgrad_slice(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
+                              int T, const int* tap_off, int64_t P, float* dW, int N_total, int n_offset, float* db,
+                              void* stream) {
+  return wgrad_launch(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, N_total, n_offset, db, 0, N, stream);
+}
+
 extern "C" int mv_wgrad(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
                         int T, const int* tap_off, int64_t P, float* dW, float* db, void* stream) {
-  return mv_wgrad_slice(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, N, 0, db, stream);
+  return wgrad_launch(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, N, 0, db, 0, N, stream);
+}
+
+extern "C" int mv_wgrad_nct(const void* X, int64_t x_rows, int x_ld, int Cin, const void* G, int64_t g_rows, int g_ld, int N,
+                            int T, const int* tap_off, int64_t P, float* dW, int n_offset, int n_valid, float* db,
+                            void* stream) {
+  MV_CHECK_ARG(n_valid >= 1 && n_valid <= N, "mv_wgrad_nct: 1 <= n_valid <= N");
+  return wgrad_launch(X, x_rows, x_ld, Cin, G, g_rows, g_ld, N, T, tap_off, P, dW, n_offset + N, n_offset, db, 1, n_valid, stream);
 }

@@ -111,16 +111,16 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
     return out
 
 
-def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=False, db=None):
+def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=False, db=None, grad_out=None, n_valid=None):
     """dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]  (fp32 [T, N, Cin]); see mv_wgrad.
-    want_db: also return db[n] = sum_p G[p, n] (bias gradient), fused into the same kernel."""
+    want_db: also return db[n] = sum_p G[p, n] (bias gradient), fused into the same kernel.
+    grad_out: accumulate straight into a gradient tensor in the torch Conv2d layout [n_valid, Cin, kh, kw] (e.g. weight.grad;
+    mv_wgrad_nct) instead of a [T, N, Cin] buffer; returns (grad_out, db) / grad_out."""
     import ctypes
     lib = C.lib()
     Cin = X.shape[1] if Cin is None else Cin
     N = G.shape[1] if N is None else N
     assert X.dtype == torch.bfloat16 and G.dtype == torch.bfloat16 and X.stride(1) == 1 and G.stride(1) == 1
-    if dW is None:
-        dW = torch.zeros(T, N, Cin, device=X.device, dtype=torch.float32)
     offs = (ctypes.c_int32 * 9)(*[int(o) for o in tap_off])
     kw = {} if tag is None else {"tag": tag}
     if want_db and db is None:
@@ -128,6 +128,17 @@ def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=Fals
     if not want_db:
         db = None
     dbp = None if db is None else db.data_ptr()
+    if grad_out is not None:
+        n_valid = N if n_valid is None else n_valid
+        assert grad_out.dtype == torch.float32 and grad_out.is_contiguous() and grad_out.numel() == n_valid * Cin * T
+        for n0 in range(0, N, 128):
+            nn = min(128, N - n0)
+            Gs = G[:, n0:n0 + nn]
+            C.check(lib.mv_wgrad_nct(X.data_ptr(), X.shape[0], X.stride(0), Cin, Gs.data_ptr(), G.shape[0], G.stride(0), nn, T, offs, P,
+                                     grad_out.data_ptr(), n0, min(nn, n_valid - n0), dbp, C.stream(), **kw), "mv_wgrad_nct")
+        return (grad_out, db) if want_db else grad_out
+    if dW is None:
+        dW = torch.zeros(T, N, Cin, device=X.device, dtype=torch.float32)
     if N <= 128:
         C.check(lib.mv_wgrad(X.data_ptr(), X.shape[0], X.stride(0), Cin, G.data_ptr(), G.shape[0], G.stride(0), N, T, offs, P,
                              dW.data_ptr(), dbp, C.stream(), **kw), "mv_wgrad")

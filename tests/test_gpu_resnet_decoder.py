@@ -57,3 +57,31 @@ def test_decoder_forward_backward_matches_torch_fp32(n_img):
     assert errs["recon"] < 1e-2, errs["recon"]
     for k, e in errs.items():
         assert e < max(3e-2, 2.5 * lib_err[k]), (k, e, lib_err[k])
+
+
+def test_decoder_direct_gradient_accumulation_equals_autograd_path():
+    """With pre-allocated fp32 .grad tensors (the trainer's flat buffer) the weight-gradient kernels accumulate in place
+    (mv_wgrad_nct) and the autograd Function returns None: same gradients as the path that returns them to autograd."""
+    import os
+    from multivae_b200.nn import DecoderResnetMMNIST
+    from multivae_b200.nn import functional as NF
+    torch.manual_seed(1)
+    dec = DecoderResnetMMNIST(64).cuda()
+    z = torch.randn(33, 64, device="cuda")
+    gy = (torch.randn(33, 3, 28, 28, device="cuda") * 0.1).to(torch.bfloat16)
+    NF.set_backend("native")
+    try:
+        os.environ["MULTIVAE_B200_DIRECT_GRADS"] = "0"
+        dec(z).reconstruction.backward(gy)
+        ref = {k: p.grad.clone() for k, p in dec.named_parameters()}
+        os.environ["MULTIVAE_B200_DIRECT_GRADS"] = "1"
+        for p in dec.parameters():
+            p.grad = torch.full_like(p, 0.5)       # accumulation on top of an existing gradient
+        dec(z).reconstruction.backward(gy)
+    finally:
+        os.environ.pop("MULTIVAE_B200_DIRECT_GRADS", None)
+        NF.set_backend("auto")
+    for k, p in dec.named_parameters():
+        got = p.grad - 0.5
+        err = float((got - ref[k]).abs().max()) / (float(ref[k].abs().max()) + 1e-12)
+        assert err < 2e-3, (k, err)
