@@ -29,7 +29,7 @@ struct WgAcc {
   int row_off;      // window row of block 0 (halo_lo + tap offset)
   int chunk;        // 64-channel chunk buffer of block 0
   uint32_t lbo;     // byte distance from block 0 to block 1 inside the stage
-  int tap[2][2];    // output tap of (M block, N block); < 0: padding, not stored.  N block 1 only exists in pair mode
+  int tap[2][8];    // output tap of (M block, N block); < 0: padding, not stored.  N blocks > 0 only exist in shift mode
   int cch[2];       // output channel chunk of each M block
 };
 
@@ -179,7 +179,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const WgAcc& A = accs[a];
       const int cc = A.cch[blk];
       for (int n0 = 0; n0 < p.n_mma; n0 += 16) {
-        const int nb = n0 >= p.N ? 1 : 0;          // N block (pair mode: the row-shifted copy of G)
+        const int nb = n0 / p.N;                   // N block (shift mode: the copy of G shifted by nb rows)
         const int t = A.tap[blk][nb];
         uint32_t v[16];
         tc::tmem_ld_32x16(tmem_base + uint32_t(a * p.Ncols + n0) + (uint32_t(q * 32) << 16), v);
@@ -252,32 +252,49 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   // filter row from 8 MMAs instead of 12, each twice as efficient.
   int Wp3 = 0;
   bool pair = false;
-  if (Cin == 64 && N == 64 && T == 9 && (N_total == N || nct) && !getenv("MV_WG_NO_PAIR")) {
+  if (Cin == 64 && (N == 64 || N == 16) && T == 9 && (N_total == N || nct) && !getenv("MV_WG_NO_PAIR")) {
     Wp3 = tap_off[7] - tap_off[4];
     pair = Wp3 >= 2;
     for (int r = 0; r < 3 && pair; ++r)
       for (int s2 = 0; s2 < 3; ++s2)
         if (tap_off[3 * r + s2] != (r - 1) * Wp3 + (s2 - 1)) pair = false;
   }
+  const int n_shift = !pair ? 1 : (N == 64 ? 2 : 8);   // N = 16: eight row-shifted copies of the 16-column G tile (N = 128)
   p.g_row_bytes = N >= 64 ? 128u : uint32_t(N) * 2u;
   p.g_box_cols = N >= 64 ? 64u : uint32_t(N);
   p.g_rows = pair ? 136u : 128u;
-  p.n_mma = pair ? 2 * N : N;
+  p.n_mma = n_shift * N;
   p.g_lbo = pair ? p.g_row_bytes : 128u * p.g_row_bytes;
   p.Ncols = p.n_mma < 32 ? 32 : p.n_mma;
   p.g_bytes = p.g_rows * uint32_t(N) * 2u;
   p.stage_bytes = uint32_t(p.n_chunks) * p.x_chunk_bytes + ((p.g_bytes + 1023u) & ~1023u);
   // accumulator table
   int na = 0;
-  if (pair) {
+  if (pair && N == 64) {
     for (int r = 0; r < 3; ++r) {
       WgAcc& A = p.acc[na++];
+      for (int i = 0; i < 16; ++i) (&A.tap[0][0])[i] = -1;
       const int base = (r - 1) * Wp3;
       A.row_off = p.halo_lo + base - 1;
       A.chunk = 0;
       A.lbo = 2u * 128u;                       // M block 1 = the same window two rows further (base + 1)
-      A.tap[0][0] = 3 * r + 0; A.tap[0][1] = -1;
+      A.tap[0][0] = 3 * r + 0;
       A.tap[1][0] = 3 * r + 2; A.tap[1][1] = 3 * r + 1;
+      A.cch[0] = A.cch[1] = 0;
+    }
+  } else if (pair) {
+    // N = 16 (image head): D[(r_blk, c), (i, n)] = sum_p X[p + (r-1)Wp + 1, c] G[p + i, n] = dW at tap offset (r-1)Wp + 1 - i:
+    // shifts i = 0, 1, 2 are the taps s = 2, 1, 0 of filter row r; two filter rows per accumulator (M blocks Wp rows apart)
+    for (int r0 = 0; r0 < 3; r0 += 2) {
+      WgAcc& A = p.acc[na++];
+      for (int i = 0; i < 16; ++i) (&A.tap[0][0])[i] = -1;
+      A.row_off = p.halo_lo + (r0 - 1) * Wp3 + 1;
+      A.chunk = 0;
+      A.lbo = r0 + 1 < 3 ? uint32_t(Wp3) * 128u : 128u;   // M block 1 = filter row r0 + 1 (r0 = 2: padding, one row further)
+      for (int i = 0; i < 3; ++i) {
+        A.tap[0][i] = 3 * r0 + (2 - i);
+        if (r0 + 1 < 3) A.tap[1][i] = 3 * (r0 + 1) + (2 - i);
+      }
       A.cch[0] = A.cch[1] = 0;
     }
   } else if (p.n_chunks == 1) {
@@ -291,7 +308,8 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
       WgAcc& A = p.acc[na++];
       A.row_off = p.halo_lo + tap_off[order[i]];
       A.chunk = 0;
-      A.tap[0][0] = order[i]; A.tap[0][1] = -1; A.tap[1][1] = -1;
+      for (int q2 = 0; q2 < 16; ++q2) (&A.tap[0][0])[q2] = -1;
+      A.tap[0][0] = order[i];
       A.cch[0] = A.cch[1] = 0;
       if (i + 1 < T && tap_off[order[i + 1]] > tap_off[order[i]]) {
         A.lbo = uint32_t(tap_off[order[i + 1]] - tap_off[order[i]]) * 128u;
@@ -311,7 +329,8 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
         A.row_off = p.halo_lo + tap_off[t];
         A.chunk = c;
         A.lbo = p.x_chunk_bytes;
-        A.tap[0][0] = t; A.tap[1][0] = t; A.tap[0][1] = A.tap[1][1] = -1;
+        for (int q2 = 0; q2 < 16; ++q2) (&A.tap[0][0])[q2] = -1;
+        A.tap[0][0] = t; A.tap[1][0] = t;
         A.cch[0] = c; A.cch[1] = c + 1;
       }
   }
