@@ -142,6 +142,7 @@ int mv_poe_bwd(const float* mu, const float* lv, const uint8_t* masks, const uin
  *              if out2 && out2_pre: out2[p,n] = y
  *              o = alpha*y + (res ? res[p,n] : 0);  out[p,n] = o
  *              if out2 && !out2_pre: out2[p,n] = alpha2 * o * (dact2 ? (dact2[p,n] > 0 ? 1 : slope2) : 1)
+ *              (out2_mask / dmask2: the same with the activation-derivative source stored as one sign bit per element)
  *   rows that are halo positions (img_stride > 0) are written as zeros.  out_mode 1 scatters the first
  *   n_valid columns of the valid pixels to a dense NCHW bf16 image tensor [n_img, n_valid, H, W].
  * ------------------------------------------------------------------------------------------- */
@@ -164,6 +165,11 @@ typedef struct mv_tapgemm_args {
   const void* dact2; int32_t dact2_ld; float slope2;
   int32_t img_stride, Wp, W, H, n_img;   /* halo geometry (img_stride = 0: plain GEMM, no mask) */
   int32_t out_mode, n_valid;
+  /* sign masks of an activation, one bit per element, 64-bit word per row ([rows padded to a multiple of 126][64 columns]):
+   *   out2_mask  written INSTEAD of out2 (out2 must be NULL): bit n = (act(acc + bias)[p, n] > 0); 3x3 / 64-output layers only
+   *   dmask2     read INSTEAD of dact2: the second output is alpha2 * o * (bit ? 1 : slope2); N_total = 64 only */
+  void* out2_mask;
+  const void* dmask2;
 } mv_tapgemm_args;
 int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 

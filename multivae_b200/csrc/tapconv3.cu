@@ -41,7 +41,7 @@ constexpr int kC3MaxSide = 4;
 constexpr int kC3N = 192;
 constexpr uint32_t kC3WBox = 192u * 128u;   // one filter row of weights: 3 taps x 64 output channels x 64 input channels
 
-enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_GENERIC = 0x80000000u };
+enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_GENERIC = 0x80000000u };
 
 struct Conv3Params {
   int P, m_tiles, n_kc, row_shift, R;
@@ -49,6 +49,7 @@ struct Conv3Params {
   uint32_t in_stage_bytes, w_bytes;
   const float* bias;
   float neg, alpha, slope1;
+  uint64_t* mask2;          // C3_MASK2: sign bits of the activation, one 64-bit word per row (rows padded to whole tiles)
   int inplace;              // first output written in place over the side tile (released by the group leader after the TMA store)
   int side_stages, n_stg;   // side-tile ring depth; staging tiles per epilogue group (outputs not written in place)
   int img_stride, Wp, W, n_img;
@@ -99,7 +100,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* side_base = stg_base + size_t(G) * size_t(p.n_stg) * 16384;   // side_stages tiles of 128 rows x 128 B
   float* xchg = reinterpret_cast<float*>(side_base + size_t(p.side_stages) * 16384);   // [2 parities][4 quarters][2][64]
   float* s_bias = xchg + 2 * 4 * 2 * 64;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint64_t* s_mask = reinterpret_cast<uint64_t*>(s_bias + 64);   // [2 groups][128 rows] sign-mask staging
+  uint64_t* bars = s_mask + 256;
   uint64_t* in_full = bars;
   uint64_t* in_empty = in_full + kC3MaxStages;
   uint64_t* w_full = in_empty + kC3MaxStages;
@@ -225,10 +227,10 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool kInPlace = p.inplace != 0;
     const uint32_t xw = tc::smem_u32(xchg) + uint32_t(grp) * 2048u;   // [4 quarters][2: E0 of lane 31 | E2 of lane 0][64 columns] floats
     const int bar_a = 1 + grp, bar_b = 3 + grp;
-    // G = 1: alpha * bias of this warp's 16 columns lives in registers (G = 2 has 32 columns per warp: shared memory)
+    // G = 1: the bias of this warp's 16 columns lives in registers (G = 2 has 32 columns per warp: shared memory)
     float ab[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) ab[e] = (G == 1 && c3_has<F>(p, C3_BIAS)) ? p.alpha * s_bias[cw0 + e] : 0.f;
+    for (int e = 0; e < 16; ++e) ab[e] = (G == 1 && c3_has<F>(p, C3_BIAS)) ? s_bias[cw0 + e] : 0.f;
     // Row geometry without divisions in the tile loop: this thread's row advances by a constant number of rows per tile,
     // so (row mod S) and (row mod Wp) are carried incrementally (S is a multiple of Wp, so the wrap of the first does not
     // disturb the second).
@@ -248,6 +250,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t row_off = uint32_t(srow) * 128u;
     const uint32_t stg_s = tc::smem_u32(stg_base) + uint32_t(grp) * uint32_t(p.n_stg) * 16384u;
     const uint32_t side_s = tc::smem_u32(side_base);
+    const uint32_t mask_s = tc::smem_u32(s_mask) + uint32_t(grp) * 1024u;
     const bool leader = (ew % GW) == 0 && lane == 0;   // issues the group's TMA stores
     int ss = grp % (p.side_stages > 0 ? p.side_stages : 1), sph = 0, prev_ss = -1, k = 0;
     for (int it = grp; int(blockIdx.x) + it * int(gridDim.x) < p.m_tiles; it += G, ++k) {
@@ -338,7 +341,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // alpha and the bias are folded into one FMA per element: alpha * act(acc + b) = act(alpha * acc + alpha * b), alpha > 0
         if (G == 1 && c3_has<F>(p, C3_BIAS)) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] = fmaf(al, y[e], vz * ab[e]);
+          for (int e = 0; e < 16; ++e) y[e] = al * (y[e] + ab[e]);   // same expression as the shared-memory path: bit-identical results
         } else if (c3_has<F>(p, C3_BIAS)) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -359,6 +362,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             y[2 * i] *= bf16lo(sv[i]) > 0.f ? 1.f : p.slope1;
             y[2 * i + 1] *= bf16hi(sv[i]) > 0.f ? 1.f : p.slope1;
           }
+        }
+        if (c3_has<F>(p, C3_MASK2)) {
+          // second output as sign bits only (all that lrelu' needs of the saved `d`): 16 bits of this row's 64-bit word
+          uint32_t bits = 0u;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) bits |= (y[e] > 0.f ? 1u : 0u) << e;
+          if (inner)
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(mask_s + uint32_t(srow) * 8u + uint32_t(c0 >> 4) * 2u), "h"(uint16_t(bits)) : "memory");
         }
         if (c3_has<F>(p, C3_OUT2)) {
           // second output = the un-scaled activation y / alpha (the saved `d` of the ResnetBlock)
@@ -391,6 +402,9 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (c3_has<F>(p, C3_OUT2))
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmO2), "r"(out2_tile), "r"(0),
                        "r"(tile * kC3OutRows) : "memory");
+        if (c3_has<F>(p, C3_MASK2))   // the tile's 126 mask words are contiguous in global memory: one 1-D bulk copy
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.mask2 + size_t(tile) * kC3OutRows), "r"(mask_s),
+                       "r"(uint32_t(kC3OutRows * 8)) : "memory");
         tc::tma_store_commit();
       }
       prev_ss = ss;
@@ -679,7 +693,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   if (p.R > 256) return MV_OK;
   p.in_stage_bytes = (uint32_t(p.R) * 128u + 1023u) & ~1023u;
   p.w_bytes = uint32_t(p.n_kc) * 3u * kC3WBox;
-  const size_t fixed = 1024 + 2 * 4 * 2 * 64 * 4 + 64 * 4 + (2 * kC3MaxStages + 5 + 2 * kC3MaxSide) * 8 + 16;
+  const size_t fixed = 1024 + 2 * 4 * 2 * 64 * 4 + 64 * 4 + 2048 + (2 * kC3MaxStages + 5 + 2 * kC3MaxSide) * 8 + 16;
   const bool has_side = a->res || a->dact1;
   // staging tiles per epilogue group: with a side input the first output is written in place over the side tile
   const int n_out = a->out2 ? 2 : 1;
@@ -720,7 +734,9 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.alpha = a->alpha;
   p.slope1 = a->slope1;
   p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.n_img = a->n_img;
-  p.flags = (a->bias ? C3_BIAS : 0u) | (a->res ? C3_RES : 0u) | (a->dact1 ? C3_DACT1 : 0u) | (a->out2 ? C3_OUT2 : 0u);
+  p.flags = (a->bias ? C3_BIAS : 0u) | (a->res ? C3_RES : 0u) | (a->dact1 ? C3_DACT1 : 0u) | (a->out2 ? C3_OUT2 : 0u) |
+            (a->out2_mask ? C3_MASK2 : 0u);
+  p.mask2 = static_cast<uint64_t*>(a->out2_mask);
   if (const char* e = getenv("MV_TG_DBG")) p.dbg = atoi(e);
 
   CUtensorMap tmA, tmW;
@@ -762,6 +778,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   switch (p.flags) {
     case C3_BIAS: MV_C3_LAUNCH(C3_BIAS); break;
     case C3_BIAS | C3_RES | C3_OUT2: MV_C3_LAUNCH(C3_BIAS | C3_RES | C3_OUT2); break;
+    case C3_BIAS | C3_RES | C3_MASK2: MV_C3_LAUNCH(C3_BIAS | C3_RES | C3_MASK2); break;
     case C3_DACT1: MV_C3_LAUNCH(C3_DACT1); break;
     case C3_RES: MV_C3_LAUNCH(C3_RES); break;
     default: MV_C3_LAUNCH(C3_GENERIC); break;

@@ -69,6 +69,7 @@ struct TapGemmParams {
   int side_kind;            // 0 res, 1 dact1, 2 dact2
   int n_out;                // staged outputs (1 or 2)
   int side_stages;          // ring depth of the side-input tiles (0: no TMA side input)
+  const unsigned long long* dmask2;   // EF_DMASK2: sign bits of the second output's activation-derivative source, 64 per row
   int dbg;                  // experiment switches (MV_TG_DBG): 1 skip epilogue body, 2 skip MMA issue, 4 skip TMA stores
 };
 
@@ -96,7 +97,7 @@ constexpr int kThreads = 384;
 // Epilogue variants are compile-time flag sets (the runtime-flag version cost ~90 instructions per column).
 enum : uint32_t {
   EF_BIAS = 1, EF_RES = 2, EF_DACT1 = 4, EF_OUT2_PRE = 8, EF_OUT2_POST = 16, EF_DACT2 = 32, EF_SIGMOID = 64,
-  EF_NCHW = 128, EF_GENERIC = 0x80000000u
+  EF_NCHW = 128, EF_DMASK2 = 256, EF_GENERIC = 0x80000000u
 };
 template <uint32_t F>
 __device__ __forceinline__ bool has(const TapGemmParams& p, uint32_t bit) {
@@ -136,7 +137,7 @@ __device__ __forceinline__ uint4 side_vec(const TapGemmParams& p, const uint8_t*
 template <int CW, uint32_t F>
 __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t* v, const uint8_t* side_tile, const float* s_bias,
                                           int cb /*column within the tile*/, int n /*global column*/, const RowCtx& r,
-                                          float neg, uint8_t* st_out, uint8_t* st_out2) {
+                                          float neg, uint8_t* st_out, uint8_t* st_out2, uint32_t mask_word) {
 #pragma unroll
   for (int g = 0; g < CW / 8; ++g) {
     float o[8], o2[8];
@@ -185,6 +186,11 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
 #pragma unroll
           for (int e = 0; e < 8; ++e) o2[e] *= d[e] > 0.f ? 1.f : p.slope2;
         }
+        if (has<F>(p, EF_DMASK2)) {
+          const uint32_t m8 = (mask_word >> (g * 8)) & 0xffu;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o2[e] *= ((m8 >> e) & 1u) ? 1.f : p.slope2;
+        }
       }
     } else {
 #pragma unroll
@@ -227,8 +233,11 @@ __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r
     uint32_t v[32];
     if (CW == 32) tc::tmem_ld_32x32(taddr + cb, v);
     else tc::tmem_ld_32x16(taddr + cb, v);
+    uint32_t mask_word = 0u;
+    if (has<F>(p, EF_DMASK2) && r.valid)   // 32 (16) sign bits of this row's columns [n0 + cb, +CW)
+      mask_word = uint32_t(p.dmask2[r.row] >> ((n0 + cb) & 63));
     tc::tmem_ld_wait();
-    epi_apply<CW, F>(p, v, side_tile, s_bias, cb, n0 + cb, r, neg, st_out, st_out2);
+    epi_apply<CW, F>(p, v, side_tile, s_bias, cb, n0 + cb, r, neg, st_out, st_out2, mask_word);
   }
 }
 
@@ -477,6 +486,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           case EF_DACT1: MV_EPI(EF_DACT1); break;
           case EF_RES: MV_EPI(EF_RES); break;
           case EF_OUT2_POST | EF_DACT2: MV_EPI(EF_OUT2_POST | EF_DACT2); break;
+          case EF_OUT2_POST | EF_DMASK2: MV_EPI(EF_OUT2_POST | EF_DMASK2); break;
           case EF_BIAS | EF_NCHW: MV_EPI(EF_BIAS | EF_NCHW); break;
           default: MV_EPI(EF_GENERIC); break;
         }
@@ -640,7 +650,10 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   p.epi_flags = (a->bias ? EF_BIAS : 0u) | (a->res ? EF_RES : 0u) | (a->dact1 ? EF_DACT1 : 0u) |
                 ((a->out2 && a->out2_pre) ? EF_OUT2_PRE : 0u) | ((a->out2 && !a->out2_pre) ? EF_OUT2_POST : 0u) |
                 ((a->out2 && !a->out2_pre && a->dact2) ? EF_DACT2 : 0u) | (a->act == MV_ACT_SIGMOID ? EF_SIGMOID : 0u) |
-                (a->out_mode == 1 ? EF_NCHW : 0u);
+                (a->out_mode == 1 ? EF_NCHW : 0u) | ((a->out2 && !a->out2_pre && a->dmask2) ? EF_DMASK2 : 0u);
+  p.dmask2 = static_cast<const unsigned long long*>(a->dmask2);
+  MV_CHECK_ARG(!a->dmask2 || (a->N_total == 64 && !a->dact2), "mv_tapgemm: dmask2 needs N_total = 64 and no dact2");
+  MV_CHECK_ARG(!a->out2_mask, "mv_tapgemm: out2_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   CUtensorMap tmA, tmW;
   const CUtensorMapSwizzle sw = CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.R), CK, sw) ||

@@ -23,6 +23,11 @@ class Geom:
         return Geom(self.n_img, self.H * 2, self.W * 2)
 
 
+def mask_rows(P):
+    """Rows (64-bit words) of a sign-mask buffer for a P-row activation: whole 126-row tiles of the conv3 kernel."""
+    return (P + 125) // 126 * 126
+
+
 def to_halo(x, dtype=torch.bfloat16):
     """NCHW -> halo matrix [P, C] (torch ops; used for inputs and by the tests)."""
     n, c, h, w = x.shape
@@ -74,7 +79,7 @@ def pack_conv_weights(specs):
 
 def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act="none", alpha=1.0, res=None, dact1=None,
             slope1=0.2, out=None, out2=None, out2_pre=False, alpha2=1.0, dact2=None, slope2=0.2, geom=None,
-            nchw_out=None, n_valid=0, tag=None):
+            nchw_out=None, n_valid=0, tag=None, out2_mask=None, dmask2=None):
     """out[p, n] = epilogue(sum_t sum_c A[p + tap_off[t], c] * Wt[t*N_total + n, c]); see mv_tapgemm."""
     lib = C.lib()
     Cin = A.shape[1] if Cin is None else Cin
@@ -104,6 +109,12 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
             setattr(a, name, t.data_ptr())
             setattr(a, name + "_ld", t.stride(0))
     a.slope1, a.slope2, a.out2_pre, a.alpha2 = float(slope1), float(slope2), int(out2_pre), float(alpha2)
+    if out2_mask is not None:
+        assert out2 is None and out2_mask.dtype == torch.int64 and out2_mask.is_contiguous() and out2_mask.numel() >= mask_rows(P)
+        a.out2_mask = out2_mask.data_ptr()
+    if dmask2 is not None:
+        assert dact2 is None and dmask2.dtype == torch.int64 and dmask2.is_contiguous() and N_total == 64
+        a.dmask2 = dmask2.data_ptr()
     if geom is not None:
         a.img_stride, a.Wp, a.W, a.H, a.n_img = geom.S, geom.Wp, geom.W, geom.H, geom.n_img
     kw = {} if tag is None else {"tag": tag}

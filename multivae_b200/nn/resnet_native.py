@@ -20,6 +20,7 @@ from . import functional as NF
 from . import halo as HL
 
 _LRELU = 0.2
+_MASK_D = os.environ.get("MULTIVAE_B200_MASK_D", "1") != "0"   # save the last block's `d` as a sign mask
 
 
 def use_native(x):
@@ -110,11 +111,18 @@ def _pack_network(blocks, extra):
     return out, packs[i:]
 
 
-def _block_fwd(x, g, blk, tag):
-    """x_s + 0.1 * lrelu(conv1(lrelu(conv0(x))))  ->  (out, saved h, saved d)."""
+def _block_fwd(x, g, blk, tag, mask_d=False):
+    """x_s + 0.1 * lrelu(conv1(lrelu(conv0(x))))  ->  (out, saved h, saved d).
+    mask_d: `d` (needed only for the sign of the LeakyReLU derivative) is saved as one bit per element (int64 word per row)."""
     taps = g.taps3x3()
     xs = x if blk.wsc is None else HL.tapgemm(x, blk.wsc, 1, [0], blk.cout, g.P, geom=g, tag=f"{tag}.sc")
     h = HL.tapgemm(x, blk.w0, 9, taps, blk.hid, g.P, bias=blk.b0, act="lrelu", geom=g, tag=f"{tag}.c0")
+    if mask_d:
+        assert blk.cout == 64
+        d = torch.empty(HL.mask_rows(g.P), device=x.device, dtype=torch.int64)
+        out = HL.tapgemm(h, blk.w1, 9, taps, blk.cout, g.P, bias=blk.b1, act="lrelu", alpha=0.1, res=xs, out2_mask=d, geom=g,
+                         tag=f"{tag}.c1")
+        return out, h, d
     d = torch.empty(g.P, blk.cout, device=x.device, dtype=torch.bfloat16)
     out = HL.tapgemm(h, blk.w1, 9, taps, blk.cout, g.P, bias=blk.b1, act="lrelu", alpha=0.1, res=xs, out2=d, out2_pre=True,
                      geom=g, tag=f"{tag}.c1")
@@ -192,7 +200,7 @@ class DecoderStackFn(torch.autograd.Function):
         u1, g14 = _upsample_fwd(o1, g7, B1.cout)
         o2, h2, d2 = _block_fwd(u1, g14, B2, "b2")
         u2, g28 = _upsample_fwd(o2, g14, B2.cout)
-        o3, h3, d3 = _block_fwd(u2, g28, B3, "b3")
+        o3, h3, d3 = _block_fwd(u2, g28, B3, "b3", mask_d=_MASK_D)   # d3: sign bits only (1/16 of the bf16 tensor's HBM traffic)
         n_ch = wh.shape[0]
         recon = torch.empty(n_img, n_ch, 28, 28, device=dev, dtype=torch.bfloat16)
         HL.tapgemm(o3, whf, 9, g28.taps3x3(), 16, g28.P, bias=bhp, act="lrelu", geom=g28, nchw_out=recon, n_valid=n_ch, tag="head")
@@ -224,8 +232,9 @@ class DecoderStackFn(torch.autograd.Function):
             arena = HL.ZeroArena(sum(_block_wgrad_floats(b) for b in (B1, B2, B3)) + 9 * 16 * B3.cout + 32, h0.device)
             dWh, dbh = HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head", want_db=True, dW=arena.take(9, 16, B3.cout), db=arena.take(16))
         g_dpre3 = torch.empty(g28.P, B3.cout, device=h0.device, dtype=torch.bfloat16)
-        g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, dact2=d3, slope2=_LRELU, geom=g28,
-                          tag="head.d")
+        dkw = dict(dmask2=d3) if d3.dtype == torch.int64 else dict(dact2=d3)
+        g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, slope2=_LRELU, geom=g28, tag="head.d",
+                          **dkw)
         T = (lambda i, j: None) if tg is None else (lambda i, j: tuple(tg[i:j]) + ((None,) if j - i == 4 else ()))
         g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3", arena=arena, tg=T(10, 14))
         g_o2, g_dpre2 = _upsample_bwd(g_u2, d2, g14, B2.cout, 0.1)

@@ -150,3 +150,34 @@ def test_pack_conv_weights_kernel_matches_torch_packs():
             assert torch.equal(dg, HL.pack_conv_weight_dgrad(wp))
         else:
             assert dg is None
+
+
+@pytest.mark.parametrize("n_img", [37, 301])
+def test_sign_mask_second_output_and_its_consumer(n_img):
+    """out2_mask (conv3 kernel: the saved activation as one sign bit per element) and dmask2 (tap-GEMM epilogue reading it)
+    against the bf16 `out2` / `dact2` path: identical first outputs, mask == (out2 > 0), identical consumer outputs."""
+    from multivae_b200.nn import halo as HL
+    H, c = 28, 64
+    x = _rnd(n_img, c, H, H, seed=41).bfloat16()
+    w = _rnd(c, c, 3, 3, seed=42, scale=c ** -0.5).bfloat16()
+    b = _rnd(c, seed=43)
+    r = _rnd(n_img, c, H, H, seed=44).bfloat16()
+    A, g = HL.to_halo(x)
+    R, _ = HL.to_halo(r)
+    d = torch.empty(g.P, c, device="cuda", dtype=torch.bfloat16)
+    out_ref = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), c, g.P, bias=b, act="lrelu", alpha=0.1, res=R, out2=d, out2_pre=True, geom=g)
+    mask = torch.zeros(HL.mask_rows(g.P), device="cuda", dtype=torch.int64)
+    out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), c, g.P, bias=b, act="lrelu", alpha=0.1, res=R, out2_mask=mask, geom=g)
+    assert torch.equal(out, out_ref)
+    bits = ((mask[: g.P].unsqueeze(1) >> torch.arange(64, device="cuda")) & 1).bool()
+    assert torch.equal(bits, d > 0)
+    # consumer: 16 -> 64 channel data gradient with a second output scaled by lrelu'(d)
+    gy = torch.zeros(n_img, 16, H, H, device="cuda", dtype=torch.bfloat16)
+    gy[:, :3] = _rnd(n_img, 3, H, H, seed=45).bfloat16()
+    G, _ = HL.to_halo(gy)
+    wd = HL.pack_conv_weight_dgrad(torch.cat([_rnd(3, c, 3, 3, seed=46, scale=0.05), torch.zeros(13, c, 3, 3, device="cuda")]).bfloat16())
+    o2a = torch.empty(g.P, c, device="cuda", dtype=torch.bfloat16)
+    o2b = torch.empty(g.P, c, device="cuda", dtype=torch.bfloat16)
+    oa = HL.tapgemm(G, wd, 9, g.taps3x3(), c, g.P, out2=o2a, alpha2=0.1, dact2=d, geom=g)
+    ob = HL.tapgemm(G, wd, 9, g.taps3x3(), c, g.P, out2=o2b, alpha2=0.1, dmask2=mask, geom=g)
+    assert torch.equal(oa, ob) and torch.equal(o2a, o2b)
