@@ -170,6 +170,7 @@ typedef struct mv_tapgemm_args {
    *   dmask2     read INSTEAD of dact2: the second output is alpha2 * o * (bit ? 1 : slope2); N_total = 64 only */
   void* out2_mask;
   const void* dmask2;
+  const void* dmask1;   /* read INSTEAD of dact1 (y *= bit ? 1 : slope1); 3x3 / 64-output layers only */
 } mv_tapgemm_args;
 int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 

@@ -37,7 +37,7 @@ class TapGemmArgs(ctypes.Structure):
         ("dact2", c_void_p), ("dact2_ld", ctypes.c_int32), ("slope2", c_float),
         ("img_stride", ctypes.c_int32), ("Wp", ctypes.c_int32), ("W", ctypes.c_int32), ("H", ctypes.c_int32),
         ("n_img", ctypes.c_int32), ("out_mode", ctypes.c_int32), ("n_valid", ctypes.c_int32),
-        ("out2_mask", c_void_p), ("dmask2", c_void_p),
+        ("out2_mask", c_void_p), ("dmask2", c_void_p), ("dmask1", c_void_p),
     ]
 
 

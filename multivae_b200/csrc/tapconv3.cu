@@ -41,7 +41,7 @@ constexpr int kC3MaxSide = 4;
 constexpr int kC3N = 192;
 constexpr uint32_t kC3WBox = 192u * 128u;   // one filter row of weights: 3 taps x 64 output channels x 64 input channels
 
-enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_GENERIC = 0x80000000u };
+enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_DMASK1 = 32, C3_GENERIC = 0x80000000u };
 
 struct Conv3Params {
   int P, m_tiles, n_kc, row_shift, R;
@@ -49,6 +49,7 @@ struct Conv3Params {
   uint32_t in_stage_bytes, w_bytes;
   const float* bias;
   float neg, alpha, slope1;
+  const uint64_t* dmask1;   // C3_DMASK1: sign bits of the activation-derivative source (instead of a bf16 side tile)
   uint64_t* mask2;          // C3_MASK2: sign bits of the activation, one 64-bit word per row (rows padded to whole tiles)
   int inplace;              // first output written in place over the side tile (released by the group leader after the TMA store)
   int side_stages, n_stg;   // side-tile ring depth; staging tiles per epilogue group (outputs not written in place)
@@ -262,6 +263,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t side_tile = side_s + uint32_t(ss) * 16384u;
       const uint32_t out_tile = (kInPlace && has_side) ? side_tile : stg_s;
       const uint32_t out2_tile = (kInPlace && has_side) ? stg_s : stg_s + 16384u;
+      unsigned long long dm = 0ull;   // this row's 64 sign bits: in flight while the MMAs of the tile still run
+      if (c3_has<F>(p, C3_DMASK1) && inner && row < p.P) dm = p.dmask1[row];
       tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
 #pragma unroll
@@ -356,6 +359,11 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t o[8], o2[8];
 #pragma unroll
         for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);   // none / relu / leaky-relu as one max: slope 1 / 0 / 0.2
+        if (c3_has<F>(p, C3_DMASK1)) {
+          const uint32_t m16 = uint32_t(dm >> c0) & 0xffffu;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] *= ((m16 >> e) & 1u) ? 1.f : p.slope1;
+        }
         if (c3_has<F>(p, C3_DACT1)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -677,6 +685,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   if (a->act == MV_ACT_SIGMOID || !(a->alpha > 0.f)) return MV_OK;   // alpha is folded through the (positively homogeneous) activation
   if (a->out2 && !a->out2_pre) return MV_OK;
   if (a->res && a->dact1) return MV_OK;
+  if (a->dmask1 && a->dact1) return MV_OK;
   if (a->dact2) return MV_OK;
   auto tma_ok = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 8 == 0); };
   if (!tma_ok(a->out, a->out_ld) || (a->out2 && !tma_ok(a->out2, a->out2_ld))) return MV_OK;
@@ -735,7 +744,8 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.slope1 = a->slope1;
   p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.n_img = a->n_img;
   p.flags = (a->bias ? C3_BIAS : 0u) | (a->res ? C3_RES : 0u) | (a->dact1 ? C3_DACT1 : 0u) | (a->out2 ? C3_OUT2 : 0u) |
-            (a->out2_mask ? C3_MASK2 : 0u);
+            (a->out2_mask ? C3_MASK2 : 0u) | (a->dmask1 ? C3_DMASK1 : 0u);
+  p.dmask1 = static_cast<const uint64_t*>(a->dmask1);
   p.mask2 = static_cast<uint64_t*>(a->out2_mask);
   if (const char* e = getenv("MV_TG_DBG")) p.dbg = atoi(e);
 
@@ -780,6 +790,8 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     case C3_BIAS | C3_RES | C3_OUT2: MV_C3_LAUNCH(C3_BIAS | C3_RES | C3_OUT2); break;
     case C3_BIAS | C3_RES | C3_MASK2: MV_C3_LAUNCH(C3_BIAS | C3_RES | C3_MASK2); break;
     case C3_DACT1: MV_C3_LAUNCH(C3_DACT1); break;
+    case C3_DMASK1: MV_C3_LAUNCH(C3_DMASK1); break;
+    case C3_BIAS | C3_MASK2: MV_C3_LAUNCH(C3_BIAS | C3_MASK2); break;
     case C3_RES: MV_C3_LAUNCH(C3_RES); break;
     default: MV_C3_LAUNCH(C3_GENERIC); break;
   }

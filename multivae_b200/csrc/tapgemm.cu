@@ -222,7 +222,8 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
 // The epilogue of one tile for one warp: its TMEM lane quarter (32 rows) and its half of the BN columns, in chunks of CW.
 template <int BN, uint32_t F>
 __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r, const float* s_bias, int n0, int half, uint32_t taddr,
-                                         float neg, uint8_t* st_out, uint8_t* st_out2, const uint8_t* side_tile) {
+                                         float neg, uint8_t* st_out, uint8_t* st_out2, const uint8_t* side_tile,
+                                         unsigned long long mask_row) {
   constexpr int WC = BN >= 32 ? BN / 2 : BN;    // columns per warp (BN = 16: the second warp of a quarter idles)
   constexpr int CW = WC >= 32 ? 32 : 16;
   constexpr int NCH = WC / CW;
@@ -233,9 +234,7 @@ __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r
     uint32_t v[32];
     if (CW == 32) tc::tmem_ld_32x32(taddr + cb, v);
     else tc::tmem_ld_32x16(taddr + cb, v);
-    uint32_t mask_word = 0u;
-    if (has<F>(p, EF_DMASK2) && r.valid)   // 32 (16) sign bits of this row's columns [n0 + cb, +CW)
-      mask_word = uint32_t(p.dmask2[r.row] >> ((n0 + cb) & 63));
+    const uint32_t mask_word = uint32_t(mask_row >> ((n0 + cb) & 63));   // 32 (16) sign bits of this row's columns [n0 + cb, +CW)
     tc::tmem_ld_wait();
     epi_apply<CW, F>(p, v, side_tile, s_bias, cb, n0 + cb, r, neg, st_out, st_out2, mask_word);
   }
@@ -468,6 +467,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
       const uint8_t* side_tile = p.side_stages > 0 ? side_base + size_t(ss) * p.stage_out_bytes : nullptr;
+      // sign-mask word of this row: requested before the wait so that the L2 round trip hides behind the tile's MMAs
+      unsigned long long mask_row = 0ull;
+      if ((p.epi_flags & EF_DMASK2) && r.valid) mask_row = p.dmask2[r.row];
       if (p.dbg & 16) tc::mbar_wait_relaxed(&tm_full[acc], uint32_t(acc_ph)); else tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
       if (side_tile) tc::mbar_wait(&side_full[ss], uint32_t(sph));
@@ -478,7 +480,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else __syncwarp();
       }
       if (!(p.dbg & 1)) {
-#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, neg, st_out, st_out2, side_tile)
+#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, neg, st_out, st_out2, side_tile, mask_row)
         switch (p.epi_flags) {
           case 0u: MV_EPI(0u); break;
           case EF_BIAS: MV_EPI(EF_BIAS); break;
@@ -653,6 +655,7 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
                 (a->out_mode == 1 ? EF_NCHW : 0u) | ((a->out2 && !a->out2_pre && a->dmask2) ? EF_DMASK2 : 0u);
   p.dmask2 = static_cast<const unsigned long long*>(a->dmask2);
   MV_CHECK_ARG(!a->dmask2 || (a->N_total == 64 && !a->dact2), "mv_tapgemm: dmask2 needs N_total = 64 and no dact2");
+  MV_CHECK_ARG(!a->dmask1, "mv_tapgemm: dmask1 is only available for 3x3 convolutions with 64 outputs in the halo layout");
   MV_CHECK_ARG(!a->out2_mask, "mv_tapgemm: out2_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   CUtensorMap tmA, tmW;
   const CUtensorMapSwizzle sw = CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;

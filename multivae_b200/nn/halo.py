@@ -79,7 +79,7 @@ def pack_conv_weights(specs):
 
 def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act="none", alpha=1.0, res=None, dact1=None,
             slope1=0.2, out=None, out2=None, out2_pre=False, alpha2=1.0, dact2=None, slope2=0.2, geom=None,
-            nchw_out=None, n_valid=0, tag=None, out2_mask=None, dmask2=None):
+            nchw_out=None, n_valid=0, tag=None, out2_mask=None, dmask2=None, dmask1=None):
     """out[p, n] = epilogue(sum_t sum_c A[p + tap_off[t], c] * Wt[t*N_total + n, c]); see mv_tapgemm."""
     lib = C.lib()
     Cin = A.shape[1] if Cin is None else Cin
@@ -112,6 +112,9 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
     if out2_mask is not None:
         assert out2 is None and out2_mask.dtype == torch.int64 and out2_mask.is_contiguous() and out2_mask.numel() >= mask_rows(P)
         a.out2_mask = out2_mask.data_ptr()
+    if dmask1 is not None:
+        assert dact1 is None and dmask1.dtype == torch.int64 and dmask1.is_contiguous() and N_total == 64
+        a.dmask1 = dmask1.data_ptr()
     if dmask2 is not None:
         assert dact2 is None and dmask2.dtype == torch.int64 and dmask2.is_contiguous() and N_total == 64
         a.dmask2 = dmask2.data_ptr()

@@ -21,6 +21,7 @@ from . import halo as HL
 
 _LRELU = 0.2
 _MASK_D = os.environ.get("MULTIVAE_B200_MASK_D", "1") != "0"   # save the last block's `d` as a sign mask
+_MASK_H = os.environ.get("MULTIVAE_B200_MASK_H", "1") != "0"   # sign mask of `h` next to h itself (64-channel hidden layers)
 
 
 def use_native(x):
@@ -116,17 +117,21 @@ def _block_fwd(x, g, blk, tag, mask_d=False):
     mask_d: `d` (needed only for the sign of the LeakyReLU derivative) is saved as one bit per element (int64 word per row)."""
     taps = g.taps3x3()
     xs = x if blk.wsc is None else HL.tapgemm(x, blk.wsc, 1, [0], blk.cout, g.P, geom=g, tag=f"{tag}.sc")
-    h = HL.tapgemm(x, blk.w0, 9, taps, blk.hid, g.P, bias=blk.b0, act="lrelu", geom=g, tag=f"{tag}.c0")
+    hm = None
+    if _MASK_H and blk.hid == 64 and blk.cin in (64, 128) and blk.cout in (64, 128):
+        # sign bits of h for the LeakyReLU derivative in the data gradient of conv1 (instead of re-reading h as a side tile)
+        hm = torch.empty(HL.mask_rows(g.P), device=x.device, dtype=torch.int64)
+    h = HL.tapgemm(x, blk.w0, 9, taps, blk.hid, g.P, bias=blk.b0, act="lrelu", geom=g, tag=f"{tag}.c0", out2_mask=hm)
     if mask_d:
         assert blk.cout == 64
         d = torch.empty(HL.mask_rows(g.P), device=x.device, dtype=torch.int64)
         out = HL.tapgemm(h, blk.w1, 9, taps, blk.cout, g.P, bias=blk.b1, act="lrelu", alpha=0.1, res=xs, out2_mask=d, geom=g,
                          tag=f"{tag}.c1")
-        return out, h, d
+        return out, h, d, hm
     d = torch.empty(g.P, blk.cout, device=x.device, dtype=torch.bfloat16)
     out = HL.tapgemm(h, blk.w1, 9, taps, blk.cout, g.P, bias=blk.b1, act="lrelu", alpha=0.1, res=xs, out2=d, out2_pre=True,
                      geom=g, tag=f"{tag}.c1")
-    return out, h, d
+    return out, h, d, hm
 
 
 def _block_wgrad_floats(blk):
@@ -153,7 +158,7 @@ def _direct_targets(params):
     return tg
 
 
-def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=None):
+def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=None, hm=None):
     """g_out: gradient of the block output; g_dpre = 0.1 * g_out * lrelu'(d) (produced upstream).
     Returns (g_x, dW0, db0, dW1, db1, dWsc); with tg = (w0.grad, b0.grad, w1.grad, b1.grad, wsc.grad | None) the weight / bias
     gradients are accumulated into those tensors by the kernels and None is returned in their place."""
@@ -164,7 +169,8 @@ def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=No
         dW1 = db1 = None
     else:
         dW1, db1 = HL.wgrad(h, g_dpre, 9, taps, g.P, tag=f"{tag}.c1", want_db=True, dW=z(9, blk.cout, blk.hid), db=z(blk.cout))
-    g_hpre = HL.tapgemm(g_dpre, blk.w1d, 9, taps, blk.hid, g.P, dact1=h, slope1=_LRELU, geom=g, tag=f"{tag}.c1d")
+    dkw = dict(dact1=h) if hm is None else dict(dmask1=hm)
+    g_hpre = HL.tapgemm(g_dpre, blk.w1d, 9, taps, blk.hid, g.P, slope1=_LRELU, geom=g, tag=f"{tag}.c1d", **dkw)
     if tg is not None:
         HL.wgrad(x, g_hpre, 9, taps, g.P, tag=f"{tag}.c0", want_db=True, grad_out=tg[0], db=tg[1])
         dW0 = db0 = None
@@ -196,15 +202,15 @@ class DecoderStackFn(torch.autograd.Function):
         bhp = torch.zeros(16, device=dev, dtype=torch.float32)
         bhp[: wh.shape[0]] = bh.detach().float()
         g7 = HL.Geom(n_img, 7, 7)
-        o1, h1, d1 = _block_fwd(h0, g7, B1, "b1")
+        o1, h1, d1, _ = _block_fwd(h0, g7, B1, "b1")
         u1, g14 = _upsample_fwd(o1, g7, B1.cout)
-        o2, h2, d2 = _block_fwd(u1, g14, B2, "b2")
+        o2, h2, d2, hm2 = _block_fwd(u1, g14, B2, "b2")
         u2, g28 = _upsample_fwd(o2, g14, B2.cout)
-        o3, h3, d3 = _block_fwd(u2, g28, B3, "b3", mask_d=_MASK_D)   # d3: sign bits only (1/16 of the bf16 tensor's HBM traffic)
+        o3, h3, d3, hm3 = _block_fwd(u2, g28, B3, "b3", mask_d=_MASK_D)   # d3: sign bits only (1/16 of the bf16 tensor's HBM traffic)
         n_ch = wh.shape[0]
         recon = torch.empty(n_img, n_ch, 28, 28, device=dev, dtype=torch.bfloat16)
         HL.tapgemm(o3, whf, 9, g28.taps3x3(), 16, g28.P, bias=bhp, act="lrelu", geom=g28, nchw_out=recon, n_valid=n_ch, tag="head")
-        ctx.save_for_backward(h0, h1, d1, u1, h2, d2, u2, h3, d3, o3, recon)
+        ctx.save_for_backward(h0, h1, d1, u1, h2, d2, u2, h3, d3, o3, recon, hm2, hm3)
         ctx.packs = (B1, B2, B3, whd)
         ctx.params = params
         ctx.n_img, ctx.n_ch = n_img, n_ch
@@ -212,7 +218,7 @@ class DecoderStackFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_recon):
-        h0, h1, d1, u1, h2, d2, u2, h3, d3, o3, recon = ctx.saved_tensors
+        h0, h1, d1, u1, h2, d2, u2, h3, d3, o3, recon, hm2, hm3 = ctx.saved_tensors
         B1, B2, B3, whd = ctx.packs
         n_img, n_ch = ctx.n_img, ctx.n_ch
         lib = C.lib()
@@ -236,9 +242,9 @@ class DecoderStackFn(torch.autograd.Function):
         g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, slope2=_LRELU, geom=g28, tag="head.d",
                           **dkw)
         T = (lambda i, j: None) if tg is None else (lambda i, j: tuple(tg[i:j]) + ((None,) if j - i == 4 else ()))
-        g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3", arena=arena, tg=T(10, 14))
+        g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3", arena=arena, tg=T(10, 14), hm=hm3)
         g_o2, g_dpre2 = _upsample_bwd(g_u2, d2, g14, B2.cout, 0.1)
-        g_u1, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_dpre2, u1, h2, g14, B2, "b2", arena=arena, tg=T(5, 10))
+        g_u1, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_dpre2, u1, h2, g14, B2, "b2", arena=arena, tg=T(5, 10), hm=hm2)
         g_o1, g_dpre1 = _upsample_bwd(g_u1, d1, g7, B1.cout, 0.1)
         need_h0 = ctx.needs_input_grad[0]
         g_h0, dW10, db10, dW11, db11, dWsc1 = _block_bwd(g_o1, g_dpre1, h0, h1, g7, B1, "b1", need_gx=need_h0, arena=arena, tg=T(0, 5))
@@ -334,12 +340,12 @@ class EncoderStackFn(torch.autograd.Function):
         (B1, B2, B3), ((wif, _),) = _pack_network([(w10, b10, w11, b11, None), (w20, b20, w21, b21, wsc2), (w30, b30, w31, b31, wsc3)],
                                                   [(wi, wi.shape[0], 16, False)])   # image conv: 3 -> 16 input channels (zeros)
         a0 = HL.tapgemm(x16, wif, 9, g28.taps3x3(), wi.shape[0], g28.P, bias=bi.detach().float().contiguous(), geom=g28, tag="e.img")
-        o1, h1, d1 = _block_fwd(a0, g28, B1, "e1")
+        o1, h1, d1, hm1 = _block_fwd(a0, g28, B1, "e1")
         x2, g14 = _avgpool_fwd(o1, g28, B1.cout)
-        o2, h2, d2 = _block_fwd(x2, g14, B2, "e2")
+        o2, h2, d2, hm2 = _block_fwd(x2, g14, B2, "e2")
         x3, g7 = _avgpool_fwd(o2, g14, B2.cout)
-        o3, h3, d3 = _block_fwd(x3, g7, B3, "e3")
-        ctx.save_for_backward(x16, a0, h1, d1, x2, h2, d2, x3, h3, d3)
+        o3, h3, d3, _ = _block_fwd(x3, g7, B3, "e3")
+        ctx.save_for_backward(x16, a0, h1, d1, x2, h2, d2, x3, h3, d3, hm1, hm2)
         ctx.packs = (B1, B2, B3)
         ctx.params = params
         ctx.n_img, ctx.cin_img = n_img, wi.shape[1]
@@ -347,7 +353,7 @@ class EncoderStackFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_o3):
-        x16, a0, h1, d1, x2, h2, d2, x3, h3, d3 = ctx.saved_tensors
+        x16, a0, h1, d1, x2, h2, d2, x3, h3, d3, hm1, hm2 = ctx.saved_tensors
         B1, B2, B3 = ctx.packs
         n_img = ctx.n_img
         g28 = HL.Geom(n_img, 28, 28)
@@ -364,9 +370,9 @@ class EncoderStackFn(torch.autograd.Function):
         T = (lambda i, j: None) if tg is None else (lambda i, j: tuple(tg[i:j]) + ((None,) if j - i == 4 else ()))
         g_x3, dW30, db30, dW31, db31, dWsc3 = _block_bwd(g3, g_d3pre, x3, h3, g7, B3, "e3", arena=arena, tg=T(9, 14))
         g_o2, g_d2pre = _avgpool_bwd(g_x3, d2, g14, B2.cout, 0.1)
-        g_x2, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_d2pre, x2, h2, g14, B2, "e2", arena=arena, tg=T(4, 9))
+        g_x2, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_d2pre, x2, h2, g14, B2, "e2", arena=arena, tg=T(4, 9), hm=hm2)
         g_o1, g_d1pre = _avgpool_bwd(g_x2, d1, g28, B1.cout, 0.1)
-        g_a0, dW10, db10, dW11, db11, _ = _block_bwd(g_o1, g_d1pre, a0, h1, g28, B1, "e1", arena=arena, tg=T(0, 4))
+        g_a0, dW10, db10, dW11, db11, _ = _block_bwd(g_o1, g_d1pre, a0, h1, g28, B1, "e1", arena=arena, tg=T(0, 4), hm=hm1)
         # conv_img (3 -> 64): weight gradient with the operand roles swapped (the 16-channel image is the N side),
         # dWs[t, c, n] = sum_p x[p + off_t, c] * g_a0[p, n]
         dWs = HL.wgrad(g_a0, x16, 9, [-o for o in g28.taps3x3()], g28.P, tag="e.img")       # [9, 16, 64]
