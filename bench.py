@@ -404,7 +404,7 @@ def run_reference(args):
                          "sample": f"batch {args.cpu_batch} per step, {args.steps} timed steps, fp32, all host threads"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    EMIT(json.dumps(line))
 
 
 def _claim_stdout():
