@@ -51,7 +51,23 @@ class MMVAEPlus(BaseMultiVAE):
         kind = self.model_config.prior_and_posterior_dist
         if self.noise_source is not None:
             return self.noise_source(shape, kind, device)
+        pool = getattr(self, "_noise_pool", None)
+        if pool is not None:   # slice of the step's single batched draw (see _begin_noise_pool)
+            n = 1
+            for d in shape:
+                n *= d
+            flat, off = pool
+            assert off + n <= flat.numel(), "noise pool exhausted"
+            self._noise_pool = (flat, off + n)
+            return flat[off:off + n].view(*shape)
         return standard_noise(shape, kind, device)
+
+    def _begin_noise_pool(self, n_elements, device):
+        """All standard draws of a forward pass in ONE batched draw (one RNG kernel + one transform chain instead of one per
+        (conditioning, reconstructed) modality pair): the draws are i.i.d., so slicing a single draw is statistically the
+        same as the reference's sequence of rsample calls (mmvaePlus_model.py:136-186).  Not used with an injected noise_source."""
+        if self.noise_source is None:
+            self._noise_pool = (standard_noise((n_elements,), self.model_config.prior_and_posterior_dist, device), 0)
 
     def forward(self, inputs, **kwargs):
         if self.objective not in C.LOSS:
@@ -67,6 +83,8 @@ class MMVAEPlus(BaseMultiVAE):
         # encoders + reparameterised samples, in the reference's noise-consumption order (per cond modality:
         # u, w, then one prior draw per *other* modality: mmvaePlus_model.py:136-186)
         mu_u, sig_u, mu_w, sig_w, u, w, w_cross = [], [], [], [], [], [], {}
+        L_, Lw_ = self.model_config.latent_dim, self.modalities_specific_dim
+        self._begin_noise_pool(len(mods) * K * B * (L_ + Lw_ + (len(mods) - 1) * Lw_), dev)
         for c in mods:
             with self._nn_ctx():
                 o = self.encoders[c](inputs.data[c])
@@ -80,6 +98,7 @@ class MMVAEPlus(BaseMultiVAE):
                 if r != c:
                     sp = log_var_to_std(self.logvars_priors[r], kind)
                     w_cross[(c, r)] = self.mean_priors[r] + sp * self._noise((K, B, sp.shape[-1]), dev)
+        self._noise_pool = None
         U, W = torch.stack(u), torch.stack(w)  # (C,K,B,L), (C,K,B,Lw)
 
         # one batched decoder call per reconstructed modality over all conditioning modalities
