@@ -17,13 +17,34 @@ static HaloGeom make_geom(int n_img, int H, int W) {
   g.n_img = n_img; g.H = H; g.W = W; g.Wp = W + 1; g.S = (H + 1) * (W + 1); g.P = n_img * g.S + g.Wp;
   return g;
 }
+// a / d for 0 <= a < 2^31, d > 0: float reciprocal estimate + exact correction (an integer division costs ~20 instructions,
+// and these kernels do two or three of them per 16-byte vector)
+__device__ __forceinline__ int fdiv(int a, int d) {
+  int q = int(float(a) * (1.f / float(d)));
+  int r = a - q * d;
+  q += (r >= d) - (r < 0);
+  r = a - q * d;
+  q += (r >= d) - (r < 0);
+  return q;
+}
 // row -> (img, y in 1..H, x in 0..W-1) or invalid
 __device__ __forceinline__ bool decode_row(const HaloGeom& g, int row, int& img, int& y, int& x) {
-  img = row / g.S;
+  img = fdiv(row, g.S);
   const int r = row - img * g.S;
-  y = r / g.Wp;
+  y = fdiv(r, g.Wp);
   x = r - y * g.Wp;
   return row < g.P && img < g.n_img && y >= 1 && x < g.W;
+}
+// flat vector index -> (row, vector within the row); vec_per_row is a power of two for every layer of the networks
+__device__ __forceinline__ void split_index(int64_t i, int vec_per_row, int& row, int& v) {
+  if ((vec_per_row & (vec_per_row - 1)) == 0) {
+    const int sh = 31 - __clz(vec_per_row);
+    row = int(i >> sh);
+    v = int(i) & (vec_per_row - 1);
+  } else {
+    row = int(i / vec_per_row);
+    v = int(i - int64_t(row) * vec_per_row);
+  }
 }
 
 __device__ __forceinline__ void unpack8f(const uint4& v, float* f) {
@@ -40,7 +61,8 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const bf16* __restr
   const int vec_per_row = C >> 3;
   const int64_t total = int64_t(go.P) * vec_per_row;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int row, v;
+    split_index(i, vec_per_row, row, v);
     int img, y, x;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (decode_row(go, row, img, y, x)) {
@@ -58,7 +80,8 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const bf16* __restr
   const int vec_per_row = C >> 3;
   const int64_t total = int64_t(gi.P) * vec_per_row;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int row, v;
+    split_index(i, vec_per_row, row, v);
     int img, y, x;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (decode_row(gi, row, img, y, x)) {
@@ -112,7 +135,8 @@ __global__ void __launch_bounds__(256) avgpool3s2_fwd_kernel(const bf16* __restr
   const int vec_per_row = C >> 3;
   const int64_t total = int64_t(go.P) * vec_per_row;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int row, v;
+    split_index(i, vec_per_row, row, v);
     int img, y, x;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (decode_row(go, row, img, y, x)) {
@@ -145,7 +169,8 @@ __global__ void __launch_bounds__(256) avgpool3s2_bwd_kernel(const bf16* __restr
   const int vec_per_row = C >> 3;
   const int64_t total = int64_t(gi.P) * vec_per_row;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int row = int(i / vec_per_row), v = int(i - int64_t(row) * vec_per_row);
+    int row, v;
+    split_index(i, vec_per_row, row, v);
     int img, y, x;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (decode_row(gi, row, img, y, x)) {
