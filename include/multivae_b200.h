@@ -226,6 +226,17 @@ typedef struct mv_pack_item {
 } mv_pack_item;
 int mv_pack_conv_weights(const mv_pack_item* items, int n_items, void* stream);
 
+/* The reverse hand-over for the gradients of a whole network in one launch: dst[n, c, t] += src[t, n, c] for every item, where
+ * src is the fp32 [T, Npad, Cpad] buffer mv_wgrad accumulated into (swapped != 0: [T, Cpad, Npad], the role-swapped image
+ * convolution) and dst the parameter's own gradient in the torch Conv2d layout [N, C, T] (`weight.grad`; a bias gradient is an
+ * item with C = T = 1).  Replaces one permuted `grad += dW` kernel per parameter (autograd's AccumulateGrad). */
+typedef struct mv_unpack_item {
+  const void* src;      /* fp32 [T, Npad, Cpad] (or [T, Cpad, Npad]) */
+  void* dst;            /* fp32 [N, C, T], accumulated into */
+  int32_t N, C, T, Npad, Cpad, swapped;
+} mv_unpack_item;
+int mv_unpack_wgrad_add(const mv_unpack_item* items, int n_items, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,12 @@ class PackItem(ctypes.Structure):
                 ("T", ctypes.c_int32), ("Npad", ctypes.c_int32), ("Cpad", ctypes.c_int32)]
 
 
+class UnpackItem(ctypes.Structure):
+    """mv_unpack_item of include/multivae_b200.h."""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("T", ctypes.c_int32),
+                ("Npad", ctypes.c_int32), ("Cpad", ctypes.c_int32), ("swapped", ctypes.c_int32)]
+
+
 # symbol -> argtypes, exactly the prototypes in include/multivae_b200.h
 _PROTOS = {
     "mv_version": [ctypes.POINTER(c_int)] * 3,
@@ -71,6 +77,7 @@ _PROTOS = {
     "mv_avgpool3s2_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
     "mv_scale_dact": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p],
     "mv_pack_conv_weights": [ctypes.POINTER(PackItem), c_int, c_void_p],
+    "mv_unpack_wgrad_add": [ctypes.POINTER(UnpackItem), c_int, c_void_p],
     "mv_wgrad_slice": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                        c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "mv_wgrad": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),

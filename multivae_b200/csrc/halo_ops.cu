@@ -376,3 +376,49 @@ extern "C" int mv_pack_conv_weights(const mv_pack_item* items, int n_items, void
   MV_CHECK_LAUNCH("mv_pack_conv_weights");
   return MV_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gradient hand-over of a whole network in ONE launch: the weight-gradient kernels produce dW as [T][Npad][C] (or, for the
+// role-swapped image convolution, [T][Cpad][N]) fp32 buffers; this adds them into the parameters' own .grad tensors in the
+// torch Conv2d layout [N][C][T] (bias gradients are items with C = T = 1).  Replaces one permuted `grad += dW` ATen kernel
+// per parameter of the autograd path.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace mv {
+struct UnpackBatch {
+  mv_unpack_item it[MV_PACK_MAX_ITEMS];
+};
+__global__ void __launch_bounds__(256) unpack_wgrad_add_kernel(const __grid_constant__ UnpackBatch b) {
+  const mv_unpack_item& w = b.it[blockIdx.y];
+  const float* __restrict__ src = static_cast<const float*>(w.src);
+  float* __restrict__ dst = static_cast<float*>(w.dst);
+  const int64_t total = int64_t(w.N) * w.C * w.T;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    // e walks the destination [N][C][T] (coalesced read-modify-write of the gradient)
+    const int t = int(e % w.T);
+    const int64_t nc = e / w.T;
+    const int c = int(nc % w.C), n = int(nc / w.C);
+    const int64_t s = w.swapped ? (int64_t(t) * w.Cpad + c) * w.Npad + n     // [T][Cpad][Npad]
+                                : (int64_t(t) * w.Npad + n) * w.Cpad + c;    // [T][Npad][Cpad]
+    dst[e] += src[s];
+  }
+}
+}  // namespace mv
+
+extern "C" int mv_unpack_wgrad_add(const mv_unpack_item* items, int n_items, void* stream) {
+  MV_CHECK_ARG(items && n_items >= 1 && n_items <= MV_PACK_MAX_ITEMS, "mv_unpack_wgrad_add: 1 <= n_items <= %d", MV_PACK_MAX_ITEMS);
+  mv::UnpackBatch b{};
+  int64_t biggest = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const mv_unpack_item& w = items[i];
+    MV_CHECK_ARG(w.src && w.dst, "mv_unpack_wgrad_add: null pointer in item %d", i);
+    MV_CHECK_ARG(w.N >= 1 && w.C >= 1 && w.T >= 1 && w.Npad >= w.N && w.Cpad >= w.C, "mv_unpack_wgrad_add: bad sizes in item %d", i);
+    b.it[i] = w;
+    const int64_t total = int64_t(w.N) * w.C * w.T;
+    biggest = total > biggest ? total : biggest;
+  }
+  int gx = int((biggest + 256 * 4 - 1) / (256 * 4));
+  gx = gx < 1 ? 1 : (gx > 1184 ? 1184 : gx);
+  mv::unpack_wgrad_add_kernel<<<dim3(gx, n_items), 256, 0, static_cast<cudaStream_t>(stream)>>>(b);
+  MV_CHECK_LAUNCH("mv_unpack_wgrad_add");
+  return MV_OK;
+}

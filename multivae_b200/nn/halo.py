@@ -165,6 +165,26 @@ def wgrad(X, G, T, tap_off, P, dW=None, Cin=None, N=None, tag=None, want_db=Fals
     return (dW, db) if want_db else dW
 
 
+def unpack_wgrad_add(items):
+    """grad[n, c, t] += dW[t, n, c] for every (dW, grad[, swapped]) pair in ONE kernel (mv_unpack_wgrad_add).
+    dW: fp32 [T, Npad, Cpad] as produced by `wgrad` (bias gradients: [Npad]); grad: the parameter's contiguous fp32 .grad."""
+    arr = (C.UnpackItem * len(items))()
+    for it, item in zip(arr, items):
+        dW, grad = item[0], item[1]
+        swapped = len(item) > 2 and item[2]
+        assert dW.dtype == torch.float32 and dW.is_contiguous() and grad.dtype == torch.float32 and grad.is_contiguous()
+        if dW.dim() == 1:       # bias
+            it.N, it.C, it.T, it.Npad, it.Cpad = grad.numel(), 1, 1, dW.shape[0], 1
+        else:
+            t = dW.shape[0]
+            n, c = grad.shape[0], grad.shape[1]
+            it.N, it.C, it.T = n, c, t
+            it.Npad, it.Cpad = (dW.shape[2], dW.shape[1]) if swapped else (dW.shape[1], dW.shape[2])
+            assert grad.numel() == n * c * t
+        it.src, it.dst, it.swapped = dW.data_ptr(), grad.data_ptr(), 1 if swapped else 0
+    C.check(C.lib().mv_unpack_wgrad_add(arr, len(items), C.stream()), "mv_unpack_wgrad_add")
+
+
 class ZeroArena:
     """One zero-filled fp32 buffer handed out in slices: the accumulating outputs (dW, db) of all weight-gradient launches
     of a backward pass share ONE fill kernel instead of one each."""

@@ -142,12 +142,18 @@ def _block_wgrad_floats(blk):
     return n
 
 
+def _grad_mode():
+    """How parameter gradients leave the native backward passes (MULTIVAE_B200_DIRECT_GRADS):
+    "1" (default)  one mv_unpack_wgrad_add launch per stack adds the [T][N][C] buffers into the parameters' .grad tensors
+                   (when those exist as contiguous fp32 tensors — the trainer's flat buffer), None goes back to autograd;
+    "nct"          the weight-gradient kernels accumulate straight into .grad with strided atomics (mv_wgrad_nct);
+    "0"            gradients are returned to autograd (one permuted `grad += dW` kernel per parameter)."""
+    return {"0": "autograd", "nct": "nct"}.get(os.environ.get("MULTIVAE_B200_DIRECT_GRADS", "1"), "unpack")
+
+
 def _direct_targets(params):
-    """The parameters' own .grad tensors if the weight-gradient kernels may accumulate into ALL of them in place (fp32,
-    contiguous, allocated — the trainer's flat gradient buffer), else None: then gradients are returned to autograd."""
-    # Opt-in: measured on the north star the strided atomics of the [N][C][T] layout cost more (small layers: 3x the epilogue
-    # time) than the ~450 `grad += dW` kernels they save (79.3 -> 82.1 ms per step), so the default returns gradients to autograd.
-    if os.environ.get("MULTIVAE_B200_DIRECT_GRADS", "0") != "1" or torch.is_grad_enabled():
+    """The parameters' own .grad tensors if ALL of them can be written in place (fp32, contiguous, allocated), else None."""
+    if _grad_mode() == "autograd" or torch.is_grad_enabled():
         return None
     tg = []
     for p in params:
@@ -229,7 +235,8 @@ class DecoderStackFn(torch.autograd.Function):
         gh = torch.empty(g28.P, 16, device=h0.device, dtype=torch.bfloat16)
         C.check(lib.mv_head_grad_pack(g_recon.data_ptr(), recon.data_ptr(), gh.data_ptr(), n_img, 28, 28, n_ch, _LRELU, C.stream()),
                 "mv_head_grad_pack")
-        tg = _direct_targets(ctx.params)   # (w10, b10, w11, b11, wsc1, w20, b20, w21, b21, wsc2, w30, b30, w31, b31, wh, bh).grad
+        tgt = _direct_targets(ctx.params)  # (w10, b10, w11, b11, wsc1, w20, b20, w21, b21, wsc2, w30, b30, w31, b31, wh, bh).grad
+        tg = tgt if _grad_mode() == "nct" else None
         arena = None
         if tg is not None:
             HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head", want_db=True, grad_out=tg[14], n_valid=n_ch, db=tg[15])
@@ -251,6 +258,10 @@ class DecoderStackFn(torch.autograd.Function):
         if g_h0 is not None:
             g_h0 = g_h0[: h0.shape[0]]
         if tg is not None:   # every parameter gradient was accumulated in place by the kernels
+            return (g_h0, None) + (None,) * 16
+        if tgt is not None:  # one launch adds all sixteen buffers into the .grad tensors
+            HL.unpack_wgrad_add(list(zip((dW10, db10, dW11, db11, dWsc1, dW20, db20, dW21, db21, dWsc2, dW30, db30, dW31, db31, dWh, dbh),
+                                         tgt)))
             return (g_h0, None) + (None,) * 16
         u = HL.unpack_conv_wgrad
         grads = (u(dW10, 3, 3), db10, u(dW11, 3, 3), db11, u(dWsc1, 1, 1), u(dW20, 3, 3), db20, u(dW21, 3, 3), db21,
@@ -365,7 +376,8 @@ class EncoderStackFn(torch.autograd.Function):
         C.check(lib.mv_scale_dact(g3.data_ptr(), d3.data_ptr(), g_d3pre.data_ptr(), g7.P, B3.cout, 0.1, _LRELU, C.stream()),
                 "mv_scale_dact")
         # block parameters (w10, b10, w11, b11 | w20, b20, w21, b21, wsc2 | w30, b30, w31, b31, wsc3) = ctx.params[2:]
-        tg = _direct_targets(ctx.params[2:])
+        tgt = _direct_targets(ctx.params)
+        tg = tgt[2:] if (tgt is not None and _grad_mode() == "nct") else None
         arena = None if tg is not None else HL.ZeroArena(sum(_block_wgrad_floats(b) for b in (B1, B2, B3)), x16.device)
         T = (lambda i, j: None) if tg is None else (lambda i, j: tuple(tg[i:j]) + ((None,) if j - i == 4 else ()))
         g_x3, dW30, db30, dW31, db31, dWsc3 = _block_bwd(g3, g_d3pre, x3, h3, g7, B3, "e3", arena=arena, tg=T(9, 14))
@@ -380,6 +392,10 @@ class EncoderStackFn(torch.autograd.Function):
         dbi = _colsum(g_a0, g28.P, dWs.shape[2])
         if tg is not None:   # the block gradients were accumulated in place by the kernels
             return (None, dWi, dbi) + (None,) * 14
+        if tgt is not None:  # one launch adds all sixteen buffers into the .grad tensors (the image conv's is role-swapped)
+            blocks = (dW10, db10, dW11, db11, dW20, db20, dW21, db21, dWsc2, dW30, db30, dW31, db31, dWsc3)
+            HL.unpack_wgrad_add([(dWs, tgt[0], True), (dbi, tgt[1])] + list(zip(blocks, tgt[2:])))
+            return (None,) * 17
         u = HL.unpack_conv_wgrad
         return (None, dWi, dbi, u(dW10, 3, 3), db10, u(dW11, 3, 3), db11, u(dW20, 3, 3), db20, u(dW21, 3, 3), db21,
                 u(dWsc2, 1, 1), u(dW30, 3, 3), db30, u(dW31, 3, 3), db31, u(dWsc3, 1, 1))

@@ -59,9 +59,11 @@ def test_decoder_forward_backward_matches_torch_fp32(n_img):
         assert e < max(3e-2, 2.5 * lib_err[k]), (k, e, lib_err[k])
 
 
-def test_decoder_direct_gradient_accumulation_equals_autograd_path():
-    """With pre-allocated fp32 .grad tensors (the trainer's flat buffer) the weight-gradient kernels accumulate in place
-    (mv_wgrad_nct) and the autograd Function returns None: same gradients as the path that returns them to autograd."""
+@pytest.mark.parametrize("mode", ["1", "nct"])
+def test_decoder_direct_gradient_accumulation_equals_autograd_path(mode):
+    """With pre-allocated fp32 .grad tensors (the trainer's flat buffer) the gradients are added in place — by one
+    mv_unpack_wgrad_add launch ("1", the default) or by the weight-gradient kernels themselves ("nct") — and the autograd
+    Function returns None: same gradients as the path that returns them to autograd ("0")."""
     import os
     from multivae_b200.nn import DecoderResnetMMNIST
     from multivae_b200.nn import functional as NF
@@ -74,7 +76,7 @@ def test_decoder_direct_gradient_accumulation_equals_autograd_path():
         os.environ["MULTIVAE_B200_DIRECT_GRADS"] = "0"
         dec(z).reconstruction.backward(gy)
         ref = {k: p.grad.clone() for k, p in dec.named_parameters()}
-        os.environ["MULTIVAE_B200_DIRECT_GRADS"] = "1"
+        os.environ["MULTIVAE_B200_DIRECT_GRADS"] = mode
         for p in dec.parameters():
             p.grad = torch.full_like(p, 0.5)       # accumulation on top of an existing gradient
         dec(z).reconstruction.backward(gy)

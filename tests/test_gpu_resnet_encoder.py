@@ -47,3 +47,39 @@ def test_encoder_matches_torch_fp32(n_img):
         e, l = _rel(g_nat[k], g_ref[k]), _rel(g_lib[k], g_ref[k])
         print(f"{k:40s} native {e:.4f}   torch-bf16 {l:.4f}")
         assert e < max(3e-2, 2.5 * l), (k, e, l)
+
+
+@pytest.mark.parametrize("mode", ["1", "nct"])
+def test_encoder_in_place_gradient_handover_equals_autograd_path(mode):
+    """Pre-allocated .grad tensors: the batched mv_unpack_wgrad_add hand-over ("1") / in-kernel accumulation ("nct") give the
+    same gradients as returning them to autograd ("0"), on top of an existing gradient value."""
+    import os
+    from multivae_b200.nn import EncoderResnetMMNIST
+    from multivae_b200.nn import functional as NF
+    torch.manual_seed(2)
+    enc = EncoderResnetMMNIST(32, 32).cuda()
+    x = torch.rand(37, 3, 28, 28, device="cuda")
+    gy = [torch.randn(37, 32, device="cuda") for _ in range(4)]
+
+    def run():
+        o = enc(x)
+        outs = [o.embedding, o.log_covariance, o.style_embedding, o.style_log_covariance]
+        sum((t.float() * g).sum() for t, g in zip(outs, gy)).backward()
+
+    NF.set_backend("native")
+    try:
+        os.environ["MULTIVAE_B200_DIRECT_GRADS"] = "0"
+        for p in enc.parameters():
+            p.grad = None
+        run()
+        ref = {k: p.grad.clone() for k, p in enc.named_parameters()}
+        os.environ["MULTIVAE_B200_DIRECT_GRADS"] = mode
+        for p in enc.parameters():
+            p.grad = torch.full_like(p, 0.25)
+        run()
+    finally:
+        os.environ.pop("MULTIVAE_B200_DIRECT_GRADS", None)
+        NF.set_backend("auto")
+    for k, p in enc.named_parameters():
+        err = float((p.grad - 0.25 - ref[k]).abs().max()) / (float(ref[k].abs().max()) + 1e-12)
+        assert err < 2e-3, (k, err)
