@@ -347,8 +347,12 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
     float* __restrict__ g_sig_u, float* __restrict__ g_mu_w, float* __restrict__ g_sig_w, float* __restrict__ g_pz_std,
     int C, int K, int B, int L, int Lw, int loss_kind, float beta, int detach_post) {
   const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= B) return;
+  // one warp per (conditioning modality c, sample b): C times the parallelism of a warp per sample.  What the C warps of a
+  // sample share (its loss, the prior-scale gradient, the posterior-parameter gradients of all modalities through the MoE
+  // term) is accumulated with atomics into buffers the host zero-fills before the launch.
+  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wi >= C * B) return;
+  const int c = wi / B, b = wi - c * B;
   int nm = 0;
   bool avail[kMaxC];
 #pragma unroll
@@ -359,20 +363,8 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
   const float log_nm = __logf(float(nm > 0 ? nm : 1));
   const float inv_nm = nm > 0 ? 1.f / float(nm) : 0.f;
   const int LT = L + Lw;
-  // zero the per-sample accumulators this warp owns
-  for (int i = lane; i < LT; i += 32) g_pz_std[int64_t(b) * LT + i] = 0.f;
-  for (int m = 0; m < C; ++m) {
-    for (int l = lane; l < L; l += 32) {
-      g_mu_u[(int64_t(m) * B + b) * L + l] = 0.f;
-      g_sig_u[(int64_t(m) * B + b) * L + l] = 0.f;
-    }
-    for (int l = lane; l < Lw; l += 32) {
-      g_mu_w[(int64_t(m) * B + b) * Lw + l] = 0.f;
-      g_sig_w[(int64_t(m) * B + b) * Lw + l] = 0.f;
-    }
-  }
   float loss_acc = 0.f;
-  for (int c = 0; c < C; ++c) {
+  {
     // ---- pass 1: lw[c,k,b] for all k -----------------------------------------------------------
     float mx = -INFINITY;
     for (int k = 0; k < K; ++k) {
@@ -472,7 +464,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
         const float uu = u[row * L + l];
         const float pm = pz_mean[l], ps = pz_std[l];
         float gu = lat_dx<KIND>(uu, pm, ps);
-        g_pz_std[int64_t(b) * LT + l] += cb * lat_ds<KIND>(uu, pm, ps);
+        atomicAdd(g_pz_std + int64_t(b) * LT + l, cb * lat_ds<KIND>(uu, pm, ps));
 #pragma unroll
         for (int m = 0; m < kMaxC; ++m)
           if (m < C && avail[m]) {
@@ -482,8 +474,8 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
             const float dx = lat_dx<KIND>(uu, mm, ss);
             gu -= r * dx;
             if (!detach_post) {
-              g_mu_u[pi] += cb * r * dx;  // -(cb) * r * dlq/dmu, dlq/dmu = -dx
-              g_sig_u[pi] -= cb * r * lat_ds<KIND>(uu, mm, ss);
+              atomicAdd(g_mu_u + pi, cb * r * dx);  // -(cb) * r * dlq/dmu, dlq/dmu = -dx
+              atomicAdd(g_sig_u + pi, -cb * r * lat_ds<KIND>(uu, mm, ss));
             }
           }
         g_u[row * L + l] = cb * gu;
@@ -495,7 +487,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
         const float mm = mu_w[pi], ss = sig_w[pi];
         const float dx = lat_dx<KIND>(ww, mm, ss);
         g_w[row * Lw + l] = cb * (lat_dx<KIND>(ww, pm, ps) - dx);
-        g_pz_std[int64_t(b) * LT + L + l] += cb * lat_ds<KIND>(ww, pm, ps);
+        atomicAdd(g_pz_std + int64_t(b) * LT + L + l, cb * lat_ds<KIND>(ww, pm, ps));
         if (!detach_post) {
           g_mu_w[pi] += cb * dx;
           g_sig_w[pi] -= cb * lat_ds<KIND>(ww, mm, ss);
@@ -503,7 +495,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
       }
     }
   }
-  if (lane == 0) loss_b[b] = -loss_acc * inv_nm;
+  if (lane == 0 && avail[c]) atomicAdd(loss_b + b, -loss_acc * inv_nm);
 }
 
 }  // namespace mv
@@ -743,7 +735,16 @@ extern "C" int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, 
   MV_CHECK_ARG(K > 0 && B > 0 && L > 0 && Lw >= 0, "mv_moe_lw_fwd: bad sizes");
   MV_CHECK_ARG(loss_kind == MV_LOSS_IWAE || loss_kind == MV_LOSS_DREG, "mv_moe_lw_fwd: unknown loss %d", loss_kind);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = (B + 3) / 4;
+  // accumulators shared by the C warps of a sample (atomics in the kernel): zero-filled here
+  cudaMemsetAsync(loss_b, 0, sizeof(float) * size_t(B), st);
+  cudaMemsetAsync(g_pz_std, 0, sizeof(float) * size_t(B) * (L + Lw), st);
+  cudaMemsetAsync(g_mu_u, 0, sizeof(float) * size_t(C) * B * L, st);
+  cudaMemsetAsync(g_sig_u, 0, sizeof(float) * size_t(C) * B * L, st);
+  if (Lw > 0) {
+    cudaMemsetAsync(g_mu_w, 0, sizeof(float) * size_t(C) * B * Lw, st);
+    cudaMemsetAsync(g_sig_w, 0, sizeof(float) * size_t(C) * B * Lw, st);
+  }
+  const int blocks = (C * B + 3) / 4;   // one warp per (conditioning modality, sample)
   if (latent_kind == MV_LATENT_LAPLACE)
     moe_lw_kernel<MV_LATENT_LAPLACE><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post);
   else if (latent_kind == MV_LATENT_NORMAL)
