@@ -13,12 +13,17 @@
 // expansion never exists anywhere and L2/HBM read amplification is (128 + 2 halo) / 128 instead of 9.
 // T = 1 with off = 0 is a plain GEMM (1x1 convolutions, Linear layers).
 //
-// Warp roles (192 threads, persistent over output tiles of 128 rows x BN columns):
-//   warp 0   TMA producer: input windows (ring of in_stages) and weight tiles (ring, or resident for the
-//            whole kernel when all T * Cin/CK tiles fit)
-//   warp 1   allocates TMEM, one lane issues tcgen05.mma and commits to the mbarriers
-//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's MMAs
-//            overlap), bias / activation / activation-derivative / residual / halo mask, bf16 store
+// Warp roles (384 threads, persistent over output tiles of 128 rows x BN columns):
+//   warp 0    TMA producer: input windows (ring of in_stages) and weight tiles (ring, or resident for the
+//             whole kernel when all T * Cin/CK tiles fit)
+//   warp 1    one lane issues tcgen05.mma and commits to the mbarriers
+//   warp 2    TMA producer of the side-input tiles (residual / activation-derivative source), own ring
+//   warp 3    owns the TMEM allocation
+//   warps 4-11 epilogue (two per TMEM lane quarter, half of the columns each): tcgen05.ld the fp32 accumulator
+//             (double-buffered in TMEM so the next tile's MMAs overlap), bias / activation / activation-derivative /
+//             residual / halo mask, bf16 pack into a swizzled staging tile, 32-row TMA stores
+// 3x3 convolutions with 64 (or <= 16, NCHW) output channels are routed to the three-taps-per-MMA kernels of tapconv3.cu.
+// MV_TG_DBG / MV_TG_IN_STAGES / MV_TG_SIDE_STAGES are experiment switches (tools/exp_tapgemm*.py), not product options.
 #include <cstdlib>
 
 #include "common.cuh"
