@@ -38,7 +38,7 @@ __device__ long long g_tg_clk[4];   // experiment: SM cycles the MMA warp of CTA
 constexpr int kMaxTaps = 9;
 constexpr int kMaxInStages = 3;
 constexpr int kMaxWStages = 20;
-constexpr int kMaxSideStages = 3;
+constexpr int kMaxSideStages = 4;
 constexpr int kBM = 128;
 
 struct TapGemmParams {
@@ -75,6 +75,8 @@ struct TapGemmParams {
   int n_out;                // staged outputs (1 or 2)
   int side_stages;          // ring depth of the side-input tiles (0: no TMA side input)
   const unsigned long long* dmask2;   // EF_DMASK2: sign bits of the second output's activation-derivative source, 64 per row
+  int seq_boxes;            // BN = 128 with staged side inputs / two outputs: the epilogue handles the tile's two 64-column boxes one
+                            // after the other through 16 KB buffers, which leaves shared memory for a deep weight ring
   int dbg;                  // experiment switches (MV_TG_DBG): 1 skip epilogue body, 2 skip MMA issue, 4 skip TMA stores
 };
 
@@ -334,15 +336,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int ss = 0, sph = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
-        if (p.dbg & 16) tc::mbar_wait_relaxed(&side_empty[ss], sph ^ 1); else tc::mbar_wait(&side_empty[ss], sph ^ 1);
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(&side_full[ss], p.stage_out_bytes);
-#pragma unroll
-          for (int b = 0; b < (BN >= 64 ? BN / 64 : 1); ++b)
-            tc::tma_load_2d(side_base + size_t(ss) * p.stage_out_bytes + b * 16384, &tmS, &side_full[ss], n0 + b * 64, p0);
+        const int nsub = (BN == 128 && p.seq_boxes) ? 2 : 1, nbox = int(p.stage_out_bytes >> 14);
+        for (int sub = 0; sub < nsub; ++sub) {
+          tc::mbar_wait(&side_empty[ss], sph ^ 1);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&side_full[ss], p.stage_out_bytes);
+            for (int b = 0; b < nbox; ++b)
+              tc::tma_load_2d(side_base + size_t(ss) * p.stage_out_bytes + b * 16384, &tmS, &side_full[ss], n0 + (sub + b) * 64, p0);
+          }
+          __syncwarp();
+          if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
         }
-        __syncwarp();
-        if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -440,8 +444,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The CTA uses (almost) all shared memory, so there is no L1: side inputs arrive as TMA tiles.
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    const bool pair_store = BN == 64;                         // the two warps of a quarter share one 64-column box
-    const bool store_leader = lane == 0 && (BN == 128 || half == 0);
+    const bool seq = BN == 128 && p.seq_boxes != 0;           // the tile's two 64-column boxes one after the other (16 KB buffers)
+    const bool pair_store = BN == 64 || seq;                  // the two warps of a quarter share one 64-column box
+    const bool store_leader = lane == 0 && ((BN == 128 && !seq) || half == 0);
     float* s_bias = s_bias_all + (warp - 4) * (BN < 32 ? 32 : BN);
     const float neg = p.act == MV_ACT_LRELU02 ? 0.2f : (p.act == MV_ACT_RELU ? 0.f : 1.f);
     const float inv_S = p.img_stride > 0 ? 1.f / float(p.img_stride) : 0.f;
@@ -449,7 +454,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool two = (p.epi_flags & (EF_OUT2_PRE | EF_OUT2_POST)) != 0;
     uint8_t* st_out = p.use_tma_store ? stg_base : nullptr;
     uint8_t* st_out2 = p.use_tma_store ? stg_base + p.stage_out_bytes : nullptr;
+    const int nsub = seq ? 2 : 1;
     int it = 0, ss = 0, sph = 0;
+    bool stored = false;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
@@ -471,51 +478,69 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
-      const uint8_t* side_tile = p.side_stages > 0 ? side_base + size_t(ss) * p.stage_out_bytes : nullptr;
       // sign-mask word of this row: requested before the wait so that the L2 round trip hides behind the tile's MMAs
       unsigned long long mask_row = 0ull;
       if ((p.epi_flags & EF_DMASK2) && r.valid) mask_row = p.dmask2[r.row];
       if (p.dbg & 16) tc::mbar_wait_relaxed(&tm_full[acc], uint32_t(acc_ph)); else tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
-      if (side_tile) tc::mbar_wait(&side_full[ss], uint32_t(sph));
-      if (p.use_tma_store && it > 0) {
-        // the previous TMA stores of this slab must have finished READING it before it is rewritten
-        if (store_leader) tc::tma_store_wait_read<0>();
-        if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        else __syncwarp();
-      }
-      if (!(p.dbg & 1)) {
-#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, neg, st_out, st_out2, side_tile, mask_row)
-        switch (p.epi_flags) {
-          case 0u: MV_EPI(0u); break;
-          case EF_BIAS: MV_EPI(EF_BIAS); break;
-          case EF_BIAS | EF_RES | EF_OUT2_PRE: MV_EPI(EF_BIAS | EF_RES | EF_OUT2_PRE); break;
-          case EF_DACT1: MV_EPI(EF_DACT1); break;
-          case EF_RES: MV_EPI(EF_RES); break;
-          case EF_OUT2_POST | EF_DACT2: MV_EPI(EF_OUT2_POST | EF_DACT2); break;
-          case EF_OUT2_POST | EF_DMASK2: MV_EPI(EF_OUT2_POST | EF_DMASK2); break;
-          case EF_BIAS | EF_NCHW: MV_EPI(EF_BIAS | EF_NCHW); break;
-          default: MV_EPI(EF_GENERIC); break;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const uint8_t* side_tile = p.side_stages > 0 ? side_base + size_t(ss) * p.stage_out_bytes : nullptr;
+        if (side_tile) tc::mbar_wait(&side_full[ss], uint32_t(sph));
+        if (p.use_tma_store && stored) {
+          // the previous TMA stores of this slab must have finished READING it before it is rewritten
+          if (store_leader) tc::tma_store_wait_read<0>();
+          if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          else __syncwarp();
         }
+        if (!(p.dbg & 1)) {
+#define MV_EPI_SWITCH(EPI)                                                              \
+  switch (p.epi_flags) {                                                                \
+    case 0u: EPI(0u); break;                                                            \
+    case EF_BIAS: EPI(EF_BIAS); break;                                                  \
+    case EF_BIAS | EF_RES | EF_OUT2_PRE: EPI(EF_BIAS | EF_RES | EF_OUT2_PRE); break;    \
+    case EF_DACT1: EPI(EF_DACT1); break;                                                \
+    case EF_RES: EPI(EF_RES); break;                                                    \
+    case EF_OUT2_POST | EF_DACT2: EPI(EF_OUT2_POST | EF_DACT2); break;                  \
+    case EF_OUT2_POST | EF_DMASK2: EPI(EF_OUT2_POST | EF_DMASK2); break;                \
+    case EF_BIAS | EF_NCHW: EPI(EF_BIAS | EF_NCHW); break;                              \
+    default: EPI(EF_GENERIC); break;                                                    \
+  }
+#define MV_EPI(FLAGS) epi_tile<BN, (FLAGS)>(p, r, s_bias, n0, half, taddr, neg, st_out, st_out2, side_tile, mask_row)
+#define MV_EPI64(FLAGS) \
+  epi_tile<64, (FLAGS)>(p, r, s_bias + sub * 64, n0 + sub * 64, half, taddr + sub * 64, neg, st_out, st_out2, side_tile, mask_row)
+          if constexpr (BN == 128) {
+            if (seq) {
+              MV_EPI_SWITCH(MV_EPI64)
+            } else {
+              MV_EPI_SWITCH(MV_EPI)
+            }
+          } else {
+            MV_EPI_SWITCH(MV_EPI)
+          }
+#undef MV_EPI64
 #undef MV_EPI
-      }
-      // accumulator drained and side tile consumed: hand both back before the stores go out
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(&tm_empty[acc]);
-        if (side_tile) tc::mbar_arrive(&side_empty[ss]);
-      }
-      if (side_tile && ++ss == p.side_stages) { ss = 0; sph ^= 1; }
-      if (p.use_tma_store && !(p.dbg & 5)) {
-        tc::fence_proxy_async();
-        if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        else __syncwarp();
-        if (store_leader) {
-          const int b = BN == 128 ? half : 0;   // this leader's 64-column box
-          tc::tma_store_2d(&tmO, st_out + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
-          if (two) tc::tma_store_2d(&tmO2, st_out2 + b * 16384 + q * 4096, n0 + b * 64, p0 + q * 32);
-          tc::tma_store_commit();
+#undef MV_EPI_SWITCH
+        }
+        // accumulator drained (last box) and side tile consumed: hand them back before the stores go out
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (sub == nsub - 1) tc::mbar_arrive(&tm_empty[acc]);
+          if (side_tile) tc::mbar_arrive(&side_empty[ss]);
+        }
+        if (side_tile && ++ss == p.side_stages) { ss = 0; sph ^= 1; }
+        if (p.use_tma_store && !(p.dbg & 5)) {
+          tc::fence_proxy_async();
+          if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          else __syncwarp();
+          if (store_leader) {
+            const int b = (BN == 128 && !seq) ? half : 0;   // this leader's 64-column box of the staging area
+            const int col = n0 + (b + sub) * 64;
+            tc::tma_store_2d(&tmO, st_out + b * 16384 + q * 4096, col, p0 + q * 32);
+            if (two) tc::tma_store_2d(&tmO2, st_out2 + b * 16384 + q * 4096, col, p0 + q * 32);
+            tc::tma_store_commit();
+          }
+          stored = true;
         }
       }
     }
@@ -599,12 +624,13 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
                        size_t(kEpiWarps) * (a->BN < 32 ? 32 : a->BN) * 4 /*bias copies*/;
   const int w_tiles = p.T * p.n_kc;
   p.use_tma_store = (a->out_mode == 0 && a->BN >= 64 && a->out_ld % 8 == 0 && (!a->out2 || a->out2_ld % 8 == 0)) ? 1 : 0;
-  p.stage_out_bytes = uint32_t(a->BN / 64) * 16384u;
   p.n_out = a->out2 ? 2 : 1;
   const void* side_ptr = a->res ? a->res : (a->dact1 ? a->dact1 : ((a->out2 && !a->out2_pre) ? a->dact2 : nullptr));
   const int side_ld = a->res ? a->res_ld : (a->dact1 ? a->dact1_ld : a->dact2_ld);
   p.side_kind = a->res ? 0 : (a->dact1 ? 1 : 2);
   p.side_tma = (side_ptr && a->BN >= 64 && side_ld % 8 == 0) ? 1 : 0;
+  p.seq_boxes = (a->BN == 128 && p.use_tma_store && (p.side_tma || a->out2) && !getenv("MV_TG_NO_SEQ")) ? 1 : 0;
+  p.stage_out_bytes = p.seq_boxes ? 16384u : uint32_t(a->BN / 64) * 16384u;
   const size_t out_stg = p.use_tma_store ? size_t(p.n_out) * p.stage_out_bytes : 0;
   auto round1k = [](size_t v) { return (v + 1023) & ~size_t(1023); };
   // shared-memory plan: try the deepest side ring first; the input ring keeps 3 stages whenever possible
@@ -630,8 +656,9 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
       p.w_stages = budget > in_b + 1024 ? int((budget - in_b - 1024) / p.w_stage_bytes) : 0;
       if (p.w_stages > 8) p.w_stages = 8;
     }
-    const bool deep_enough = p.w_resident ? p.in_stages >= 3 : p.w_stages >= 4;
-    if (deep_enough || side_try <= (p.side_tma ? 2 : 0)) break;
+    // a streaming weight ring wants depth (each 16 KB tile feeds only ~260 cycles of MMAs against ~1.5 k cycles of L2 latency)
+    const bool deep_enough = p.w_resident ? p.in_stages >= 3 : p.w_stages >= 6;
+    if (deep_enough || side_try <= (p.side_tma ? (p.seq_boxes ? 3 : 2) : 0)) break;
   }
   p.side_stages = side_try;
   MV_CHECK_ARG(p.w_resident || p.w_stages >= 2, "mv_tapgemm: not enough shared memory for the weight ring");
