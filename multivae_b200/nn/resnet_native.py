@@ -21,6 +21,7 @@ from . import halo as HL
 
 _LRELU = 0.2
 _MASK_D = os.environ.get("MULTIVAE_B200_MASK_D", "1") != "0"   # save the last block's `d` as a sign mask
+_SPLIT_C0D = os.environ.get("MULTIVAE_B200_SPLIT_C0D", "1") != "0"
 _MASK_H = os.environ.get("MULTIVAE_B200_MASK_H", "1") != "0"   # sign mask of `h` next to h itself (64-channel hidden layers)
 
 
@@ -93,6 +94,7 @@ class _Block:
         self.wsc = self.wscd = None
         if wsc is not None:
             self.wsc, self.wscd = packs[2]
+        self.w0d_halves = None   # data-gradient packs of conv0 per 64 input channels (two 64-output launches, see _block_bwd)
 
 
 def _pack_network(blocks, extra):
@@ -103,13 +105,23 @@ def _pack_network(blocks, extra):
         specs += [(w0, w0.shape[0], w0.shape[1], True), (w1, w1.shape[0], w1.shape[1], True)]
         if wsc is not None:
             specs.append((wsc, wsc.shape[0], wsc.shape[1], True))
-    packs = HL.pack_conv_weights(specs + list(extra))
+    # conv0 of a 128 -> 64 block: its data gradient (64 -> 128) runs as two 64-output convolutions on the three-taps-per-MMA
+    # kernel (the 128-column tap-GEMM streams its 144 KB of weights per tile), each with its own pack
+    split = [k for k, (w0, *_r) in enumerate(blocks) if _SPLIT_C0D and w0.shape[0] == 64 and w0.shape[1] == 128]
+    halves = []
+    for k in split:
+        w0 = blocks[k][0].detach()
+        halves += [(w0[:, :64].contiguous(), 64, 64, True), (w0[:, 64:].contiguous(), 64, 64, True)]
+    n_extra = len(extra)
+    packs = HL.pack_conv_weights(specs + list(extra) + halves)
     out, i = [], 0
     for w0, b0, w1, b1, wsc in blocks:
         n = 2 if wsc is None else 3
         out.append(_Block(w0, b0, w1, b1, wsc, packs[i:i + n]))
         i += n
-    return out, packs[i:]
+    for j, k in enumerate(split):
+        out[k].w0d_halves = (packs[i + n_extra + 2 * j][1], packs[i + n_extra + 2 * j + 1][1])
+    return out, packs[i:i + n_extra]
 
 
 def _block_fwd(x, g, blk, tag, mask_d=False):
@@ -191,7 +203,12 @@ def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=No
             dWsc = HL.wgrad(x, g_out, 1, [0], g.P, tag=f"{tag}.sc", dW=z(1, blk.cout, blk.cin))
         g_short = HL.tapgemm(g_out, blk.wscd, 1, [0], blk.cin, g.P, geom=g, tag=f"{tag}.scd") if need_gx else None
     g_x = None
-    if need_gx:
+    if need_gx and blk.w0d_halves is not None:
+        g_x = torch.empty(g.P, blk.cin, device=g_hpre.device, dtype=torch.bfloat16)
+        for j, wd in enumerate(blk.w0d_halves):
+            HL.tapgemm(g_hpre, wd, 9, taps, 64, g.P, res=g_short[:, 64 * j:64 * j + 64], out=g_x[:, 64 * j:64 * j + 64], geom=g,
+                       tag=f"{tag}.c0d")
+    elif need_gx:
         g_x = HL.tapgemm(g_hpre, blk.w0d, 9, taps, blk.cin, g.P, res=g_short, geom=g, tag=f"{tag}.c0d")
     return g_x, dW0, db0, dW1, db1, dWsc
 
