@@ -82,3 +82,31 @@ def test_config_and_constructor_errors():
         mb.MMVAEConfig(n_modalities=2, loss="nope")
     cfg = mb.MVAEConfig(n_modalities=2, input_dims={"a": (4,), "b": (4,)}, k=3)
     assert mb.MVAE(cfg).k == 0  # k forced to 0 when M <= 2 (mvae_model.py:40-41)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _cabi.py must have the size and field offsets of the structs in include/multivae_b200.h
+    (compiled here with the host C compiler)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from multivae_b200 import _cabi
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no host C compiler")
+    structs = {"mv_tapgemm_args": _cabi.TapGemmArgs, "mv_pack_item": _cabi.PackItem, "mv_unpack_item": _cabi.UnpackItem}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "multivae_b200.h")}"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
