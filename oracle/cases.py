@@ -26,6 +26,26 @@ CASES = {
     "mopoe": dict(model="mopoe", dims=_DIMS3, B=9, cfg=dict(latent_dim=5, beta=2.5, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
     "mopoe_5mod": dict(model="mopoe", dims={f"m{i}": (2, 4, 4) for i in range(5)}, B=40, cfg=dict(latent_dim=6, beta=2.5, decoders_dist={f"m{i}": "laplace" for i in range(5)}, decoder_dist_params={f"m{i}": {"scale": 0.75} for i in range(5)})),
     "mopoe_masked": dict(model="mopoe", dims=_DIMS3, B=9, masks=True, cfg=dict(latent_dim=5, beta=1.0, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    # ---- BASELINE.json configs at their real input shapes (default MLP architectures; every hyper-parameter written out — the values
+    # are the reference configs' defaults / the example scripts' settings; small batches where the config's own is big)
+    "cfg1_mvtcae_quickstart": dict(model="mvtcae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=32,
+                                   cfg=dict(latent_dim=20, alpha=0.1, beta=2.5, decoders_dist={"mnist": "normal", "svhn": "normal"},
+                                            decoder_dist_params={"mnist": {}, "svhn": {}})),
+    "cfg2_mvae_mnistsvhn": dict(model="mvae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=8, fwd=dict(epoch=12, batch_ratio=0.5),
+                                cfg=dict(latent_dim=20, k=0, beta=1.0, warmup=10, uses_likelihood_rescaling=True,
+                                         decoders_dist={"mnist": "normal", "svhn": "normal"}, decoder_dist_params={"mnist": {}, "svhn": {}})),
+    "cfg3_mmvae_mnistsvhn": dict(model="mmvae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=4,
+                                 cfg=dict(K=10, latent_dim=20, loss="iwae_looser", prior_and_posterior_dist="laplace_with_softmax",
+                                          decoders_dist={"mnist": "laplace", "svhn": "laplace"},
+                                          decoder_dist_params={"mnist": {"scale": 0.75}, "svhn": {"scale": 0.75}})),
+    "cfg4_mopoe_polymnist": dict(model="mopoe", dims={f"m{i}": (3, 28, 28) for i in range(5)}, B=62,
+                                 cfg=dict(latent_dim=512, beta=2.5, decoders_dist={f"m{i}": "laplace" for i in range(5)},
+                                          decoder_dist_params={f"m{i}": {"scale": 0.75} for i in range(5)})),
+    "cfg5_mmvaeplus_celeba": dict(model="mmvaeplus", dims={"image": (3, 64, 64), "attributes": (40,)}, B=4,
+                                  cfg=dict(K=10, latent_dim=32, modalities_specific_dim=32, beta=1.0, loss="dreg_looser",
+                                           prior_and_posterior_dist="laplace_with_softmax",
+                                           decoders_dist={"image": "normal", "attributes": "normal"},
+                                           decoder_dist_params={"image": {}, "attributes": {}})),
 }
 
 
