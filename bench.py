@@ -158,41 +158,12 @@ def north_star_model(device):
 
 
 def elbo_rel_err(device, compute_dtype=torch.float32):
-    """|loss_gpu - loss_oracle| / |loss_oracle| on a tiny batch with injected noise.  fp32: library networks + native ELBO
-    kernels; bf16: the tcgen05 decoders (bf16 operands) + native ELBO kernels, against the same fp32 CPU oracle."""
-    import multivae_b200 as mb
-    from oracle.port import elbo as E
-    from oracle.port import nets as N
-    B, Kk = 2, 2
-    model = north_star_model(device)
-    model.compute_dtype = compute_dtype
-    mods = [f"m{i}" for i in range(M)]
-    data = synthetic_batch(B)
-    g = torch.Generator().manual_seed(2000)
-    q = []
-
-    def noise_source(shape, kind, dev):
-        e = mb.elbo.standard_noise(shape, kind, "cpu", generator=g)
-        q.append(e)
-        return e.to(dev)
-
-    model.noise_source = noise_source
-    out = model(mb.MultimodalBaseDataset(data={k: v.to(device) for k, v in data.items()}), K=Kk)
-    p = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    it = iter(q)
-    noise = {"u": {}, "w": {}, "prior": {}}
-    for c in mods:
-        noise["u"][c], noise["w"][c] = next(it), next(it)
-        noise["prior"][c] = {r: next(it) for r in mods if r != c}
-    enc = {m: (lambda x, m=m: N.encoder_resnet_mmnist(p, f"encoders.{m}.", x)) for m in mods}
-    dec = {m: (lambda z, m=m: N.decoder_resnet_mmnist(p, f"decoders.{m}.", z)) for m in mods}
-    with torch.no_grad():
-        ref = E.mmvae_plus_forward(
-            enc, dec, data, noise, K=Kk, latent_dim=L, style_dim=LW, beta=2.5, kind="laplace_with_softmax",
-            loss="dreg_looser", dec_dist={m: "laplace" for m in mods}, dec_scale={m: 0.75 for m in mods},
-            rescale={m: 1 for m in mods}, prior_mean={m: p[f"mean_priors.{m}"] for m in mods + ["shared"]},
-            prior_logvar={m: p[f"logvars_priors.{m}"] for m in mods + ["shared"]})
-    return abs(float(out.loss) - float(ref)) / abs(float(ref))
+    """|loss_gpu - loss_reference| / |loss_reference| on the north-star golden produced by the REAL reference
+    (tests/golden/elbo_ns_mmvaeplus_resnet.pt: ResNet encoders/decoders, K = 10, B = 4, recorded noise).  fp32: library
+    networks + native ELBO kernels; bf16: the tcgen05 encoders/decoders (bf16 operands) + native ELBO kernels."""
+    from tests.gpu_checks import rel, run_product
+    out, _, rec = run_product("ns_mmvaeplus_resnet", device=device, compute_dtype=compute_dtype)
+    return rel(out.loss.detach().cpu(), rec["loss"])
 
 
 def run_gpu(args):

@@ -21,7 +21,7 @@ __device__ __forceinline__ float lp_term(float x, float r) {
   } else if (DIST == MV_DIST_LAPLACE) {
     return fabsf(x - r);
   } else {  // Bernoulli(logits=r).log_prob(x) = x*r - softplus(r)
-    return x * r - (fmaxf(r, 0.f) + log1pf(__expf(-fabsf(r))));
+    return x * r - (fmaxf(r, 0.f) + log1pf(expf(-fabsf(r))));
   }
 }
 template <int DIST>
@@ -32,7 +32,7 @@ __device__ __forceinline__ float lp_grad(float x, float r, float inv_s) {
     float t = x - r;
     return t > 0.f ? inv_s : (t < 0.f ? -inv_s : 0.f);
   } else {
-    return x - 1.f / (1.f + __expf(-r));
+    return x - 1.f / (1.f + expf(-r));
   }
 }
 
@@ -314,9 +314,9 @@ __global__ void __launch_bounds__(128) lpx_bwd_scalar_kernel(const T* __restrict
 // ---- latent log-densities -----------------------------------------------------------------------
 template <int KIND>
 __device__ __forceinline__ float lat_lp(float x, float mu, float s) {
-  if (KIND == MV_LATENT_LAPLACE) return -__logf(2.f * s) - fabsf(x - mu) / s;
+  if (KIND == MV_LATENT_LAPLACE) return -logf(2.f * s) - fabsf(x - mu) / s;
   float t = (x - mu) / s;
-  return -0.5f * t * t - __logf(s) - 0.5f * kLog2Pi;
+  return -0.5f * t * t - logf(s) - 0.5f * kLog2Pi;
 }
 // d/dx of lat_lp (d/dmu is the negative)
 template <int KIND>
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
     avail[m] = m < C && (masks == nullptr || masks[m * B + b] != 0);
     nm += avail[m] ? 1 : 0;
   }
-  const float log_nm = __logf(float(nm > 0 ? nm : 1));
+  const float log_nm = logf(float(nm > 0 ? nm : 1));
   const float inv_nm = nm > 0 ? 1.f / float(nm) : 0.f;
   const int LT = L + Lw;
   float loss_acc = 0.f;
@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
         float se = 0.f;
 #pragma unroll
         for (int m = 0; m < kMaxC; ++m)
-          if (m < C && avail[m]) se += __expf(lq[m] - mq);
-        const float lqu = mq + __logf(se) - log_nm;
+          if (m < C && avail[m]) se += expf(lq[m] - mq);
+        const float lqu = mq + logf(se) - log_nm;
         val = lpx[row] + beta * (lpz - lqu - lqw);
       }
       if (lane == 0) lw[row] = val;
@@ -409,20 +409,20 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
     __syncwarp();
     // ---- softmax over k ------------------------------------------------------------------------
     float se = 0.f;
-    for (int k = lane; k < K; k += 32) se += __expf(lw[(int64_t(c) * K + k) * B + b] - mx);
+    for (int k = lane; k < K; k += 32) se += expf(lw[(int64_t(c) * K + k) * B + b] - mx);
     se = warp_sum(se);
-    const float lse = mx + __logf(se);
+    const float lse = mx + logf(se);
     float term = 0.f;  // sum_k wk*lw (DReG) or lse - log K (IWAE)
     for (int k = lane; k < K; k += 32) {
       const int64_t row = (int64_t(c) * K + k) * B + b;
       const float v = lw[row];
-      const float wgt = __expf(v - lse);
+      const float wgt = expf(v - lse);
       wk[row] = wgt;
       coef[row] = avail[c] ? -wgt * inv_nm : 0.f;
       term += wgt * v;
     }
     term = warp_sum(term);
-    if (loss_kind == MV_LOSS_IWAE) term = lse - __logf(float(K));
+    if (loss_kind == MV_LOSS_IWAE) term = lse - logf(float(K));
     if (avail[c]) loss_acc += term;
     __syncwarp();
     // ---- pass 2: unit gradients of the latent terms ----------------------------------------------
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
 #pragma unroll
       for (int m = 0; m < kMaxC; ++m)
         if (m < C && avail[m]) {
-          lq[m] = __expf(lq[m] - mq);
+          lq[m] = expf(lq[m] - mq);
           sq += lq[m];
         }
       const float inv_sq = 1.f / sq;

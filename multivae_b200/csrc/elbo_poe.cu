@@ -18,7 +18,53 @@ struct PoeAcc {
 
 // precision of expert m at this (b,l); 0 when masked (lv = +inf in the reference)
 __device__ __forceinline__ float expert_T(float lv, bool stable, float eps) {
-  return stable ? __expf(-lv) : 1.f / (__expf(lv) + eps);
+  return stable ? 0.f /* stable form: subset_poe works on the log-variances */ : 1.f / (expf(lv) + eps);
+}
+
+// PoE of the experts of one subset at one (b, l).  eps form (base_utils.py:122-130): precisions T_m = 1/(exp(lv)+eps).
+// stable form (base_utils.py:133-147): ln var = -logsumexp(-lv) with the maximum taken out per subset, so log-variances
+// far outside exp()'s fp32 range neither overflow nor underflow the sum.  rr (optional) = T_m / sum_T per expert.
+__device__ __forceinline__ void subset_poe(uint32_t bits, bool prior, bool stable, float Tp, const float* T, const float* mm,
+                                           const float* lvv, const bool* avail, float* pmu, float* var, float* plv,
+                                           float* rr) {
+  constexpr int kM = 8;
+  float st, sm = 0.f;
+  if (stable) {
+    float shift = prior ? 0.f : -INFINITY;
+#pragma unroll
+    for (int m = 0; m < kM; ++m)
+      if ((bits >> m & 1u) && avail[m]) shift = fmaxf(shift, -lvv[m]);
+    st = prior ? expf(-shift) : 0.f;
+    float t[kM];
+#pragma unroll
+    for (int m = 0; m < kM; ++m) {
+      t[m] = ((bits >> m & 1u) && avail[m]) ? expf(-lvv[m] - shift) : 0.f;
+      st += t[m];
+      sm += mm[m] * t[m];
+    }
+    *pmu = sm / st;
+    *plv = -shift - logf(st);
+    *var = expf(*plv);
+    if (rr) {
+#pragma unroll
+      for (int m = 0; m < kM; ++m) rr[m] = t[m] / st;
+    }
+    return;
+  }
+  st = prior ? Tp : 0.f;
+#pragma unroll
+  for (int m = 0; m < kM; ++m)
+    if (bits >> m & 1u) {
+      st += T[m];
+      sm += mm[m] * T[m];
+    }
+  *pmu = sm / st;
+  *var = 1.f / st;
+  *plv = logf(*var);
+  if (rr) {
+#pragma unroll
+    for (int m = 0; m < kM; ++m) rr[m] = T[m] * *var;
+  }
 }
 
 __device__ __forceinline__ bool use_prior(uint32_t bits, int M, int prior_mode) {
@@ -71,14 +117,8 @@ __global__ void __launch_bounds__(128) poe_fwd_kernel(
     const float Tp = stable ? 1.f : 1.f / (1.f + eps);  // prior expert N(0,I)
     for (int s = 0; s < S; ++s) {
       const uint32_t bits = subsets[s];
-      float st = use_prior(bits, M, prior_mode) ? Tp : 0.f, sm = 0.f;
-#pragma unroll
-      for (int m = 0; m < kMaxM; ++m)
-        if (bits >> m & 1u) {
-          st += T[m];
-          sm += mm[m] * T[m];
-        }
-      const float pmu = sm / st, var = 1.f / st, plv = __logf(var);
+      float pmu, var, plv;
+      subset_poe(bits, use_prior(bits, M, prior_mode), stable, Tp, T, mm, lvv, avail, &pmu, &var, &plv, nullptr);
       const float ws = w ? w[int64_t(s) * B + b] : w_uniform;
       kl_acc += ws * (-0.5f * (1.f + plv - pmu * pmu - var));
       if (s == my_sel) {
@@ -90,7 +130,7 @@ __global__ void __launch_bounds__(128) poe_fwd_kernel(
 #pragma unroll
           for (int m = 0; m < kMaxM; ++m)
             if (m < M && avail[m]) {
-              const float iv = __expf(-lvv[m]);
+              const float iv = expf(-lvv[m]);
               const float d = pmu - mm[m];
               km_acc[m] += -0.5f * (1.f - var * iv - d * d * iv + plv - lvv[m]);
             }
@@ -144,14 +184,9 @@ __global__ void __launch_bounds__(128) poe_bwd_kernel(
     const int64_t o = int64_t(b) * L + l;
     for (int s = 0; s < S; ++s) {
       const uint32_t bits = subsets[s];
-      float st = use_prior(bits, M, prior_mode) ? Tp : 0.f, sm = 0.f;
-#pragma unroll
-      for (int m = 0; m < kMaxM; ++m)
-        if (bits >> m & 1u) {
-          st += T[m];
-          sm += mm[m] * T[m];
-        }
-      const float pmu = sm / st, var = 1.f / st;
+      float pmu, var, plv, rr[kMaxM];   // rr[m] = T_m / sum of precisions (responsibility of expert m in this subset)
+      subset_poe(bits, use_prior(bits, M, prior_mode), stable, Tp, T, mm, lvv, avail, &pmu, &var, &plv, rr);
+      const float st = 1.f / var;
       const float a = (w ? w[int64_t(s) * B + b] : w_uniform) * gk;
       float gmu = a * pmu;                       // d KL / d mu
       float gvar = a * 0.5f * (1.f - st);        // d KL / d var = 0.5 * (1 - 1/var)
@@ -165,7 +200,7 @@ __global__ void __launch_bounds__(128) poe_bwd_kernel(
 #pragma unroll
           for (int m = 0; m < kMaxM; ++m)
             if (m < M && avail[m]) {
-              const float iv = __expf(-lvv[m]);
+              const float iv = expf(-lvv[m]);
               const float d = pmu - mm[m];
               gmu += gkm[m] * d * iv;
               gvar += gkm[m] * 0.5f * (iv - st);
@@ -174,12 +209,16 @@ __global__ void __launch_bounds__(128) poe_bwd_kernel(
             }
         }
       }
-      const float ist = var;  // 1/st
 #pragma unroll
       for (int m = 0; m < kMaxM; ++m)
         if (bits >> m & 1u) {
-          gm[m] += gmu * T[m] * ist;
-          gT[m] += gmu * (mm[m] - pmu) * ist - gvar * var * var;
+          gm[m] += gmu * rr[m];
+          if (stable) {
+            // d/dlv through T = exp(-lv): dT/dlv = -T, written with the responsibilities (no raw exp(-lv) anywhere)
+            glv_direct[m] += -(gmu * (mm[m] - pmu) - gvar * var) * rr[m];
+          } else {
+            gT[m] += gmu * (mm[m] - pmu) * var - gvar * var * var;
+          }
         }
     }
 #pragma unroll
@@ -187,7 +226,7 @@ __global__ void __launch_bounds__(128) poe_bwd_kernel(
       if (m < M) {
         const int64_t i = (int64_t(m) * B + b) * L + l;
         // dT/dlv: stable: -T ; eps form: -exp(lv) * T^2
-        const float dT = stable ? -T[m] : -__expf(lvv[m]) * T[m] * T[m];
+        const float dT = stable ? 0.f : -expf(lvv[m]) * T[m] * T[m];
         g_mu[i] = avail[m] ? gm[m] : 0.f;
         g_lv[i] = avail[m] ? gT[m] * dT + glv_direct[m] : 0.f;
       }

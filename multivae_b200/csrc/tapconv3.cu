@@ -31,7 +31,6 @@ namespace mv {
 using bf16 = __nv_bfloat16;
 int num_sms();
 
-__device__ long long g_c3_clk[4];   // experiment counter: cycles / tiles of CTA 0's MMA warp (MV_TG_DBG != 0)
 
 constexpr int kC3Threads = 640;
 constexpr int kC3EpiWarps = 16;
@@ -55,7 +54,6 @@ struct Conv3Params {
   int side_stages, n_stg;   // side-tile ring depth; staging tiles per epilogue group (outputs not written in place)
   int img_stride, Wp, W, n_img;
   uint32_t flags;
-  int dbg;
 };
 
 template <uint32_t F>
@@ -179,7 +177,6 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc::mbar_wait(w_full, 0);
     tc::fence_after_sync();
     int is = 0, iph = 0, it = 0;
-    const long long clk0 = clock64();
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
       tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
@@ -208,7 +205,6 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (tc::elect_one()) tc::umma_commit(&tm_full[acc]);
       __syncwarp();
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { g_c3_clk[0] = clock64() - clk0; g_c3_clk[1] = it; }
   } else if (warp >= 4) {
     // ================= epilogue (warps 4..19) =================
     // 16 warps in G groups.  G = 1: all warps work on the same tile, 16 output columns each.  G = 2: group g takes the
@@ -627,7 +623,6 @@ head3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 int head3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   *handled = false;
-  if (getenv("MV_NO_CONV3") || getenv("MV_NO_HEAD3")) return MV_OK;
   if (a->T != 9 || a->N_total != 16 || a->BN != 16 || a->Cin != 64 || a->out_mode != 1) return MV_OK;
   if (a->img_stride <= 0 || a->Wp < 2 || a->n_valid < 1 || a->n_valid > 16) return MV_OK;
   for (int r = 0; r < 3; ++r)
@@ -676,7 +671,6 @@ int head3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
 // layout (see the eligibility tests); returns MV_OK with *handled = false otherwise.
 int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   *handled = false;
-  if (getenv("MV_NO_CONV3")) return MV_OK;
   if (a->T != 9 || a->N_total != 64 || a->BN != 64 || (a->Cin != 64 && a->Cin != 128) || a->out_mode != 0) return MV_OK;
   if (a->img_stride <= 0 || a->Wp < 2) return MV_OK;
   for (int r = 0; r < 3; ++r)
@@ -716,14 +710,10 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     return fixed + p.w_bytes + size_t(G) * size_t(nstg) * 16384 + size_t(side_stages) * 16384 + size_t(in_stages) * p.in_stage_bytes;
   };
   int G = 0, in_min = 3;
-  const bool one_group = getenv("MV_C3_ONE_GROUP") != nullptr || p.n_kc != 1;
+  const bool one_group = p.n_kc != 1;
   if (!one_group && !has_side && plan(2, n_out, 0, 3) <= kC3SmemLimit) { G = 2; p.n_stg = n_out; p.side_stages = 0; }
-  if (!G && !one_group && has_side && !getenv("MV_C3_SIDE_ONE_GROUP")) {
-    if (getenv("MV_C3_INPLACE") && plan(2, n_out - 1, 4, 3) <= kC3SmemLimit) {
-      G = 2; p.n_stg = n_out - 1; p.side_stages = 4; p.inplace = 1;
-    } else if (plan(2, n_out, 3, 2) <= kC3SmemLimit) {
-      G = 2; p.n_stg = n_out; p.side_stages = 3; in_min = 2;
-    }
+  if (!G && !one_group && has_side && plan(2, n_out, 3, 2) <= kC3SmemLimit) {
+    G = 2; p.n_stg = n_out; p.side_stages = 3; in_min = 2;
   }
   if (!G) {
     in_min = p.n_kc == 1 ? 3 : 2;
@@ -734,10 +724,6 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.in_stages = int((kC3SmemLimit - plan(G, p.n_stg, p.side_stages, 0)) / p.in_stage_bytes);
   if (p.in_stages > kC3MaxStages) p.in_stages = kC3MaxStages;
   if (p.in_stages < in_min) return MV_OK;
-  if (const char* e = getenv("MV_TG_IN_STAGES")) {
-    int v = atoi(e);
-    if (v >= 1 && v <= p.in_stages) p.in_stages = v;
-  }
   p.bias = a->bias;
   p.neg = a->act == MV_ACT_LRELU02 ? 0.2f : (a->act == MV_ACT_RELU ? 0.f : 1.f);
   p.alpha = a->alpha;
@@ -747,7 +733,6 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
             (a->out2_mask ? C3_MASK2 : 0u) | (a->dmask1 ? C3_DMASK1 : 0u);
   p.dmask1 = static_cast<const uint64_t*>(a->dmask1);
   p.mask2 = static_cast<uint64_t*>(a->out2_mask);
-  if (const char* e = getenv("MV_TG_DBG")) p.dbg = atoi(e);
 
   CUtensorMap tmA, tmW;
   if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.R), 64,
@@ -809,10 +794,3 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
 
 }  // namespace mv
 
-extern "C" int mv_debug_c3_clk(long long* cycles, long long* tiles) {
-  long long h[4];
-  if (cudaMemcpyFromSymbol(h, mv::g_c3_clk, sizeof(h)) != cudaSuccess) return MV_ERR_CUDA;
-  *cycles = h[0];
-  *tiles = h[1];
-  return MV_OK;
-}

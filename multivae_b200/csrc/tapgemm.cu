@@ -23,17 +23,12 @@
 //             (double-buffered in TMEM so the next tile's MMAs overlap), bias / activation / activation-derivative /
 //             residual / halo mask, bf16 pack into a swizzled staging tile, 32-row TMA stores
 // 3x3 convolutions with 64 (or <= 16, NCHW) output channels are routed to the three-taps-per-MMA kernels of tapconv3.cu.
-// MV_TG_DBG / MV_TG_IN_STAGES / MV_TG_SIDE_STAGES are experiment switches (tools/exp_tapgemm*.py), not product options.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace mv {
 
 using bf16 = __nv_bfloat16;
-
-__device__ long long g_tg_clk[4];   // experiment: SM cycles the MMA warp of CTA 0 spent in its tile loop
 
 constexpr int kMaxTaps = 9;
 constexpr int kMaxInStages = 3;
@@ -77,7 +72,6 @@ struct TapGemmParams {
   const unsigned long long* dmask2;   // EF_DMASK2: sign bits of the second output's activation-derivative source, 64 per row
   int seq_boxes;            // BN = 128 with staged side inputs / two outputs: the epilogue handles the tile's two 64-column boxes one
                             // after the other through 16 KB buffers, which leaves shared memory for a deep weight ring
-  int dbg;                  // experiment switches (MV_TG_DBG): 1 skip epilogue body, 2 skip MMA issue, 4 skip TMA stores
 };
 
 
@@ -310,7 +304,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
       for (int kc = 0; kc < p.n_kc; ++kc) {
-        if (p.dbg & 16) tc::mbar_wait_relaxed(&in_empty[is], iph ^ 1); else tc::mbar_wait(&in_empty[is], iph ^ 1);
+        tc::mbar_wait(&in_empty[is], iph ^ 1);
         if (tc::elect_one()) {
           tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * ROWB);
           tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], kc * CK, p0 - p.halo_lo);
@@ -363,7 +357,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int t = 0; t < TU; ++t) tap_lo[t] = uint32_t(int(p.halo_lo + p.tap_off[t]) * int(ROWB)) >> 4;
     int is = 0, iph = 0, ws = 0, wph = 0, it = 0;
-    const long long clk0 = clock64();
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
       tc::mbar_wait(&tm_empty[acc], acc_ph ^ 1);
@@ -380,7 +373,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           const uint32_t b_lo0 = desc_lo_const | ((tc::smem_u32(w_base + size_t(kc * T) * p.w_stage_bytes) & 0x3FFFFu) >> 4);
           const uint32_t b_step = p.w_stage_bytes >> 4;
-          if (tc::elect_one() && !(p.dbg & 2)) {
+          if (tc::elect_one()) {
             if (TT > 0) {
 #pragma unroll
               for (int t = 0; t < TU; ++t) {
@@ -435,7 +428,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tc::elect_one()) tc::umma_commit(&tm_full[acc]);
       __syncwarp();
     }
-    if (p.dbg && blockIdx.x == 0 && lane == 0) { g_tg_clk[0] = clock64() - clk0; g_tg_clk[1] = it; }
   } else if (warp >= 4) {
     // ================= epilogue (warps 4..11) =================
     // A warp owns one TMEM lane quarter = 32 rows of the tile and half of its columns, with its own copy of the bias
@@ -481,7 +473,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // sign-mask word of this row: requested before the wait so that the L2 round trip hides behind the tile's MMAs
       unsigned long long mask_row = 0ull;
       if ((p.epi_flags & EF_DMASK2) && r.valid) mask_row = p.dmask2[r.row];
-      if (p.dbg & 16) tc::mbar_wait_relaxed(&tm_full[acc], uint32_t(acc_ph)); else tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
+      tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
       for (int sub = 0; sub < nsub; ++sub) {
         const uint8_t* side_tile = p.side_stages > 0 ? side_base + size_t(ss) * p.stage_out_bytes : nullptr;
@@ -492,7 +484,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
           else __syncwarp();
         }
-        if (!(p.dbg & 1)) {
+        {
 #define MV_EPI_SWITCH(EPI)                                                              \
   switch (p.epi_flags) {                                                                \
     case 0u: EPI(0u); break;                                                            \
@@ -529,7 +521,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (side_tile) tc::mbar_arrive(&side_empty[ss]);
         }
         if (side_tile && ++ss == p.side_stages) { ss = 0; sph ^= 1; }
-        if (p.use_tma_store && !(p.dbg & 5)) {
+        if (p.use_tma_store) {
           tc::fence_proxy_async();
           if (pair_store) asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
           else __syncwarp();
@@ -554,15 +546,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled);
 int head3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled);
 
-static int g_num_sms = 0;
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return cache[dev];
 }
 
 constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
@@ -570,14 +565,6 @@ constexpr size_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA
 }  // namespace mv
 
 using namespace mv;
-
-extern "C" int mv_debug_tg_clk(long long* cycles, long long* tiles) {
-  long long h[4];
-  if (cudaMemcpyFromSymbol(h, g_tg_clk, sizeof(h)) != cudaSuccess) return MV_ERR_CUDA;
-  *cycles = h[0];
-  *tiles = h[1];
-  return MV_OK;
-}
 
 extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   MV_CHECK_ARG(a && a->A && a->Wt && a->out, "mv_tapgemm: null pointer");
@@ -616,10 +603,6 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   const uint32_t rowb = CK * 2;
   p.in_stage_bytes = (uint32_t(p.R) * rowb + 1023u) & ~1023u;
   p.w_stage_bytes = uint32_t(a->BN) * rowb;
-  if (const char* e = getenv("MV_TG_IN_STAGE_BYTES")) {  // layout experiments
-    uint32_t v = uint32_t(atoi(e));
-    if (v >= p.in_stage_bytes) p.in_stage_bytes = v & ~1023u;
-  }
   const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 4 + 2 * kMaxSideStages) * 8 + 16 +
                        size_t(kEpiWarps) * (a->BN < 32 ? 32 : a->BN) * 4 /*bias copies*/;
   const int w_tiles = p.T * p.n_kc;
@@ -629,16 +612,12 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   const int side_ld = a->res ? a->res_ld : (a->dact1 ? a->dact1_ld : a->dact2_ld);
   p.side_kind = a->res ? 0 : (a->dact1 ? 1 : 2);
   p.side_tma = (side_ptr && a->BN >= 64 && side_ld % 8 == 0) ? 1 : 0;
-  p.seq_boxes = (a->BN == 128 && p.use_tma_store && (p.side_tma || a->out2) && !getenv("MV_TG_NO_SEQ")) ? 1 : 0;
+  p.seq_boxes = (a->BN == 128 && p.use_tma_store && (p.side_tma || a->out2)) ? 1 : 0;
   p.stage_out_bytes = p.seq_boxes ? 16384u : uint32_t(a->BN / 64) * 16384u;
   const size_t out_stg = p.use_tma_store ? size_t(p.n_out) * p.stage_out_bytes : 0;
   auto round1k = [](size_t v) { return (v + 1023) & ~size_t(1023); };
   // shared-memory plan: try the deepest side ring first; the input ring keeps 3 stages whenever possible
   int side_try = p.side_tma ? kMaxSideStages : 0;
-  if (const char* e = getenv("MV_TG_SIDE_STAGES")) {
-    int v = atoi(e);
-    if (p.side_tma && v >= 1 && v <= kMaxSideStages) side_try = v;
-  }
   for (;; --side_try) {
     const size_t stg = out_stg + size_t(side_try) * p.stage_out_bytes;
     const size_t budget = kSmemLimit - fixed - stg;
@@ -663,12 +642,7 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   p.side_stages = side_try;
   MV_CHECK_ARG(p.w_resident || p.w_stages >= 2, "mv_tapgemm: not enough shared memory for the weight ring");
   if (p.in_stages > kMaxInStages) p.in_stages = kMaxInStages;
-  if (const char* e = getenv("MV_TG_IN_STAGES")) {
-    int v = atoi(e);
-    if (v >= 1 && v <= p.in_stages) p.in_stages = v;
-  }
   MV_CHECK_ARG(p.in_stages >= 1, "mv_tapgemm: not enough shared memory for one input stage");
-  if (const char* e = getenv("MV_TG_DBG")) p.dbg = atoi(e);
   p.acc_stride = a->BN < 32 ? 32 : a->BN;
   p.tmem_cols = 2 * p.acc_stride;  // 64 / 128 / 256: powers of two
   p.bias = a->bias; p.act = a->act; p.alpha = a->alpha;

@@ -252,7 +252,7 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   // filter row from 8 MMAs instead of 12, each twice as efficient.
   int Wp3 = 0;
   bool pair = false;
-  if (Cin == 64 && (N == 64 || N == 16) && T == 9 && (N_total == N || nct) && !getenv("MV_WG_NO_PAIR")) {
+  if (Cin == 64 && (N == 64 || N == 16) && T == 9 && (N_total == N || nct)) {
     Wp3 = tap_off[7] - tap_off[4];
     pair = Wp3 >= 2;
     for (int r = 0; r < 3 && pair; ++r)

@@ -3,8 +3,9 @@ only) and tests/ (replays the same cases through the oracle port and the CUDA pa
 TEST INFRASTRUCTURE ONLY."""
 import torch
 
-# name -> spec.  All use the reference's default MLP architectures (what Model(config) builds when
-# encoders/decoders are None) with weights from oracle.port.nets.synth_state_dict(seed).
+# name -> spec.  Networks: the reference's default MLP architectures (what Model(config) builds when encoders/decoders are
+# None) unless the spec carries `arch` = {modality: "mlp" | "svhn" | "conv_mmnist" | "resnet_mmnist"}; weights from
+# oracle.port.nets.synth_state_dict(seed).
 _DIMS3 = {"m0": (3, 8, 8), "m1": (1, 6, 6), "m2": (10,)}
 _DIST3 = {"m0": "laplace", "m1": "normal", "m2": "normal"}
 _PAR3 = {"m0": {"scale": 0.75}, "m1": {"scale": 0.5}, "m2": {}}
@@ -31,14 +32,19 @@ CASES = {
     "cfg1_mvtcae_quickstart": dict(model="mvtcae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=32,
                                    cfg=dict(latent_dim=20, alpha=0.1, beta=2.5, decoders_dist={"mnist": "normal", "svhn": "normal"},
                                             decoder_dist_params={"mnist": {}, "svhn": {}})),
-    "cfg2_mvae_mnistsvhn": dict(model="mvae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=8, fwd=dict(epoch=12, batch_ratio=0.5),
+    # cfg2-cfg4 on the networks SURVEY 8(d) names (mnist: default MLP, svhn: Encoder/Decoder_VAE_SVHN, PolyMNIST:
+    # EncoderConvMMNIST_adapted / DecoderConvMMNIST) at the configurations' own per-device batch sizes
+    "cfg2_mvae_mnistsvhn": dict(model="mvae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=512, fwd=dict(epoch=12, batch_ratio=0.5),
+                                arch={"mnist": "mlp", "svhn": "svhn"},
                                 cfg=dict(latent_dim=20, k=0, beta=1.0, warmup=10, uses_likelihood_rescaling=True,
                                          decoders_dist={"mnist": "normal", "svhn": "normal"}, decoder_dist_params={"mnist": {}, "svhn": {}})),
-    "cfg3_mmvae_mnistsvhn": dict(model="mmvae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=4,
+    "cfg3_mmvae_mnistsvhn": dict(model="mmvae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=256,
+                                 arch={"mnist": "mlp", "svhn": "svhn"},
                                  cfg=dict(K=10, latent_dim=20, loss="iwae_looser", prior_and_posterior_dist="laplace_with_softmax",
                                           decoders_dist={"mnist": "laplace", "svhn": "laplace"},
                                           decoder_dist_params={"mnist": {"scale": 0.75}, "svhn": {"scale": 0.75}})),
-    "cfg4_mopoe_polymnist": dict(model="mopoe", dims={f"m{i}": (3, 28, 28) for i in range(5)}, B=62,
+    "cfg4_mopoe_polymnist": dict(model="mopoe", dims={f"m{i}": (3, 28, 28) for i in range(5)}, B=256,
+                                 arch={f"m{i}": "conv_mmnist" for i in range(5)},
                                  cfg=dict(latent_dim=512, beta=2.5, decoders_dist={f"m{i}": "laplace" for i in range(5)},
                                           decoder_dist_params={f"m{i}": {"scale": 0.75} for i in range(5)})),
     "cfg5_mmvaeplus_celeba": dict(model="mmvaeplus", dims={"image": (3, 64, 64), "attributes": (40,)}, B=4,
@@ -46,6 +52,20 @@ CASES = {
                                            prior_and_posterior_dist="laplace_with_softmax",
                                            decoders_dist={"image": "normal", "attributes": "normal"},
                                            decoder_dist_params={"image": {}, "attributes": {}})),
+    "cfg5_mmvaeplus_celeba_b128": dict(model="mmvaeplus", dims={"image": (3, 64, 64), "attributes": (40,)}, B=128,
+                                       cfg=dict(K=10, latent_dim=32, modalities_specific_dim=32, beta=2.5, loss="dreg_looser",
+                                                prior_and_posterior_dist="laplace_with_softmax",
+                                                decoders_dist={"image": "normal", "attributes": "normal"},
+                                                decoder_dist_params={"image": {}, "attributes": {}})),
+    # the north star: MMVAE+ PolyMNIST, 5 modalities, K = 10, DReG, EncoderResnetMMNIST(32, 32) / DecoderResnetMMNIST(64)
+    # (examples/case_studies/mmvaePlus_on_partial_data/train.py:49-78), synthetic (non-initial) weights
+    "ns_mmvaeplus_resnet": dict(model="mmvaeplus", dims={f"m{i}": (3, 28, 28) for i in range(5)}, B=4,
+                                arch={f"m{i}": "resnet_mmnist" for i in range(5)},
+                                cfg=dict(K=10, latent_dim=32, modalities_specific_dim=32, beta=2.5, loss="dreg_looser",
+                                         prior_and_posterior_dist="laplace_with_softmax", learn_modality_prior=True,
+                                         learn_shared_prior=False,
+                                         decoders_dist={f"m{i}": "laplace" for i in range(5)},
+                                         decoder_dist_params={f"m{i}": {"scale": 0.75} for i in range(5)})),
 }
 
 

@@ -30,6 +30,32 @@ def summarize_grads(model):
     return g
 
 
+def reference_archs(spec):
+    """Encoders / decoders of the REAL reference for a spec's `arch` table (None, None = the model's own defaults)."""
+    if "arch" not in spec:
+        return None, None
+    from multivae.models.base.base_config import BaseAEConfig
+    from multivae.models.nn import default_architectures as da
+    from multivae.models.nn import mmnist, svhn
+    L = spec["cfg"]["latent_dim"]
+    Lw = spec["cfg"].get("modalities_specific_dim")
+    enc, dec = {}, {}
+    for m, a in spec["arch"].items():
+        c = BaseAEConfig(input_dim=tuple(spec["dims"][m]), latent_dim=L)
+        if a == "mlp":
+            assert Lw is None
+            enc[m], dec[m] = da.Encoder_VAE_MLP(c), da.Decoder_AE_MLP(c)
+        elif a == "svhn":
+            enc[m], dec[m] = svhn.Encoder_VAE_SVHN(c), svhn.Decoder_VAE_SVHN(c)
+        elif a == "conv_mmnist":
+            enc[m], dec[m] = mmnist.EncoderConvMMNIST_adapted(c), mmnist.DecoderConvMMNIST(c)
+        elif a == "resnet_mmnist":
+            enc[m], dec[m] = mmnist.EncoderResnetMMNIST(Lw or 0, L), mmnist.DecoderResnetMMNIST(L + (Lw or 0))
+        else:
+            raise ValueError(a)
+    return enc, dec
+
+
 def run_case(name, spec):
     ref_harness.import_reference()
     from multivae.data.datasets.base import IncompleteDataset, MultimodalBaseDataset
@@ -40,7 +66,8 @@ def run_case(name, spec):
            "mvae": (MVAE, MVAEConfig), "mopoe": (MoPoE, MoPoEConfig)}[spec["model"]]
     import copy
     cfg = cls[1](n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"]))
-    model = cls[0](cfg)
+    enc, dec = reference_archs(spec)
+    model = cls[0](cfg, enc, dec)
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     sd = synth_state_dict(shapes, seed=1)
     # non-trivial prior parameters so that their gradients are exercised

@@ -26,6 +26,25 @@ def dist_tables(spec):
 def default_nets(spec, p, dtype=torch.float32):
     """Closures over a parameter dict `p` for the reference's default MLP architectures."""
     mods = list(spec["dims"])
+    if "arch" in spec:
+        enc, dec = {}, {}
+        for m in mods:
+            a, e, d = spec["arch"][m], f"encoders.{m}.", f"decoders.{m}."
+            if a == "mlp":
+                enc[m] = lambda x, e=e: N.encoder_vae_mlp(p, e, x)
+                dec[m] = lambda z, d=d, m=m: N.decoder_ae_mlp(p, d, z, spec["dims"][m])
+            elif a == "svhn":
+                enc[m] = lambda x, e=e: N.encoder_vae_svhn(p, e, x)
+                dec[m] = lambda z, d=d: N.decoder_vae_svhn(p, d, z)
+            elif a == "conv_mmnist":
+                enc[m] = lambda x, e=e: N.encoder_conv_mmnist_adapted(p, e, x)
+                dec[m] = lambda z, d=d: N.decoder_conv_mmnist(p, d, z)
+            elif a == "resnet_mmnist":
+                enc[m] = lambda x, e=e: N.encoder_resnet_mmnist(p, e, x)
+                dec[m] = lambda z, d=d: N.decoder_resnet_mmnist(p, d, z)
+            else:
+                raise ValueError(a)
+        return enc, dec
     if spec["model"] == "mmvaeplus":
         enc = {m: (lambda x, m=m: N.encoder_vae_mlp_style(p, f"encoders.{m}.", x)) for m in mods}
     else:

@@ -19,11 +19,34 @@ def load_golden(name):
     return torch.load(os.path.join(GOLD, f"elbo_{name}.pt"), weights_only=False)
 
 
+def product_archs(spec):
+    """multivae_b200.nn encoders / decoders for a spec's `arch` table (None, None = the model's own defaults)."""
+    if "arch" not in spec:
+        return None, None
+    from multivae_b200 import nn as NN
+    L, Lw = spec["cfg"]["latent_dim"], spec["cfg"].get("modalities_specific_dim")
+    enc, dec = {}, {}
+    for m, a in spec["arch"].items():
+        c = mb.BaseAEConfig(input_dim=tuple(spec["dims"][m]), latent_dim=L)
+        if a == "mlp":
+            enc[m], dec[m] = NN.Encoder_VAE_MLP(c), NN.Decoder_AE_MLP(c)
+        elif a == "svhn":
+            enc[m], dec[m] = NN.Encoder_VAE_SVHN(c), NN.Decoder_VAE_SVHN(c)
+        elif a == "conv_mmnist":
+            enc[m], dec[m] = NN.EncoderConvMMNIST_adapted(c), NN.DecoderConvMMNIST(c)
+        elif a == "resnet_mmnist":
+            enc[m], dec[m] = NN.EncoderResnetMMNIST(Lw or 0, L), NN.DecoderResnetMMNIST(L + (Lw or 0))
+        else:
+            raise ValueError(a)
+    return enc, dec
+
+
 def build_model(spec, rec, device):
     import copy
     cls, cfgcls = MODELS[spec["model"]]
     cfg = cfgcls(n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"]))
-    model = cls(cfg)
+    enc, dec = product_archs(spec)
+    model = cls(cfg, enc, dec)
     sd = synth_state_dict(rec["state_shapes"], seed=rec["sd_seed"])
     missing = set(model.state_dict().keys()) ^ set(sd.keys())
     assert not missing, f"state_dict keys differ from the reference: {sorted(missing)[:5]}"
@@ -31,11 +54,14 @@ def build_model(spec, rec, device):
     return model.to(device).train()
 
 
-def run_product(name, device="cuda"):
-    """Returns (ModelOutput, model) after loss.backward()."""
+def run_product(name, device="cuda", compute_dtype=None):
+    """Returns (ModelOutput, model, golden record) after loss.backward().  compute_dtype = torch.bfloat16 runs the encoder /
+    decoder contractions on the native tensor-core kernels (bf16 operands, fp32 accumulate)."""
     import numpy as np
     spec, rec = CASES[name], load_golden(name)
     model = build_model(spec, rec, device)
+    if compute_dtype is not None:
+        model.compute_dtype = compute_dtype
     data, masks = make_data(spec)
     data = {k: v.to(device) for k, v in data.items()}
     q = [e.to(device) for e in rec["noise"]]
@@ -65,11 +91,8 @@ def rel(a, b):
     return abs(a - b) / max(abs(b), 1e-12)
 
 
-# Per-case tolerances where fp32 itself cannot do better.  cfg5 (D = 12288, DReG): the importance weights are nearly one-hot
-# over log-weights of magnitude 1.2e4, so fp32 rounding of the log-weights (1e-6 relative = 1e-2 absolute) moves the loss by
-# ~1e-4 relative: the reference's own fp32 value differs from an fp64 evaluation of the same algorithm by 7.4e-5
-# (tests/test_oracle_port.py::test_cfg5_fp32_conditioning), so 1e-4 agreement between two fp32 implementations is not defined.
-CASE_TOL = {"cfg5_mmvaeplus_celeba": dict(loss=3e-4)}   # measured on B200: loss 1.24e-4, gradients 9e-4 of the tensor max
+# Per-case tolerance overrides: none — every case, cfg5 (D = 12288, DReG) included, is held to 1e-4.
+CASE_TOL = {}
 
 
 def check_case(name, rtol_loss=1e-4, verbose=False):
@@ -112,23 +135,43 @@ def check_case(name, rtol_loss=1e-4, verbose=False):
     return errs
 
 
+def check_case_bf16(name, verbose=False):
+    """The same golden case with the encoder / decoder contractions on the native tensor-core path (bf16 operands, fp32
+    accumulate, fp32 master weights, fp32 ELBO): returns the loss error and the worst parameter-gradient error against the
+    fp32 reference — the distance is the operand precision BASELINE.json asks for, so it is reported and bounded, not 1e-4."""
+    out, model, rec = run_product(name, compute_dtype=torch.bfloat16)
+    _, _, _, pp = run_port(CASES[name], rec)
+    errs = {"loss": rel(out.loss.detach().cpu(), rec["loss"]), "grad_max_rel": 0.0, "grad_rel_l2": 0.0}
+    num = den = 0.0
+    for k, p in model.named_parameters():
+        if rec["grads"][k] is None:
+            continue
+        ref = pp[k].grad
+        pg = p.grad.detach().float().cpu()
+        e = float((pg - ref).abs().max()) / max(float(ref.abs().max()), 1e-12)
+        if e > errs["grad_max_rel"]:
+            errs["grad_max_rel"], errs["grad_worst"] = e, k
+        num += float((pg - ref).double().pow(2).sum())
+        den += float(ref.double().pow(2).sum())
+    errs["grad_rel_l2"] = (num / max(den, 1e-30)) ** 0.5
+    if verbose:
+        print(name, "bf16 tensor path:", errs)
+    return errs
+
+
 def smoke_check():
     """One small invocation of the hot path on cuda:0, checked against the oracle."""
     assert torch.cuda.is_available(), "smoke() needs a GPU"
     torch.cuda.set_device(0)
+    # 1) the north-star model on the tcgen05 path FIRST (so its kernels are inside the driver's launch window): the real
+    #    reference's golden (ResNet encoders / decoders, K = 10, non-initial weights), bf16 operands vs the fp32 reference
+    e16 = check_case_bf16("ns_mmvaeplus_resnet", verbose=True)
+    assert e16["loss"] <= NS_BF16_LOSS_TOL and e16["grad_rel_l2"] <= NS_BF16_GRAD_L2_TOL, e16
+    # 2) the fused ELBO kernels on a small MMVAE+ case: loss / lw / every gradient against the reference golden and the port
     e = check_case("mmvaeplus_dreg", verbose=True)
-    # the north-star model (ResNet encoders/decoders): library-network fp32 path and the tcgen05 decoder path (bf16
-    # operands) against the fp32 CPU oracle, plus one backward through the native decoders
-    import bench
-    dev = torch.device("cuda", 0)
-    r32 = bench.elbo_rel_err(dev)
-    r16 = bench.elbo_rel_err(dev, torch.bfloat16)
-    assert r32 <= 1e-4, r32
-    assert r16 <= 2e-2, r16
-    model = bench.north_star_model(dev)
-    model.compute_dtype = torch.bfloat16
-    out = model(mb.MultimodalBaseDataset(data={k: v.to(dev) for k, v in bench.synthetic_batch(2).items()}), K=2)
-    out.loss.backward()
-    g = model.decoders["m0"].resnet[4].conv_layers[0].weight.grad
-    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().sum()) > 0
-    print("smoke ok:", e, "north-star ELBO rel err fp32 path", r32, "bf16 tensor path", r16)
+    print("smoke ok:", e, "north-star bf16 tensor path", e16)
+
+
+# bounds of the bf16 tensor-core path on the north-star golden = 3x what was measured on B200 (see DESIGN.md section 2)
+NS_BF16_LOSS_TOL = 2e-3
+NS_BF16_GRAD_L2_TOL = 6e-2

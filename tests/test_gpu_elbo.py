@@ -15,6 +15,15 @@ def test_case_matches_reference(name):
     check_case(name, verbose=True)
 
 
+def test_north_star_golden_on_the_bf16_tensor_core_path():
+    """MMVAE+ / ResNet golden of the REAL reference (K = 10, B = 4, non-initial weights) through the native tcgen05 encoders and
+    decoders: loss and every-parameter gradient error against the fp32 reference, bounded at 3x the measured values."""
+    from tests.gpu_checks import NS_BF16_GRAD_L2_TOL, NS_BF16_LOSS_TOL, check_case_bf16
+    e = check_case_bf16("ns_mmvaeplus_resnet", verbose=True)
+    assert e["loss"] <= NS_BF16_LOSS_TOL, e
+    assert e["grad_rel_l2"] <= NS_BF16_GRAD_L2_TOL, e
+
+
 def test_mopoe_selection_bit_exact():
     from oracle.port.elbo import mopoe_sample_to_subset, mopoe_subset_bitmasks
     from tests.gpu_checks import run_product

@@ -38,12 +38,12 @@ def test_no_cpu_fallback():
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_state_dict_keys_match_reference(name):
-    from tests.gpu_checks import MODELS
+    from tests.gpu_checks import MODELS, product_archs
     import copy
     rec = torch.load(os.path.join(GOLD, f"elbo_{name}.pt"), weights_only=False)
     spec = CASES[name]
     cls, cfgcls = MODELS[spec["model"]]
-    model = cls(cfgcls(n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"])))
+    model = cls(cfgcls(n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"])), *product_archs(spec))
     mine = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     assert mine == rec["state_shapes"]
     ref_trainable = {k for k, g in rec["grads"].items() if g is not None or "prior" not in k}
@@ -51,18 +51,19 @@ def test_state_dict_keys_match_reference(name):
     assert {k for k in mine_trainable if "prior" in k} == {k for k in ref_trainable if "prior" in k}
 
 
-@pytest.mark.parametrize("net", ["enc_resnet_mmnist", "dec_resnet_mmnist", "enc_conv_mmnist", "dec_conv_mmnist", "enc_svhn", "dec_svhn", "enc_mlp", "enc_mlp_style", "dec_mlp"])
+@pytest.mark.parametrize("net", sorted(__import__("tests.net_checks", fromlist=["NETS"]).NETS))
 def test_network_state_dict_matches_reference(net):
-    from multivae_b200 import nn as N
+    from tests.net_checks import NETS
     rec = torch.load(os.path.join(GOLD, f"nets_{net}.pt"), weights_only=False)
-    c = lambda i, l, s=0: mb.BaseAEConfig(input_dim=i, latent_dim=l, style_dim=s)  # noqa: E731
-    ctor = {"enc_resnet_mmnist": lambda: N.EncoderResnetMMNIST(32, 32), "dec_resnet_mmnist": lambda: N.DecoderResnetMMNIST(64),
-            "enc_conv_mmnist": lambda: N.EncoderConvMMNIST_adapted(c((3, 28, 28), 64)), "dec_conv_mmnist": lambda: N.DecoderConvMMNIST(c((3, 28, 28), 64)),
-            "enc_svhn": lambda: N.Encoder_VAE_SVHN(c((3, 32, 32), 20)), "dec_svhn": lambda: N.Decoder_VAE_SVHN(c((3, 32, 32), 20)),
-            "enc_mlp": lambda: N.Encoder_VAE_MLP(c((1, 28, 28), 20)), "enc_mlp_style": lambda: N.Encoder_VAE_MLP_Style(c((3, 8, 8), 8, 4)),
-            "dec_mlp": lambda: N.Decoder_AE_MLP(c((1, 28, 28), 20))}[net]
-    m = ctor()
+    m = NETS[net]()
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == rec["state_shapes"]
+
+
+@pytest.mark.parametrize("net", sorted(__import__("tests.net_checks", fromlist=["NETS"]).NETS))
+def test_network_forward_backward_matches_reference_on_cpu(net):
+    """The product's nn modules (library-layer path, CPU) against outputs and gradients of the REAL reference modules."""
+    from tests.net_checks import check_net
+    check_net(net, "cpu", rtol=1e-4, atol=1e-5, grad_tol=1e-3)
 
 
 def test_subset_logic_known_answers():
