@@ -30,6 +30,7 @@ extern "C" {
 #define MV_DIST_NORMAL 0
 #define MV_DIST_LAPLACE 1
 #define MV_DIST_BERNOULLI 2
+#define MV_DIST_CATEGORICAL 3   /* own entry points (mv_moe_lpx_cat_*): the log-prob needs a softmax over the class dimension */
 
 /* latent prior/posterior families: models/mmvaePlus/mmvaePlus_model.py:57-73 */
 #define MV_LATENT_LAPLACE 0
@@ -84,6 +85,29 @@ int mv_moe_lpx_fwd_multi(int n_mod, const void* const* recon, int recon_dtype, c
 int mv_moe_lpx_bwd_multi(int n_mod, const void* const* recon, int recon_dtype, const float* const* x, const float* coef,
                          const float* g_loss, void* const* g_recon, int C, int K, int B, int64_t D, int dist,
                          const float* dist_scale, const float* rescale, const uint8_t* const* mask_r, void* stream);
+
+/* Categorical decoders (base_utils.py:28-59 cross_entropy_, :81-87): recon [C,K,B,P,V] holds logits over V classes at P positions,
+ * x [B,P,V] the target probabilities (one-hot):
+ *   lpx[c,k,b] (+)= rescale * mask_r[b] * sum_p sum_v x[b,p,v] * log_softmax(recon[c,k,b,p,:] + 1e-6)[v]
+ *   g_recon[c,k,b,p,v] = g_loss * coef[c,k,b] * rescale * mask_r[b] * (x[b,p,v] - softmax(recon[c,k,b,p,:])[v] * sum_v' x[b,p,v']) */
+int mv_moe_lpx_cat_fwd(const void* recon, int recon_dtype, const float* x, float* lpx, int C, int K, int B, int P, int V,
+                       float rescale, const uint8_t* mask_r, int accumulate, void* stream);
+int mv_moe_lpx_cat_bwd(const void* recon, int recon_dtype, const float* x, const float* coef, const float* g_loss, void* g_recon,
+                       int C, int K, int B, int P, int V, float rescale, const uint8_t* mask_r, void* stream);
+
+/* out[b] = logsumexp_r lw[r,b] - log R: the importance-sampled log-likelihood estimate over R = K (or n_modalities * K) samples
+ * (compute_joint_nll / compute_cond_nll: base_ae_model.py:396-442, mmvaePlus_model.py:478-533, mmvae_model.py:366-444,
+ * mopoe_model.py:468-595, mvae_model.py:241-317, mvtcae_model.py:214-289).  lw [R,B] f32, out [B] f32. */
+int mv_logmeanexp(const float* lw, int R, int B, float* out, void* stream);
+
+/* General Gaussian KL of base_utils.py:90-119, summed over the last dimension:
+ *   out[r] = sum_l 0.5 * (plv - lv + exp(lv - plv) + (mu - pm)^2 / exp(plv) - 1)
+ * mu, lv [rows, L]; prior_mu, prior_lv [prior_rows, L] with prior_rows = rows or 1 (broadcast).  The backward returns the
+ * gradients of all four inputs given g_out [rows] (g_prior_* may be NULL; for a broadcast prior they are summed over rows). */
+int mv_gauss_kl_fwd(const float* mu, const float* lv, const float* prior_mu, const float* prior_lv, float* out, int64_t rows, int L,
+                    int prior_rows, void* stream);
+int mv_gauss_kl_bwd(const float* mu, const float* lv, const float* prior_mu, const float* prior_lv, const float* g_out, float* g_mu,
+                    float* g_lv, float* g_prior_mu, float* g_prior_lv, int64_t rows, int L, int prior_rows, void* stream);
 
 /* Latent terms + importance weights + loss for one batch, and their unit gradients.
  * Replaces _compute_k_lws + _dreg_looser/_iwae_looser (mmvaePlus_model.py:230-363) and

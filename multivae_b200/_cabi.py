@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmultivae_b200.so")
 
 MV_F32, MV_BF16 = 0, 1
-DIST = {"normal": 0, "laplace": 1, "bernoulli": 2}
+DIST = {"normal": 0, "laplace": 1, "bernoulli": 2, "categorical": 3}
 LATENT = {"laplace_with_softmax": 0, "normal": 1, "normal_with_softplus": 1}
 LOSS = {"iwae_looser": 0, "dreg_looser": 1}
 ACT = {"none": 0, "relu": 1, "lrelu": 2, "sigmoid": 3}
@@ -65,6 +65,12 @@ _PROTOS = {
     "mv_moe_lpx_bwd_multi": [c_int, ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_void_p), c_void_p, c_void_p,
                              ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int, ctypes.POINTER(c_float),
                              ctypes.POINTER(c_float), ctypes.POINTER(c_void_p), c_void_p],
+    "mv_moe_lpx_cat_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p],
+    "mv_moe_lpx_cat_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                           c_void_p, c_void_p],
+    "mv_logmeanexp": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "mv_gauss_kl_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
+    "mv_gauss_kl_bwd": [c_void_p] * 9 + [c_int64, c_int, c_int, c_void_p],
     "mv_moe_lw_fwd": [c_void_p] * 21 + [c_int] * 7 + [c_float, c_int, c_void_p],
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],

@@ -408,20 +408,24 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
     }
     __syncwarp();
     // ---- softmax over k ------------------------------------------------------------------------
+    // The weights are normalised exactly (wk = e_k / sum e) and the DReG term is evaluated relative to the maximum,
+    // sum_k wk*lw = mx + sum_k wk*(lw - mx): with |lw| ~ 1e4 (D = 12288) the textbook form exp(lw - fl(logsumexp)) leaves
+    // sum_k wk = 1 +- 5e-4 (half an ulp of lse) and that error multiplies |lw|.
     float se = 0.f;
     for (int k = lane; k < K; k += 32) se += expf(lw[(int64_t(c) * K + k) * B + b] - mx);
     se = warp_sum(se);
+    const float inv_se = 1.f / se;
     const float lse = mx + logf(se);
-    float term = 0.f;  // sum_k wk*lw (DReG) or lse - log K (IWAE)
+    float term = 0.f;  // sum_k wk*(lw - mx) (DReG)
     for (int k = lane; k < K; k += 32) {
       const int64_t row = (int64_t(c) * K + k) * B + b;
       const float v = lw[row];
-      const float wgt = expf(v - lse);
+      const float wgt = expf(v - mx) * inv_se;
       wk[row] = wgt;
       coef[row] = avail[c] ? -wgt * inv_nm : 0.f;
-      term += wgt * v;
+      term += wgt * (v - mx);
     }
-    term = warp_sum(term);
+    term = mx + warp_sum(term);
     if (loss_kind == MV_LOSS_IWAE) term = lse - logf(float(K));
     if (avail[c]) loss_acc += term;
     __syncwarp();

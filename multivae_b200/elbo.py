@@ -21,7 +21,32 @@ def _same_family(recons, xs, recon_meta):
     if not 2 <= len(recons) <= 8:
         return False
     d0, t0, f0 = xs[0][0].numel(), recons[0].dtype, recon_meta[0][0]
+    if f0 == C.DIST["categorical"]:
+        return False
     return all(x[0].numel() == d0 and r.dtype == t0 and m[0] == f0 for r, x, m in zip(recons, xs, recon_meta))
+
+
+def lpx_fwd(lib, r, x, lpx, Cn, K, B, dist, scale, rescale, mask_r, accumulate):
+    """One reconstructed modality: lpx[c,k,b] (+)= rescale * mask * sum_d log p(x[b,d] | recon[c,k,b,d])."""
+    D = x[0].numel()
+    if dist == C.DIST["categorical"]:
+        V = r.shape[-1]
+        C.check(lib.mv_moe_lpx_cat_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, D // V, V, rescale, C.ptr(mask_r),
+                                       1 if accumulate else 0, C.stream()), "mv_moe_lpx_cat_fwd")
+    else:
+        C.check(lib.mv_moe_lpx_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, D, dist, scale, rescale, C.ptr(mask_r),
+                                   1 if accumulate else 0, C.stream()), "mv_moe_lpx_fwd")
+
+
+def lpx_bwd(lib, r, x, coef, g_loss, g, Cn, K, B, dist, scale, rescale, mask_r):
+    D = x[0].numel()
+    if dist == C.DIST["categorical"]:
+        V = r.shape[-1]
+        C.check(lib.mv_moe_lpx_cat_bwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(coef), C.ptr(g_loss), C.ptr(g), Cn, K, B, D // V, V,
+                                       rescale, C.ptr(mask_r), C.stream()), "mv_moe_lpx_cat_bwd")
+    else:
+        C.check(lib.mv_moe_lpx_bwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(coef), C.ptr(g_loss), C.ptr(g), Cn, K, B, D, dist, scale,
+                                   rescale, C.ptr(mask_r), C.stream()), "mv_moe_lpx_bwd")
 
 
 class MoEElboFn(torch.autograd.Function):
@@ -62,8 +87,7 @@ class MoEElboFn(torch.autograd.Function):
             for i, (r, x) in enumerate(zip(recons, xs)):
                 dist, scale, rescale, mrow = meta["recon"][i]
                 mask_r = None if masks is None else masks[mrow]
-                C.check(lib.mv_moe_lpx_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, x[0].numel(), dist, scale,
-                                           rescale, C.ptr(mask_r), 1 if i > 0 else 0, C.stream()), "mv_moe_lpx_fwd")
+                lpx_fwd(lib, r, x, lpx, Cn, K, B, dist, scale, rescale, mask_r, i > 0)
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         lw, wk, coef, loss_b = f(Cn, K, B), f(Cn, K, B), f(Cn, K, B), f(B)
         g_u, g_mu_u, g_sig_u = f(Cn, K, B, L), f(Cn, B, L), f(Cn, B, L)
@@ -110,9 +134,7 @@ class MoEElboFn(torch.autograd.Function):
             x = meta["x"][i]
             g = torch.empty_like(r)
             mask_r = None if masks is None else masks[mrow]
-            C.check(lib.mv_moe_lpx_bwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(coef), C.ptr(g_loss), C.ptr(g), Cn, K,
-                                       B, x[0].numel(), dist, scale, rescale, C.ptr(mask_r), C.stream()),
-                    "mv_moe_lpx_bwd")
+            lpx_bwd(lib, r, x, coef, g_loss, g, Cn, K, B, dist, scale, rescale, mask_r)
             g_recons.append(g)
         s = g_loss
         det = meta["detach"]
@@ -206,8 +228,7 @@ class ReconNLLFn(torch.autograd.Function):
         B = recon.shape[0]
         D = recon[0].numel()
         lp = torch.empty(B, device=recon.device, dtype=torch.float32)
-        C.check(lib.mv_moe_lpx_fwd(C.ptr(recon), C.dtype_code(recon), C.ptr(x), C.ptr(lp), 1, 1, B, D, dist, scale,
-                                   rescale, C.ptr(mask), 0, C.stream()), "mv_moe_lpx_fwd")
+        lpx_fwd(lib, recon, x, lp, 1, 1, B, dist, scale, rescale, mask, False)
         ctx.save_for_backward(recon, x, mask if mask is not None else torch.empty(0, device=recon.device))
         ctx.args = (dist, scale, rescale, mask is not None)
         return -lp
@@ -221,7 +242,79 @@ class ReconNLLFn(torch.autograd.Function):
         coef = (-g).float().contiguous()  # d(-lp)/d lp = -1, times upstream
         one = torch.ones(1, device=recon.device, dtype=torch.float32)
         gr = torch.empty_like(recon)
-        C.check(lib.mv_moe_lpx_bwd(C.ptr(recon), C.dtype_code(recon), C.ptr(x), C.ptr(coef), C.ptr(one), C.ptr(gr), 1, 1,
-                                   B, D, dist, scale, rescale, C.ptr(mask) if has_mask else None, C.stream()),
-                "mv_moe_lpx_bwd")
+        lpx_bwd(lib, recon, x, coef, one, gr, 1, 1, B, dist, scale, rescale, mask if has_mask else None)
         return gr, None, None, None, None, None
+
+
+class GaussKLFn(torch.autograd.Function):
+    """kl_divergence(mean, log_var, prior_mean, prior_log_var) of models/base/base_utils.py:90-119: the general Gaussian KL summed
+    over the last dimension (mv_gauss_kl_fwd / mv_gauss_kl_bwd); the prior is per sample or one broadcast row."""
+
+    @staticmethod
+    def forward(ctx, mean, log_var, prior_mean, prior_log_var):
+        lib = C.lib()
+        L = mean.shape[-1]
+        mu, lv = _f32c(mean).reshape(-1, L), _f32c(log_var).reshape(-1, L)
+        pm = _f32c(prior_mean.expand_as(prior_log_var) if prior_mean.numel() < prior_log_var.numel() else prior_mean).reshape(-1, L)
+        pl = _f32c(prior_log_var.expand_as(prior_mean) if prior_log_var.numel() < prior_mean.numel() else prior_log_var).reshape(-1, L)
+        rows = mu.shape[0]
+        if pm.shape[0] not in (1, rows):
+            pm, pl = pm.expand(rows, L).contiguous(), pl.expand(rows, L).contiguous()
+        out = torch.empty(rows, device=mu.device, dtype=torch.float32)
+        C.check(lib.mv_gauss_kl_fwd(C.ptr(mu), C.ptr(lv), C.ptr(pm), C.ptr(pl), C.ptr(out), rows, L, pm.shape[0], C.stream()),
+                "mv_gauss_kl_fwd")
+        ctx.save_for_backward(mu, lv, pm, pl)
+        ctx.shapes = (mean.shape, log_var.shape, prior_mean.shape, prior_log_var.shape)
+        return out.reshape(mean.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = C.lib()
+        mu, lv, pm, pl = ctx.saved_tensors
+        rows, L = mu.shape
+        g = _f32c(g).reshape(-1)
+        g_mu, g_lv, g_pm, g_pl = torch.empty_like(mu), torch.empty_like(lv), torch.empty_like(pm), torch.empty_like(pl)
+        C.check(lib.mv_gauss_kl_bwd(C.ptr(mu), C.ptr(lv), C.ptr(pm), C.ptr(pl), C.ptr(g), C.ptr(g_mu), C.ptr(g_lv), C.ptr(g_pm),
+                                    C.ptr(g_pl), rows, L, pm.shape[0], C.stream()), "mv_gauss_kl_bwd")
+        s = ctx.shapes
+        red = lambda t, shp: t.reshape(*([1] * (len(s[0]) - 1)), L).sum_to_size(shp) if t.shape[0] == 1 else t.reshape(s[0]).sum_to_size(shp)  # noqa: E731
+        return g_mu.reshape(s[0]), g_lv.reshape(s[1]), red(g_pm, s[2]), red(g_pl, s[3])
+
+
+def kl_divergence(mean, log_var, prior_mean, prior_log_var):
+    """base_utils.py:90-119."""
+    return GaussKLFn.apply(mean, log_var, prior_mean, prior_log_var)
+
+
+def logmeanexp(lw):
+    """lw (R, B) -> (B,): logsumexp over the R importance samples - log R (mv_logmeanexp)."""
+    lw = _f32c(lw)
+    R, B = lw.shape
+    out = torch.empty(B, device=lw.device, dtype=torch.float32)
+    C.check(C.lib().mv_logmeanexp(C.ptr(lw), R, B, C.ptr(out), C.stream()), "mv_logmeanexp")
+    return out
+
+
+def poe_joint(mu, lv, masks, bits, prior_mode, stable, eps=1e-8):
+    """Parameters (joint_mu, joint_lv), each (B, L), of the product of the experts in ONE subset (bitmask tensor `bits` of one
+    element): the forward kernel of the PoE family run for its joint_mu / joint_lv outputs only (inference paths: encode,
+    compute_joint_nll).  mu, lv (M, B, L); masks (M, B) uint8 or None."""
+    lib = C.lib()
+    mu, lv = _f32c(mu), _f32c(lv)
+    M, B, L = mu.shape
+    jm = torch.empty(B, L, device=mu.device, dtype=torch.float32)
+    jl = torch.empty_like(jm)
+    kl = torch.empty(B, device=mu.device, dtype=torch.float32)
+    C.check(lib.mv_poe_fwd(C.ptr(mu), C.ptr(lv), C.ptr(masks), C.ptr(bits), 1, None, None, 1.0, None, prior_mode,
+                           1 if stable else 0, float(eps), None, C.ptr(jm), C.ptr(jl), C.ptr(kl), None, M, B, L, C.stream()),
+            "mv_poe_fwd")
+    return jm, jl
+
+
+LOG_SQRT_2PI = 0.5 * math.log(2 * math.pi)
+
+
+def normal_logpdf_sum(z, mu, log_var):
+    """sum_l log N(z; mu, exp(log_var)) over the last dimension, torch.distributions.Normal.log_prob's formula."""
+    var = torch.exp(log_var)
+    return (-((z - mu) ** 2) / (2 * var) - 0.5 * log_var - LOG_SQRT_2PI).sum(-1)

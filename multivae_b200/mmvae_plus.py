@@ -4,6 +4,9 @@ forward(inputs, **kwargs) -> ModelOutput(loss, loss_sum, metrics={}).  Differenc
 the M*M decoder invocations of the reference are batched into one call per decoder over the M*K*B rows
 of all conditioning modalities, and _compute_k_lws + the IWAE/DReG looser are three fused CUDA kernels
 (multivae_b200/csrc/elbo_moe.cu) instead of ~10^4 ATen calls."""
+import math
+
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -73,9 +76,17 @@ class MMVAEPlus(BaseMultiVAE):
         if self.objective not in C.LOSS:
             raise NotImplementedError()
         inputs = drop_unused_modalities(inputs)
-        kind = self.model_config.prior_and_posterior_dist
+        self._unused_modalities = [m for m in self.encoders if m not in inputs.data]   # their parameters get NO gradient this step
         K = kwargs.pop("K", self.model_config.K)
-        detach = self.objective == "dreg_looser"
+        loss, meta = self._elbo(inputs, K, self.objective)
+        self._last = meta
+        return ModelOutput(loss=loss, loss_sum=loss, metrics=dict())
+
+    def _elbo(self, inputs, K, loss_name, rescale=None, beta=None):
+        """Encoders, reparameterised samples, one batched decoder call per reconstructed modality over the C*K*B rows, fused
+        lpx / lw kernels.  Returns (loss, meta with lw / wk / lpx).  rescale / beta override the model's (likelihood estimation)."""
+        kind = self.model_config.prior_and_posterior_dist
+        detach = loss_name == "dreg_looser"
         mods = list(inputs.data.keys())
         dev = inputs.data[mods[0]].device
         B = len(inputs.data[mods[0]])
@@ -107,14 +118,17 @@ class MMVAEPlus(BaseMultiVAE):
             wz = torch.stack([W[i] if c == r else w_cross[(c, r)] for i, c in enumerate(mods)])
             z = torch.cat([U, wz], dim=-1)
             with self._nn_ctx():
-                rec = self.decoders[r](z.reshape(-1, z.shape[-1]))["reconstruction"]
+                rec = self._logits(self.decoders[r](z.reshape(-1, z.shape[-1]))["reconstruction"])
             recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
 
         pz_std = log_var_to_std(self.logvars_priors["shared"], kind).reshape(-1)
-        meta = dict(x=[inputs.data[r].float().contiguous() for r in mods],
+        rmeta = self._recon_meta(mods, mods)
+        if rescale is not None:
+            rmeta = [(d, sc, float(rescale), row) for d, sc, _, row in rmeta]
+        meta = dict(x=[self._target(inputs, r, rec) for r, rec in zip(mods, recons)],
                     pz_mean=self.mean_priors["shared"].detach().reshape(-1).float().contiguous(),
-                    masks=self._stack_masks(inputs, mods), recon=self._recon_meta(mods, mods),
-                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[self.objective], beta=self.beta, detach=detach)
+                    masks=self._stack_masks(inputs, mods), recon=rmeta,
+                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=self.beta if beta is None else beta, detach=detach)
         loss = MoEElboFn.apply(meta, U, W, torch.stack(mu_u), torch.stack(sig_u), torch.stack(mu_w),
                                torch.stack(sig_w), pz_std, *recons)
         if detach:
@@ -123,5 +137,109 @@ class MMVAEPlus(BaseMultiVAE):
             if U.requires_grad:
                 U.register_hook(lambda g: g * wk)
                 W.register_hook(lambda g: g * wk)
-        self._last = meta
-        return ModelOutput(loss=loss, loss_sum=loss, metrics=dict())
+        return loss, meta
+
+    # ---- inference (mmvaePlus_model.py:365-533) ---------------------------------------------------------------------------
+    @property
+    def post_dist(self):
+        import torch.distributions as td
+        return td.Laplace if self.model_config.prior_and_posterior_dist == "laplace_with_softmax" else td.Normal
+
+    prior_dist = post_dist
+
+    def _log_var_to_std(self, log_var):
+        return log_var_to_std(log_var, self.model_config.prior_and_posterior_dist)
+
+    def _style_prior(self, m, batch_size):
+        """Prior parameters of modality m's private code for cross-modal generation (:424-437)."""
+        if self.reconstruction_option == "single_prior":
+            mu_m, lv_m = self.mean_priors[m], self.logvars_priors[m]
+        else:   # joint_prior
+            mu_m = self.mean_priors["shared"][:, self.latent_dim:]
+            lv_m = self.logvars_priors["shared"][:, self.latent_dim:]
+        return torch.cat([mu_m] * batch_size, dim=0), torch.cat([lv_m] * batch_size, dim=0)
+
+    def encode(self, inputs, cond_mod="all", N=1, return_mean=False, **kwargs):
+        """Shared code from ONE conditioning modality chosen at random (numpy, like the reference) or the mean of the posterior
+        means; private codes from the posteriors of the conditioning modalities and from the priors for the others."""
+        batch_size = len(list(inputs.data.values())[0])
+        cond_mod = super().encode(inputs, cond_mod, N, **kwargs).cond_mod
+        with self._nn_ctx():
+            outs = {m: self.encoders[m](inputs.data[m]) for m in cond_mod}
+        dev = outs[cond_mod[0]].embedding.device
+        sample = (lambda mu, sg: mu + sg * self._noise(tuple(mu.shape) if N == 1 else (N,) + tuple(mu.shape), dev))
+        if return_mean:
+            emb = torch.stack([o.embedding.float() for o in outs.values()]).mean(0)
+            z = torch.stack([emb] * N) if N > 1 else emb
+        else:
+            rm = np.random.choice(cond_mod)
+            z = sample(outs[rm].embedding.float(), self._log_var_to_std(outs[rm].log_covariance.float()))
+        flatten = kwargs.pop("flatten", False)
+        if flatten:
+            z = z.reshape(-1, self.latent_dim)
+        style_z = {}
+        for m in self.encoders:
+            if m not in cond_mod:
+                mu_m, lv_m = self._style_prior(m, batch_size)
+            else:
+                mu_m, lv_m = outs[m].style_embedding.float(), outs[m].style_log_covariance.float()
+            if return_mean:
+                style_z[m] = torch.stack([mu_m] * N) if N > 1 else mu_m
+            else:
+                style_z[m] = sample(mu_m, self._log_var_to_std(lv_m))
+            if flatten:
+                style_z[m] = style_z[m].reshape(-1, self.modalities_specific_dim)
+        return ModelOutput(z=z, one_latent_space=False, modalities_z=style_z)
+
+    def _encode_many(self, inputs, cond_mod, n):
+        """n independent encode() calls (own random conditioning modality each, same numpy stream) in one pass."""
+        batch_size = len(list(inputs.data.values())[0])
+        cond_mod = BaseMultiVAE.encode(self, inputs, cond_mod, 1).cond_mod
+        with self._nn_ctx():
+            outs = {m: self.encoders[m](inputs.data[m]) for m in cond_mod}
+        dev = outs[cond_mod[0]].embedding.device
+        picks = [np.random.choice(cond_mod) for _ in range(n)]
+        mu = torch.stack([outs[m].embedding.float() for m in picks])
+        sg = torch.stack([self._log_var_to_std(outs[m].log_covariance.float()) for m in picks])
+        z = mu + sg * self._noise(tuple(mu.shape), dev)
+        style_z = {}
+        for m in self.encoders:
+            mu_m, lv_m = (self._style_prior(m, batch_size) if m not in cond_mod
+                          else (outs[m].style_embedding.float(), outs[m].style_log_covariance.float()))
+            style_z[m] = mu_m + self._log_var_to_std(lv_m) * self._noise((n,) + tuple(mu_m.shape), dev)
+        return ModelOutput(z=z, one_latent_space=False, modalities_z=style_z)
+
+    def generate_from_prior(self, n_samples, **kwargs):
+        kind = self.model_config.prior_and_posterior_dist
+        std = log_var_to_std(self.logvars_priors["shared"], kind)
+        shape = (n_samples,) + tuple(std.shape) if n_samples > 1 else tuple(std.shape)
+        z = self.mean_priors["shared"] + std * self._noise(shape, std.device)
+        return ModelOutput(z=z.squeeze(), one_latent_space=True)
+
+    @torch.no_grad()
+    def compute_joint_nll(self, inputs, K=1000, batch_size_K=100, reference_quirk=True):
+        """-sum_i ln p(x_i) from K // n_modalities importance samples per conditioning modality with rescale = beta = 1
+        (mmvaePlus_model.py:478-533), batched over datapoints and chunked over the samples.
+
+        reference_quirk: the reference measures the batch with `len(inputs.data.popitem()[1])` (:497), which REMOVES the last
+        modality from the batch before the estimate is computed: the estimate then uses the remaining modalities only (while
+        the mixture normaliser stays log n_modalities).  True reproduces those numbers (without mutating the caller's batch);
+        False computes the estimator over all modalities."""
+        from .containers import MultimodalBaseDataset
+        from .elbo import logmeanexp
+        self.eval()
+        if hasattr(inputs, "masks"):
+            raise AttributeError("The compute_joint_nll method is not yet implemented for incomplete datasets.")
+        mods = list(inputs.data.keys())
+        if reference_quirk:
+            mods = mods[:-1]
+        sub = MultimodalBaseDataset(data={m: inputs.data[m] for m in mods})
+        k_iwae = K // self.n_modalities
+        lws = []
+        for k0 in range(0, k_iwae, batch_size_K):
+            _, meta = self._elbo(sub, min(batch_size_K, k_iwae - k0), "iwae_looser", rescale=1.0, beta=1.0)
+            lws.append(meta["lw"])                                   # (C, n, B)
+        lw = torch.cat(lws, dim=1)
+        # the kernel normalises the mixture-of-experts density by the number of modalities PRESENT; the reference by n_modalities
+        lw = lw + (math.log(self.n_modalities) - math.log(len(mods)))
+        return -logmeanexp(lw.reshape(-1, lw.shape[-1])).sum()

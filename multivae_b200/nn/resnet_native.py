@@ -163,13 +163,35 @@ def _grad_mode():
     return {"0": "autograd", "nct": "nct"}.get(os.environ.get("MULTIVAE_B200_DIRECT_GRADS", "1"), "unpack")
 
 
+_DIRECT = [False]
+
+
+class direct_grads:
+    """Context manager the trainer wraps around `loss.backward()`: inside it the native stacks may add their weight gradients
+    straight into the parameters' `.grad` tensors (the trainer's flat all-reduce buffer) and hand `None` back to autograd.
+    Outside it (plain `loss.backward()`, `torch.autograd.grad`, gradient hooks, `backward(inputs=...)`) every gradient is
+    returned through autograd like any other Function."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.prev, _DIRECT[0] = _DIRECT[0], self.on
+
+    def __exit__(self, *a):
+        _DIRECT[0] = self.prev
+
+
 def _direct_targets(params):
-    """The parameters' own .grad tensors if ALL of them can be written in place (fp32, contiguous, allocated), else None."""
-    if _grad_mode() == "autograd" or torch.is_grad_enabled():
+    """The parameters' own .grad tensors if the trainer opted in (`direct_grads`) and ALL of them can be written in place
+    (require a gradient; fp32, contiguous, allocated), else None."""
+    if not _DIRECT[0] or _grad_mode() == "autograd" or torch.is_grad_enabled():
         return None
     tg = []
     for p in params:
         g = getattr(p, "grad", None)
+        if not p.requires_grad:
+            return None
         if g is None or g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous() or g.shape != p.shape:
             return None
         tg.append(g)

@@ -4,14 +4,14 @@
 
   * one process per GPU (`LOCAL_RANK`/`RANK`/`WORLD_SIZE` from the environment, like
     base_trainer_config.py:80-100); the batch is sharded by rank exactly like
-    `DistributedSampler(num_replicas, rank, shuffle=False)`; parameters are replicated;
+    `DistributedSampler(num_replicas, rank)` (its default shuffle=True: a new permutation every epoch); parameters are replicated;
   * gradients live in ONE flat fp32 buffer per model (every `p.grad` is a view into it), so the
     data-parallel exchange is one NCCL all-reduce (mean) over NVLink per step instead of DDP's 25 MB
     buckets (payloads are 6-89 MB, SURVEY 2.2) and `zero_grad` is one memset;
   * no per-step `torch.cuda.empty_cache()` and no per-step `.item()`: `loss_sum` is accumulated on
     the device and read back once per epoch (the NaN guard keeps the reference's `ArithmeticError`).
 
-Out of scope here (the reference's Python stays as is): callbacks, checkpoints, schedulers, eval/predict.
+Out of scope here (the reference's Python stays as is): callbacks, checkpoints, schedulers, image logging.
 """
 import os
 from dataclasses import dataclass, field
@@ -27,6 +27,7 @@ from .containers import DatasetOutput
 class BaseTrainerConfig:
     """The subset of base_trainer_config.py:10-152 the training step reads."""
     per_device_train_batch_size: int = 64
+    per_device_eval_batch_size: int = 64
     num_epochs: int = 100
     optimizer_cls: str = "Adam"
     optimizer_params: Optional[dict] = None
@@ -43,6 +44,9 @@ class BaseTrainerConfig:
     # batch shape has been seen `graph_warmup_steps` times — the step is ~10^3 kernel launches and host-bound otherwise
     use_cuda_graph: bool = False
     graph_warmup_steps: int = 3
+    # batch order: the reference builds DataLoader(shuffle=True) / DistributedSampler(shuffle=True) (base_trainer.py:199-210)
+    shuffle: bool = True
+    seed: int = 0
     beta_schedule: Optional[list] = field(default=None)
 
     def __post_init__(self):
@@ -57,12 +61,23 @@ class BaseTrainerConfig:
             raise AttributeError(f"Unable to import `{self.optimizer_cls}` optimizer from 'torch.optim'.")
 
 
-def shard_indices(n, world_size, rank):
-    """Indices of `DistributedSampler(dataset, num_replicas=world_size, rank=rank, shuffle=False,
-    drop_last=False)`: pad to a multiple of world_size by wrapping, then take rank::world_size."""
+def shard_indices(n, world_size, rank, shuffle=False, seed=0, epoch=0):
+    """Indices of `DistributedSampler(dataset, num_replicas=world_size, rank=rank, shuffle=shuffle, seed=seed,
+    drop_last=False)` after `set_epoch(epoch)`: a `randperm` from a generator seeded with seed + epoch (shuffle), padded to a
+    multiple of world_size by wrapping, then rank::world_size — torch/utils/data/distributed.py, what the reference's
+    trainer builds with the sampler's default shuffle=True (base_trainer.py:198-201)."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        idx = torch.randperm(n, generator=g).tolist()
+    else:
+        idx = list(range(n))
     total = (n + world_size - 1) // world_size * world_size
-    idx = list(range(n))
-    idx += idx[: total - n]
+    pad = total - n
+    if pad <= len(idx):
+        idx += idx[:pad]
+    else:
+        idx += (idx * ((pad + len(idx) - 1) // len(idx)))[:pad]
     return idx[rank:total:world_size]
 
 
@@ -118,6 +133,7 @@ class BaseTrainer:
         cfg = self.training_config
         self.model = model
         self.train_dataset = train_dataset
+        self.eval_dataset = eval_dataset
         self.world_size = max(cfg.world_size, 1)
         self.rank = max(cfg.rank, 0)
         self.local_rank = max(cfg.local_rank, 0)
@@ -163,19 +179,31 @@ class BaseTrainer:
             kw.setdefault("capturable", True)  # step counter on the device
         self.optimizer = cls([p for p in self.model.parameters() if p.requires_grad], lr=cfg.learning_rate, **kw)
 
-    def local_batches(self):
-        """This rank's batches of the dataset, in DistributedSampler order."""
-        n = len(self.train_dataset)
-        idx = shard_indices(n, self.world_size, self.rank) if self.distributed else list(range(n))
-        bs = self.training_config.per_device_train_batch_size
+    def _batches_of(self, dataset, idx, bs):
         for i in range(0, len(idx), bs):
             sel = idx[i:i + bs]
             contiguous = sel == list(range(sel[0], sel[0] + len(sel)))
             take = (lambda t: t[sel[0]:sel[0] + len(sel)]) if contiguous else (lambda t: t[torch.as_tensor(sel)])
-            out = DatasetOutput(data={m: take(t) for m, t in self.train_dataset.data.items()})
-            if hasattr(self.train_dataset, "masks"):
-                out["masks"] = {m: take(t) for m, t in self.train_dataset.masks.items()}
+            out = DatasetOutput(data={m: take(t) for m, t in dataset.data.items()})
+            if hasattr(dataset, "masks"):
+                out["masks"] = {m: take(t) for m, t in dataset.masks.items()}
             yield out
+
+    def local_eval_batches(self):
+        """This rank's batches of the evaluation set (base_trainer.py:212-219: no shuffling in a single process; the
+        DistributedSampler's default permutation of seed + 0 when distributed)."""
+        n = len(self.eval_dataset)
+        idx = (shard_indices(n, self.world_size, self.rank, shuffle=True, seed=0, epoch=0) if self.distributed else list(range(n)))
+        return self._batches_of(self.eval_dataset, idx, self.training_config.per_device_eval_batch_size)
+
+    def local_batches(self, epoch=0):
+        """This rank's batches of the dataset for `epoch`: a fresh permutation per epoch (single process: the DataLoader's
+        shuffle=True; distributed: the DistributedSampler permutation of seed + epoch, sharded rank::world)."""
+        n = len(self.train_dataset)
+        cfg = self.training_config
+        idx = shard_indices(n, self.world_size if self.distributed else 1, self.rank if self.distributed else 0,
+                            shuffle=cfg.shuffle, seed=cfg.seed, epoch=epoch)
+        return self._batches_of(self.train_dataset, idx, cfg.per_device_train_batch_size)
 
     def _to_device(self, inputs):
         mv = lambda t: t.to(self.device, non_blocking=True)  # noqa: E731
@@ -186,18 +214,31 @@ class BaseTrainer:
 
     # base_trainer.py:350-361
     def _optimizers_step(self, model_output):
+        from .nn import resnet_native as RN
         self.flat.zero()
-        model_output.loss.backward()
+        with RN.direct_grads(True):   # the native stacks may add their weight gradients straight into the flat buffer's views
+            model_output.loss.backward()
         self.flat.rebind()
         if self.distributed:
             self.flat.allreduce_mean()
+        # parameters that received NO gradient (modalities missing from the whole batch) must not move: the reference's
+        # zero_grad() leaves their .grad at None and the optimizer skips them (no stale-momentum / weight-decay update)
+        skipped = []
+        for m in getattr(self.model, "_unused_modalities", None) or ():
+            for mod in (self.model.encoders[m], self.model.decoders[m]):
+                for p in mod.parameters():
+                    if p.grad is not None:
+                        skipped.append(p)
+                        p.grad = None
         self.optimizer.step()
+        if skipped:
+            self.flat.rebind()
 
-    def _eager_step(self, inputs, epoch, batch_ratio):
+    def _eager_step(self, inputs, epoch, batch_ratio, **extra):
         sched = self.training_config.beta_schedule
         beta_epoch = sched[epoch - 1] if sched is not None else 1
         out = self.model(inputs, epoch=epoch, dataset_size=len(self.train_dataset), uses_ddp=self.distributed,
-                         batch_ratio=batch_ratio, beta=beta_epoch)
+                         batch_ratio=batch_ratio, beta=beta_epoch, **extra)
         self._optimizers_step(out)
         return out
 
@@ -211,17 +252,21 @@ class BaseTrainer:
     # ---- CUDA-graph replay of the step ------------------------------------------------------------
     def _graph_step(self, inputs, epoch, batch_ratio):
         """Eager for the first `graph_warmup_steps` occurrences of a batch signature, then capture once and replay.
-        The signature includes every Python scalar the models read per step (epoch, batch_ratio), so a model whose
-        arithmetic depends on them (MVAE's KL warm-up) is re-captured only when they change."""
+        Per-step Python scalars the models read (MVAE's KL warm-up weight) live in device scalars refreshed by
+        `model.prepare_step` outside the graph, so one capture serves every epoch; models whose step draws host-side
+        randomness (`graph_safe` False: MVAE with k random subsets) and incomplete batches (masks: data-dependent host
+        decisions) always run eagerly."""
         has_masks = hasattr(inputs, "masks")
-        sig = (tuple((m, tuple(t.shape), t.dtype) for m, t in inputs.data.items()), has_masks,
-               epoch if getattr(self.model, "step_depends_on_epoch", False) else None,
-               batch_ratio if getattr(self.model, "step_depends_on_epoch", False) else None)
+        if has_masks or not getattr(self.model, "graph_safe", True):
+            return self._eager_step(self._to_device(inputs), epoch, batch_ratio)
+        sig = tuple((m, tuple(t.shape), t.dtype) for m, t in inputs.data.items())
         st = self._graphs.setdefault(sig, {"seen": 0})
+        extra = {"beta_on_device": True} if hasattr(self.model, "_beta_dev") else {}
+        self.model.prepare_step(epoch, batch_ratio)
         if "graph" not in st:
-            if st["seen"] < self.training_config.graph_warmup_steps or has_masks:
+            if st["seen"] < self.training_config.graph_warmup_steps:
                 st["seen"] += 1
-                return self._eager_step(self._to_device(inputs), epoch, batch_ratio)
+                return self._eager_step(self._to_device(inputs), epoch, batch_ratio, **extra)
             static = DatasetOutput(data={m: torch.empty(t.shape, dtype=t.dtype, device=self.device)
                                          for m, t in inputs.data.items()})
             for m, t in inputs.data.items():
@@ -230,7 +275,7 @@ class BaseTrainer:
             torch.cuda.empty_cache()   # hand the eager pool's blocks to the graph's private pool
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self._eager_step(static, epoch, batch_ratio)
+                out = self._eager_step(static, epoch, batch_ratio, **extra)
             st.update(graph=graph, static=static, out=out)
         else:
             for m, t in inputs.data.items():
@@ -241,7 +286,7 @@ class BaseTrainer:
     # base_trainer.py:682-750
     def train_step(self, epoch):
         self.model.train()
-        batches = list(self.local_batches())
+        batches = list(self.local_batches(epoch))
         epoch_loss = torch.zeros((), device=self.device, dtype=torch.float64)
         metrics = {}
         for i, inputs in enumerate(batches):
@@ -257,3 +302,28 @@ class BaseTrainer:
         self.model.update()
         metrics = {k: float(v) / len(batches) for k, v in metrics.items()}
         return total / len(self.train_dataset), metrics
+
+    # base_trainer.py:618-680
+    def eval_step(self, epoch):
+        """Evaluation pass: `model(inputs, ..., use_mean_embedding=True)` under no_grad over the evaluation set; returns
+        (sum of loss_sum / len(eval_dataset), metrics averaged over batches) like the reference.  The loss is accumulated on the
+        device and read back once (the NaN guard keeps the reference's ArithmeticError)."""
+        if self.eval_dataset is None:
+            raise AttributeError("eval_step needs an eval_dataset")
+        self.model.eval()
+        batches = list(self.local_eval_batches())
+        epoch_loss = torch.zeros((), device=self.device, dtype=torch.float64)
+        metrics = {}
+        for inputs in batches:
+            with torch.no_grad():
+                out = self.model(self._to_device(inputs), epoch=epoch, dataset_size=len(self.eval_dataset),
+                                 uses_ddp=self.distributed, use_mean_embedding=True)
+            loss = out.loss_sum if hasattr(out, "loss_sum") else out.loss
+            epoch_loss += loss.detach().double()
+            for k, v in out.metrics.items():
+                v = v.detach().double() if torch.is_tensor(v) else torch.tensor(float(v), device=self.device, dtype=torch.float64)
+                metrics[k] = metrics.get(k, 0) + v
+        total = float(epoch_loss)
+        if total != total:
+            raise ArithmeticError("NaN detected in eval loss")
+        return total / len(self.eval_dataset), {k: float(v) / len(batches) for k, v in metrics.items()}

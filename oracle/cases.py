@@ -27,6 +27,11 @@ CASES = {
     "mopoe": dict(model="mopoe", dims=_DIMS3, B=9, cfg=dict(latent_dim=5, beta=2.5, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
     "mopoe_5mod": dict(model="mopoe", dims={f"m{i}": (2, 4, 4) for i in range(5)}, B=40, cfg=dict(latent_dim=6, beta=2.5, decoders_dist={f"m{i}": "laplace" for i in range(5)}, decoder_dist_params={f"m{i}": {"scale": 0.75} for i in range(5)})),
     "mopoe_masked": dict(model="mopoe", dims=_DIMS3, B=9, masks=True, cfg=dict(latent_dim=5, beta=1.0, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    # modality-specific latent spaces in MoPoE (mopoe_model.py:57-74,171-225) and a categorical decoder (base_utils.py:28-59)
+    "mopoe_private": dict(model="mopoe", dims=_DIMS3, B=9, cfg=dict(latent_dim=5, beta=2.5, beta_style=2.0, modalities_specific_dim={"m0": 3, "m1": 2, "m2": 4}, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "mopoe_private_masked": dict(model="mopoe", dims=_DIMS3, B=9, masks=True, cfg=dict(latent_dim=5, beta=1.0, beta_style=0.5, modalities_specific_dim={"m0": 3, "m1": 2, "m2": 4}, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "mvtcae_categorical": dict(model="mvtcae", dims={"m0": (3, 8, 8), "m1": (1, 6, 6), "m2": (4, 5)}, B=6, onehot=["m2"], cfg=dict(latent_dim=5, alpha=0.1, beta=2.5, decoders_dist={"m0": "laplace", "m1": "bernoulli", "m2": "categorical"}, decoder_dist_params={"m0": {"scale": 0.75}, "m1": {}, "m2": {}}, uses_likelihood_rescaling=True)),
+    "mmvaeplus_categorical": dict(model="mmvaeplus", dims={"m0": (3, 8, 8), "m2": (4, 5)}, B=5, onehot=["m2"], cfg=dict(K=3, latent_dim=5, modalities_specific_dim=3, beta=2.5, loss="dreg_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist={"m0": "laplace", "m2": "categorical"}, decoder_dist_params={"m0": {"scale": 0.75}, "m2": {}})),
     # ---- BASELINE.json configs at their real input shapes (default MLP architectures; every hyper-parameter written out — the values
     # are the reference configs' defaults / the example scripts' settings; small batches where the config's own is big)
     "cfg1_mvtcae_quickstart": dict(model="mvtcae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=32,
@@ -74,6 +79,10 @@ def make_data(spec):
     data = {}
     for i, (m, d) in enumerate(spec["dims"].items()):
         data[m] = torch.rand(spec["B"], *d, generator=torch.Generator().manual_seed(1000 + i))
+        if m in spec.get("onehot", ()):   # categorical targets: one-hot over the last dimension
+            data[m] = torch.nn.functional.one_hot(data[m].argmax(-1), d[-1]).float()
+        if spec["cfg"].get("decoders_dist", {}).get(m) == "bernoulli":
+            data[m] = (data[m] > 0.5).float()
     masks = None
     if spec.get("masks"):
         B = spec["B"]

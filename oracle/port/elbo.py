@@ -443,5 +443,7 @@ def mopoe_forward(enc, dec, data, noise, *, latent_dim, beta, dec_dist, dec_scal
             if masks is not None:
                 sk = sk * masks[m].float()
             kld = kld + sk.mean() * beta_style
+    # the reference adds the style KLs IN PLACE to the tensor it stored under "joint_divergence" (mopoe_model.py:166,222)
+    res["joint_divergence"] = kld
     loss = loss + beta * kld
     return loss, loss * B, res

@@ -45,7 +45,7 @@ def default_nets(spec, p, dtype=torch.float32):
             else:
                 raise ValueError(a)
         return enc, dec
-    if spec["model"] == "mmvaeplus":
+    if spec["model"] == "mmvaeplus" or spec["cfg"].get("modalities_specific_dim") is not None:
         enc = {m: (lambda x, m=m: N.encoder_vae_mlp_style(p, f"encoders.{m}.", x)) for m in mods}
     else:
         enc = {m: (lambda x, m=m: N.encoder_vae_mlp(p, f"encoders.{m}.", x)) for m in mods}
@@ -72,6 +72,8 @@ def split_noise(spec, noise, mods_active=None):
         return {"z": {c: next(it) for c in mods}}
     if model == "mvae":
         return {"z": list(noise)}
+    if model == "mopoe" and spec["cfg"].get("modalities_specific_dim") is not None:
+        return {"z": next(it), "style": {m: next(it) for m in spec["dims"]}}   # shared, then one style draw per modality
     return {"z": next(it)}
 
 
@@ -125,7 +127,8 @@ def run_port(spec, rec, dtype=torch.float32, want_grads=True, details=None):
     elif model == "mopoe":
         loss, loss_sum, metrics = E.mopoe_forward(enc, dec, data, noise, latent_dim=cfg["latent_dim"], beta=cfg["beta"],
                                                   dec_dist=dd, dec_scale=ds, rescale=rs, masks=masks,
-                                                  choice=rec.get("choice"))
+                                                  choice=rec.get("choice"), style=cfg.get("modalities_specific_dim") is not None,
+                                                  beta_style=cfg.get("beta_style", 1.0))
     else:
         raise ValueError(model)
     if want_grads:

@@ -16,6 +16,15 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     has_ref = os.path.isdir("/root/reference/src")
     skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    has_lib = os.path.exists(os.path.join(ROOT, "multivae_b200", "libmultivae_b200.so"))
+    skip_gpu = pytest.mark.skip(reason="needs a CUDA device and the built libmultivae_b200.so (run on the B200 box with -m gpu)")
     for item in items:
         if "reference" in item.keywords and not has_ref:
             item.add_marker(skip_ref)
+        if "gpu" in item.keywords and not (has_gpu and has_lib):
+            item.add_marker(skip_gpu)

@@ -62,6 +62,9 @@ def run_product(name, device="cuda", compute_dtype=None):
     model = build_model(spec, rec, device)
     if compute_dtype is not None:
         model.compute_dtype = compute_dtype
+    # the fp32 comparison runs the library layers in true fp32 (cuDNN / cuBLAS default to TF32 convolutions)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     data, masks = make_data(spec)
     data = {k: v.to(device) for k, v in data.items()}
     q = [e.to(device) for e in rec["noise"]]
@@ -173,5 +176,5 @@ def smoke_check():
 
 
 # bounds of the bf16 tensor-core path on the north-star golden = 3x what was measured on B200
-NS_BF16_LOSS_TOL = 2e-3
-NS_BF16_GRAD_L2_TOL = 6e-2
+NS_BF16_LOSS_TOL = 5e-6      # measured 8.2e-7
+NS_BF16_GRAD_L2_TOL = 3e-2   # measured 9.3e-3 (relative L2 over all parameter gradients; worst single tensor 0.11 of its max)

@@ -105,3 +105,64 @@ def test_lpx_batched_launch_equals_per_modality_launches(dist, D, dtype):
     assert float((lpx - lpx_ref).abs().max()) <= 1e-5 * float(lpx_ref.abs().max())
     for a, b in zip(g_out, g_ref):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("P,V", [(4, 5), (1, 40), (7, 100)])
+def test_categorical_lpx_kernels_vs_torch(P, V, dtype):
+    """mv_moe_lpx_cat_fwd / bwd against target * log_softmax(input + 1e-6) (base_utils.py:28-39)."""
+    import torch.nn.functional as F
+    from multivae_b200 import _cabi as C
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Cn, K, B = 2, 3, 5
+    recon = (torch.randn(Cn, K, B, P, V, device="cuda", generator=g) * 2).to(dtype)
+    x = F.one_hot(torch.randint(0, V, (B, P), device="cuda", generator=g), V).float()
+    mask = torch.tensor([1, 1, 0, 1, 1], dtype=torch.uint8, device="cuda")
+    lpx = torch.empty(Cn, K, B, device="cuda")
+    lib = C.lib()
+    C.check(lib.mv_moe_lpx_cat_fwd(C.ptr(recon), C.dtype_code(recon), C.ptr(x), C.ptr(lpx), Cn, K, B, P, V, 1.3, C.ptr(mask), 0, C.stream()), "f")
+    r32 = recon.float().requires_grad_(True)
+    ref = (x * F.log_softmax(r32 + 1e-6, dim=-1)).mul(1.3).sum((-1, -2)) * mask.float()
+    assert torch.allclose(lpx, ref, rtol=2e-5, atol=1e-4), float((lpx - ref).abs().max())
+    coef = torch.randn(Cn, K, B, device="cuda", generator=g)
+    gl = torch.tensor([0.7], device="cuda")
+    gr = torch.empty_like(recon)
+    C.check(lib.mv_moe_lpx_cat_bwd(C.ptr(recon), C.dtype_code(recon), C.ptr(x), C.ptr(coef), C.ptr(gl), C.ptr(gr), Cn, K, B, P, V, 1.3, C.ptr(mask), C.stream()), "b")
+    (ref * coef).sum().mul(0.7).backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert torch.allclose(gr.float(), r32.grad, rtol=tol, atol=tol * float(r32.grad.abs().max()))
+
+
+def test_logmeanexp_and_gauss_kl_kernels_vs_torch():
+    import math
+    from multivae_b200.elbo import kl_divergence, logmeanexp
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lw = torch.randn(1000, 37, device="cuda", generator=g) * 50 - 12000
+    ref = torch.logsumexp(lw.double(), 0) - math.log(1000)
+    assert torch.allclose(logmeanexp(lw).double(), ref, rtol=1e-6, atol=1e-3)
+    for prior_shape in [(1, 16), (9, 16)]:
+        mu, lv = [torch.randn(9, 16, device="cuda", generator=g).requires_grad_(True) for _ in range(2)]
+        pm, pl = [torch.randn(*prior_shape, device="cuda", generator=g).requires_grad_(True) for _ in range(2)]
+        kl = kl_divergence(mu, lv, pm, pl)
+        ref = (0.5 * (pl - lv + torch.exp(lv - pl) + (mu - pm) ** 2 / torch.exp(pl) - 1)).sum(-1)
+        assert torch.allclose(kl, ref, rtol=1e-5, atol=1e-5)
+        w = torch.randn(9, device="cuda", generator=g)
+        got = torch.autograd.grad((kl * w).sum(), [mu, lv, pm, pl])
+        want = torch.autograd.grad((ref * w).sum(), [mu, lv, pm, pl])
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_stable_poe_survives_extreme_log_variances():
+    """stable_poe (base_utils.py:133-147) is a logsumexp: log-variances far outside exp()'s fp32 range must neither overflow
+    nor underflow the product (MVAE path, prior expert always)."""
+    from multivae_b200.elbo import poe_joint
+    mu = torch.tensor([[[1.0, 2.0, -1.0]], [[3.0, -2.0, 0.5]]], device="cuda")           # (M=2, B=1, L=3)
+    lv = torch.tensor([[[-200.0, 150.0, 0.0]], [[-190.0, 160.0, 0.0]]], device="cuda")
+    bits = torch.tensor([3], dtype=torch.int32, device="cuda")
+    jm, jl = poe_joint(mu, lv, None, bits, 1, True, 0.0)
+    lv64, mu64 = torch.cat([lv.double(), torch.zeros(1, 1, 3, dtype=torch.float64, device="cuda")]), torch.cat([mu.double(), torch.zeros(1, 1, 3, dtype=torch.float64, device="cuda")])
+    ref_lv = -torch.logsumexp(-lv64, 0)
+    ref_mu = (torch.softmax(-lv64, 0) * mu64).sum(0)
+    assert torch.isfinite(jm).all() and torch.isfinite(jl).all()
+    assert torch.allclose(jl.double(), ref_lv, rtol=1e-6, atol=1e-6) and torch.allclose(jm.double(), ref_mu, rtol=1e-5, atol=1e-6)

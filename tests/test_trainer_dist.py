@@ -45,6 +45,11 @@ def test_shard_indices_match_distributed_sampler():
         for r in range(w):
             ref = list(DistributedSampler(ds, num_replicas=w, rank=r, shuffle=False))
             assert shard_indices(n, w, r) == ref
+            # the reference's trainer keeps the sampler's default shuffle=True: same permutation per (seed, epoch)
+            for epoch in (0, 3):
+                smp = DistributedSampler(ds, num_replicas=w, rank=r, shuffle=True, seed=5)
+                smp.set_epoch(epoch)
+                assert shard_indices(n, w, r, shuffle=True, seed=5, epoch=epoch) == list(smp)
 
 
 def test_flat_grads_are_views_and_survive_backward():
@@ -107,7 +112,10 @@ def test_two_rank_gradient_average_matches_manual():
     (_, g0, w0, x0, _), (_, g1, w1, x1, _) = [tuple(torch.tensor(v) if isinstance(v, list) else v for v in r) for r in res]
     assert torch.equal(g0, g1) and torch.equal(w0, w1)          # replicas stay identical
     ds = _dataset(16)
-    assert torch.equal(x0, ds.data["a"][0::2]) and torch.equal(x1, ds.data["a"][1::2])   # DistributedSampler shards
+    from torch.utils.data import DistributedSampler
+    for r, x in ((0, x0), (1, x1)):   # DistributedSampler shards (shuffle=True, seed 0, epoch 0), first batch of 8
+        idx = list(DistributedSampler(list(range(16)), num_replicas=2, rank=r, shuffle=True, seed=0))[:8]
+        assert torch.equal(x, ds.data["a"][torch.tensor(idx)])
     # manual DDP semantics: mean over ranks of each rank's own loss gradient
     m = TinyModel()
     gs = []
