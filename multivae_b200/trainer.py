@@ -263,10 +263,21 @@ class BaseTrainer:
         st = self._graphs.setdefault(sig, {"seen": 0})
         extra = {"beta_on_device": True} if hasattr(self.model, "_beta_dev") else {}
         self.model.prepare_step(epoch, batch_ratio)
+        # Warm-up and capture both run on ONE side stream: autograd binds each parameter's AccumulateGrad node to the stream of
+        # the first backward that uses it, and a node bound to the default stream makes the captured backward synchronise with
+        # the (non-capturing) default stream, which invalidates the capture.
+        if getattr(self, "_graph_stream", None) is None:
+            self._graph_stream = torch.cuda.Stream(device=self.device)
+        side = self._graph_stream
         if "graph" not in st:
             if st["seen"] < self.training_config.graph_warmup_steps:
                 st["seen"] += 1
-                return self._eager_step(self._to_device(inputs), epoch, batch_ratio, **extra)
+                dev_inputs = self._to_device(inputs)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    out = self._eager_step(dev_inputs, epoch, batch_ratio, **extra)
+                torch.cuda.current_stream().wait_stream(side)
+                return out
             static = DatasetOutput(data={m: torch.empty(t.shape, dtype=t.dtype, device=self.device)
                                          for m, t in inputs.data.items()})
             for m, t in inputs.data.items():
@@ -274,7 +285,7 @@ class BaseTrainer:
             torch.cuda.synchronize()
             torch.cuda.empty_cache()   # hand the eager pool's blocks to the graph's private pool
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):
                 out = self._eager_step(static, epoch, batch_ratio, **extra)
             st.update(graph=graph, static=static, out=out)
         else:
