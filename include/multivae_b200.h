@@ -198,6 +198,44 @@ typedef struct mv_tapgemm_args {
 } mv_tapgemm_args;
 int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * General tensor-core GEMM of the fully connected layers (tcgen05 + TMA, bf16 operands, fp32 accumulate):
+ *
+ *   out[m, n] (+)= epilogue( alpha * sum_k A(m, k) * B(n, k) )
+ *
+ * A is stored [M][K] (a_mn = 0, "K-major") or [K][M] (a_mn = 1, "MN-major"); B is stored [N][K] (b_mn = 0) or [K][N] (b_mn = 1);
+ * a_ld / b_ld are the row pitches in elements (multiples of 8), base pointers 16-byte aligned.  No padding of M, N, K is needed
+ * (out-of-range elements are zero-filled by TMA).  One entry point covers the three products of a Linear layer
+ * (models/nn/default_architectures.py:21-130,225-258; nn.Linear of mmnist.py:98,181,289-295,339 and autograd's addmm backward):
+ *   forward         Y = X W^T + b      A = X  [B][K],  B = W [N][K]
+ *   data gradient   dX = dY W          A = dY [B][N],  B = W [N][K] with b_mn = 1 (the reduction runs over W's rows)
+ *   weight gradient dW += dY^T X       A = dY [B][N] with a_mn = 1,  B = X [B][K] with b_mn = 1,  out_kind = MV_OUT_F32_ADD
+ * epilogue (MV_OUT_BF16 / MV_OUT_F32):  y = act(alpha * acc + bias[n]);  if dact: y *= (dact[m, n] > 0 ? 1 : dslope)
+ *   (dact = the saved OUTPUT of the ReLU / LeakyReLU that produced this layer's input: the activation derivative of the
+ *   layer below fused into the data-gradient GEMM).  MV_OUT_F32_ADD adds alpha * acc (+ bias) into fp32 `out` with vector
+ *   reductions and splits the reduction over CTAs when the output has fewer tiles than the GPU has SMs.
+ * ------------------------------------------------------------------------------------------- */
+#define MV_OUT_BF16 0
+#define MV_OUT_F32 1
+#define MV_OUT_F32_ADD 2
+typedef struct mv_gemm_args {
+  const void* A; int64_t M; int32_t a_ld, a_mn;
+  const void* B; int32_t N, b_ld, b_mn;
+  int32_t K;
+  const float* bias;    /* [N] or NULL */
+  int32_t act;          /* MV_ACT_* */
+  float alpha;
+  const void* dact; int32_t dact_ld; float dslope;   /* bf16 [M][dact_ld] or NULL */
+  void* out; int32_t out_ld, out_kind;               /* bf16 or fp32 [M][out_ld] */
+} mv_gemm_args;
+int mv_gemm(const mv_gemm_args* args, void* stream);
+/* out[n] += sum_p G[p, n] for any N % 8 == 0 (bias gradients of the fully connected layers; G bf16 [P][ld], out fp32) */
+int mv_colsum_any(const void* G, int64_t P, int ld, int N, float* out, void* stream);
+/* out = g * act'(.) elementwise over n elements (n % 8 == 0): the derivative is taken from the SAVED OUTPUT y of the activation
+ * (Sigmoid: y (1 - y); ReLU / LeakyReLU: y > 0 ? 1 : slope); g fp32 or bf16 (MV_F32 / MV_BF16), y and out bf16.
+ * Replaces autograd's sigmoid_backward / threshold_backward in front of the gradient GEMMs of a layer. */
+int mv_act_bwd(const void* g, int g_dtype, const void* y, void* out, int64_t n, int act, float slope, void* stream);
+
 /* Weight gradient of a tap-GEMM layer:  dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]   (fp32, accumulating).
  * Replaces the weight-gradient half of autograd's convolution_backward / addmm backward for the layers above
  * (the reference reaches it through loss.backward(), trainers/base/base_trainer.py:359).

@@ -41,6 +41,15 @@ class TapGemmArgs(ctypes.Structure):
     ]
 
 
+class GemmArgs(ctypes.Structure):
+    """mv_gemm_args of include/multivae_b200.h."""
+    _fields_ = [("A", c_void_p), ("M", c_int64), ("a_ld", ctypes.c_int32), ("a_mn", ctypes.c_int32),
+                ("B", c_void_p), ("N", ctypes.c_int32), ("b_ld", ctypes.c_int32), ("b_mn", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("bias", c_void_p), ("act", ctypes.c_int32), ("alpha", c_float),
+                ("dact", c_void_p), ("dact_ld", ctypes.c_int32), ("dslope", c_float),
+                ("out", c_void_p), ("out_ld", ctypes.c_int32), ("out_kind", ctypes.c_int32)]
+
+
 class PackItem(ctypes.Structure):
     """mv_pack_item of include/multivae_b200.h."""
     _fields_ = [("src", c_void_p), ("dst_fwd", c_void_p), ("dst_dgrad", c_void_p), ("N", ctypes.c_int32), ("C", ctypes.c_int32),
@@ -75,6 +84,9 @@ _PROTOS = {
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "mv_tapgemm": [ctypes.POINTER(TapGemmArgs), c_void_p],
+    "mv_gemm": [ctypes.POINTER(GemmArgs), c_void_p],
+    "mv_colsum_any": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
+    "mv_act_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p],
     "mv_upsample2x_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "mv_upsample2x_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
     "mv_head_grad_pack": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],

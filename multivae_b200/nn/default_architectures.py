@@ -1,15 +1,24 @@
 """Default MLP architectures (reference: models/nn/default_architectures.py:21-258).
 
 Parameter names: `layers.<i>.0.{weight,bias}`, `embedding`, `log_var`, `style_embedding`,
-`style_log_var`.  The linear algebra runs through multivae_b200.nn.functional (tcgen05 GEMM with
-fused bias+activation epilogue on sm_100a)."""
+`style_log_var`.  On CUDA with bf16 compute the whole stack runs as ONE autograd Function over the native tcgen05 GEMM
+(nn/linear_native.py: bias + ReLU / Sigmoid fused in the epilogue, native weight / data gradients); the fp32 path (and CPU
+construction / state-dict handling) uses the library layers of nn/functional.py."""
 import numpy as np
+import torch
 import torch.nn as nn
 
 from ..configs import BaseAEConfig
 from ..containers import ModelOutput
 from . import functional as NF
 from .base_architectures import BaseDecoder, BaseEncoder
+
+
+def _native(x):
+    """Native tensor-core path: CUDA tensor and bf16 compute (autocast active, set by the model's compute_dtype) or forced."""
+    if not x.is_cuda or NF.backend() == "torch":
+        return False
+    return NF.backend() == "native" or torch.is_autocast_enabled()
 
 
 def _hidden(n_in, n_out):
@@ -28,6 +37,11 @@ class Encoder_VAE_MLP(BaseEncoder):
 
     def forward(self, x, output_layer_levels=None):
         h = x.reshape(-1, int(np.prod(self.input_dim)))
+        if _native(h):
+            from .linear_native import mlp_chain
+            out = mlp_chain(h, [l[0] for l in self.layers] + [[self.embedding, self.log_var]], ["relu"] * self.depth + ["none"], out_fp32=True)
+            mu, lv = torch.split(out, [self.latent_dim, self.latent_dim], dim=-1)
+            return ModelOutput(embedding=mu, log_covariance=lv)
         for layer in self.layers:
             h = NF.linear(h, layer[0].weight, layer[0].bias, act="relu")
         mu, lv = NF.linear_heads(h, [self.embedding, self.log_var])
@@ -49,6 +63,12 @@ class Encoder_VAE_MLP_Style(BaseEncoder):
 
     def forward(self, x, output_layer_levels=None):
         h = x.reshape(-1, int(np.prod(self.input_dim)))
+        if _native(h):
+            from .linear_native import mlp_chain
+            heads = [self.embedding, self.log_var, self.style_embedding, self.style_log_var]
+            out = mlp_chain(h, [self.layers[0][0], heads], ["relu", "none"], out_fp32=True)
+            mu, lv, smu, slv = torch.split(out, [hd.weight.shape[0] for hd in heads], dim=-1)
+            return ModelOutput(embedding=mu, log_covariance=lv, style_embedding=smu, style_log_covariance=slv)
         h = NF.linear(h, self.layers[0][0].weight, self.layers[0][0].bias, act="relu")
         mu, lv, smu, slv = NF.linear_heads(h, [self.embedding, self.log_var, self.style_embedding, self.style_log_var])
         return ModelOutput(embedding=mu, log_covariance=lv, style_embedding=smu, style_log_covariance=slv)
@@ -65,6 +85,10 @@ class Decoder_AE_MLP(BaseDecoder):
         self.depth = 2
 
     def forward(self, z, **kwargs):
+        if _native(z):
+            from .linear_native import mlp_chain
+            h = mlp_chain(z.reshape(-1, z.shape[-1]), [self.layers[0][0], self.layers[1][0]], ["relu", "sigmoid"])
+            return ModelOutput(reconstruction=h.reshape(*z.shape[:-1], *self.input_dim))
         h = NF.linear(z.reshape(-1, z.shape[-1]), self.layers[0][0].weight, self.layers[0][0].bias, act="relu")
         h = NF.linear(h, self.layers[1][0].weight, self.layers[1][0].bias, act="sigmoid", out_dtype=kwargs.get("out_dtype"))
         return ModelOutput(reconstruction=h.reshape(*z.shape[:-1], *self.input_dim))
