@@ -236,6 +236,30 @@ int mv_colsum_any(const void* G, int64_t P, int ld, int N, float* out, void* str
  * Replaces autograd's sigmoid_backward / threshold_backward in front of the gradient GEMMs of a layer. */
 int mv_act_bwd(const void* g, int g_dtype, const void* y, void* out, int64_t n, int act, float slope, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Strided and transposed convolutions of the small convolutional networks (models/nn/svhn.py:7-70, mmnist.py:78-110,173-207) as
+ * gather + mv_gemm.  The patch matrix `cols` is bf16 [n_img * grid_h * grid_w][ld] with columns ordered (channel, tap) = a torch
+ * Conv2d / ConvTranspose2d weight flattened over its last three dimensions, so packed weights and weight gradients need no
+ * permutation; columns >= C*kh*kw are zero padding.  `H, W, C, nchw` describe the image-side tensor (NHWC when nchw = 0).
+ *   mv_im2col  cols[(n, gy, gx), c*T + t] = src[n, gy*stride - pad + ky, gx*stride - pad + kx, c]  (0 outside), src fp32 or bf16
+ *              (nn.Conv2d forward: grid = the convolution's output; nn.ConvTranspose2d backward: src = gradient of its output,
+ *              grid = its input)
+ *   mv_col2im  dst[n, y, x, c] = act(bias[c] + sum over the taps t that reach (y, x) of cols[(n, gy, gx), c*T + t])
+ *              * (dact ? (dact[n, y, x, c] > 0 ? 1 : dslope) : 1), dst / dact bf16 in the image-side layout; cols fp32 or bf16
+ *              (the GEMM that produces it writes fp32, so the sum over the taps sees unrounded partial products)
+ *              (nn.ConvTranspose2d forward after `cols = x W`; nn.Conv2d data gradient after `cols = dY W`)
+ *   mv_chan_sum_nchw  out[c] += sum_{n, y, x} g[n, c, y, x]  (bias gradient of an NCHW layer, g bf16, out fp32)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mv_conv_geom {
+  int32_t n_img, H, W, C, nchw;
+  int32_t kh, kw, stride, pad;
+  int32_t grid_h, grid_w, ld;
+} mv_conv_geom;
+int mv_im2col(const void* src, int src_dtype, void* cols, const mv_conv_geom* geom, void* stream);
+int mv_col2im(const void* cols, int cols_dtype, void* dst, const mv_conv_geom* geom, const float* bias, int act, const void* dact,
+              float dslope, void* stream);
+int mv_chan_sum_nchw(const void* g, int n_img, int C, int HW, float* out, void* stream);
+
 /* Weight gradient of a tap-GEMM layer:  dW[t, n, c] += sum_p G[p, n] * X[p + tap_off[t], c]   (fp32, accumulating).
  * Replaces the weight-gradient half of autograd's convolution_backward / addmm backward for the layers above
  * (the reference reaches it through loss.backward(), trainers/base/base_trainer.py:359).

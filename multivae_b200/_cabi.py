@@ -50,6 +50,11 @@ class GemmArgs(ctypes.Structure):
                 ("out", c_void_p), ("out_ld", ctypes.c_int32), ("out_kind", ctypes.c_int32)]
 
 
+class ConvGeom(ctypes.Structure):
+    """mv_conv_geom of include/multivae_b200.h."""
+    _fields_ = [(k, ctypes.c_int32) for k in ("n_img", "H", "W", "C", "nchw", "kh", "kw", "stride", "pad", "grid_h", "grid_w", "ld")]
+
+
 class PackItem(ctypes.Structure):
     """mv_pack_item of include/multivae_b200.h."""
     _fields_ = [("src", c_void_p), ("dst_fwd", c_void_p), ("dst_dgrad", c_void_p), ("N", ctypes.c_int32), ("C", ctypes.c_int32),
@@ -85,6 +90,9 @@ _PROTOS = {
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "mv_tapgemm": [ctypes.POINTER(TapGemmArgs), c_void_p],
     "mv_gemm": [ctypes.POINTER(GemmArgs), c_void_p],
+    "mv_im2col": [c_void_p, c_int, c_void_p, ctypes.POINTER(ConvGeom), c_void_p],
+    "mv_col2im": [c_void_p, c_int, c_void_p, ctypes.POINTER(ConvGeom), c_void_p, c_int, c_void_p, c_float, c_void_p],
+    "mv_chan_sum_nchw": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "mv_colsum_any": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
     "mv_act_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p],
     "mv_upsample2x_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -1,0 +1,176 @@
+// Strided / transposed convolutions of the small convolutional networks (models/nn/svhn.py:7-70, mmnist.py:78-110,173-207:
+// 4x4 and 3x3 kernels, stride 2, 3..128 channels, < 10 MFLOP per sample) as "gather + tensor-core GEMM":
+//
+//   mv_im2col   cols[(n, gy, gx), c*T + t] = src[n, gy*s - pad + ky, gx*s - pad + kx, c]   (0 outside the source)
+//               the patch matrix of a strided convolution's forward pass, and of a transposed convolution's weight / data
+//               gradient (there `src` is the gradient of the transposed convolution's output and (gy, gx) its input grid)
+//   mv_col2im   dst[n, y, x, c] = act(bias[c] + sum_{t : (y + pad - ky) % s == 0, ...} cols[(n, (y+pad-ky)/s, (x+pad-kx)/s), c*T + t])
+//               the gather form of the scatter-add: a transposed convolution's forward pass (after the GEMM x W that produces
+//               `cols`) and a strided convolution's data gradient; bias, ReLU / Sigmoid and the activation-derivative mask of
+//               the layer below are fused
+//
+// The contractions themselves run on the general tcgen05 GEMM (csrc/gemm.cu).  Columns are ordered (channel, tap) like a torch
+// Conv2d weight [N, C, kh, kw] flattened, so packed weights and weight gradients need no permutation.  HBM-bound helpers:
+// one thread per element, coalesced along the innermost index of whichever side is written.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mv {
+
+using bf16 = __nv_bfloat16;
+
+struct ConvGeom {
+  int n_img, H, W, C;          // the image-side tensor (im2col: source; col2im: destination)
+  int kh, kw, stride, pad;
+  int Gh, Gw;                  // the grid the patch matrix has one row per position of
+  int64_t sn, sy, sx, sc;      // element strides of the image-side tensor (NHWC or NCHW)
+  int ld;                      // row pitch of the patch matrix (>= C*kh*kw, multiple of 8; extra columns are written as zeros)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ src, bf16* __restrict__ cols, const ConvGeom g) {
+  const int T_ = g.kh * g.kw;
+  const int64_t total = int64_t(g.n_img) * g.Gh * g.Gw * g.ld;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int col = int(e % g.ld);
+    const int64_t row = e / g.ld;
+    float v = 0.f;
+    if (col < g.C * T_) {
+      const int c = col / T_, t = col - c * T_;
+      const int ky = t / g.kw, kx = t - ky * g.kw;
+      const int gx = int(row % g.Gw);
+      const int64_t r2 = row / g.Gw;
+      const int gy = int(r2 % g.Gh), n = int(r2 / g.Gh);
+      const int y = gy * g.stride - g.pad + ky, x = gx * g.stride - g.pad + kx;
+      if (y >= 0 && y < g.H && x >= 0 && x < g.W) v = Vec<T>::load1(src + n * g.sn + y * g.sy + x * g.sx + c * g.sc);
+    }
+    cols[e] = __float2bfloat16_rn(v);
+  }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(256) col2im_kernel(const TC* __restrict__ cols, bf16* __restrict__ dst, const ConvGeom g,
+                                                     const float* __restrict__ bias, int act, const bf16* __restrict__ dact,
+                                                     float dslope, int c_fastest) {
+  const int T_ = g.kh * g.kw;
+  const int64_t total = int64_t(g.n_img) * g.H * g.W * g.C;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    int n, y, x, c;
+    if (c_fastest) {   // NHWC destination
+      c = int(e % g.C);
+      int64_t r = e / g.C;
+      x = int(r % g.W); r /= g.W;
+      y = int(r % g.H); n = int(r / g.H);
+    } else {           // NCHW destination
+      x = int(e % g.W);
+      int64_t r = e / g.W;
+      y = int(r % g.H); r /= g.H;
+      c = int(r % g.C); n = int(r / g.C);
+    }
+    float acc = bias ? bias[c] : 0.f;
+    for (int ky = 0; ky < g.kh; ++ky) {
+      const int yy = y + g.pad - ky;
+      if (yy < 0 || yy % g.stride) continue;
+      const int gy = yy / g.stride;
+      if (gy >= g.Gh) continue;
+      for (int kx = 0; kx < g.kw; ++kx) {
+        const int xx = x + g.pad - kx;
+        if (xx < 0 || xx % g.stride) continue;
+        const int gx = xx / g.stride;
+        if (gx >= g.Gw) continue;
+        acc += Vec<TC>::load1(cols + ((int64_t(n) * g.Gh + gy) * g.Gw + gx) * g.ld + c * T_ + ky * g.kw + kx);
+      }
+    }
+    if (act == MV_ACT_RELU) acc = fmaxf(acc, 0.f);
+    else if (act == MV_ACT_LRELU02) acc = fmaxf(acc, 0.2f * acc);
+    else if (act == MV_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
+    const int64_t o = n * g.sn + y * g.sy + x * g.sx + c * g.sc;
+    if (dact) acc *= __bfloat162float(dact[o]) > 0.f ? 1.f : dslope;
+    dst[o] = __float2bfloat16_rn(acc);
+  }
+}
+
+// out[c] += sum over (n, y, x) of g[n, c, y, x] (bias gradient of a layer whose output is NCHW with few channels)
+__global__ void __launch_bounds__(256) chan_sum_nchw_kernel(const bf16* __restrict__ g, int n_img, int C, int HW, float* __restrict__ out) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int n = blockIdx.y; n < n_img; n += gridDim.y)
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __bfloat162float(g[(int64_t(n) * C + c) * HW + i]);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(out + c, s);
+  }
+}
+
+int num_sms();
+
+static int fill_geom(ConvGeom* g, const mv_conv_geom* a, const char* who) {
+  MV_CHECK_ARG(a && a->n_img > 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->kh > 0 && a->kw > 0 && a->stride > 0 && a->pad >= 0 &&
+                   a->grid_h > 0 && a->grid_w > 0, "%s: bad geometry", who);
+  MV_CHECK_ARG(a->ld >= a->C * a->kh * a->kw && a->ld % 4 == 0, "%s: patch-matrix pitch %d must be >= C*kh*kw and a multiple of 4", who, a->ld);
+  g->n_img = a->n_img; g->H = a->H; g->W = a->W; g->C = a->C; g->kh = a->kh; g->kw = a->kw; g->stride = a->stride; g->pad = a->pad;
+  g->Gh = a->grid_h; g->Gw = a->grid_w; g->ld = a->ld;
+  if (a->nchw) { g->sn = int64_t(a->C) * a->H * a->W; g->sc = int64_t(a->H) * a->W; g->sy = a->W; g->sx = 1; }
+  else { g->sn = int64_t(a->H) * a->W * a->C; g->sy = int64_t(a->W) * a->C; g->sx = a->C; g->sc = 1; }
+  return MV_OK;
+}
+
+}  // namespace mv
+
+using namespace mv;
+
+extern "C" int mv_im2col(const void* src, int src_dtype, void* cols, const mv_conv_geom* geom, void* stream) {
+  MV_CHECK_ARG(src && cols, "mv_im2col: null pointer");
+  ConvGeom g;
+  const int rc = fill_geom(&g, geom, "mv_im2col");
+  if (rc != MV_OK) return rc;
+  const int64_t total = int64_t(g.n_img) * g.Gh * g.Gw * g.ld;
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_dtype == MV_F32) im2col_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(src), static_cast<bf16*>(cols), g);
+  else if (src_dtype == MV_BF16) im2col_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(src), static_cast<bf16*>(cols), g);
+  else {
+    mv::set_error("mv_im2col: unsupported dtype %d", src_dtype);
+    return MV_ERR_UNSUPPORTED;
+  }
+  MV_CHECK_LAUNCH("mv_im2col");
+  return MV_OK;
+}
+
+extern "C" int mv_col2im(const void* cols, int cols_dtype, void* dst, const mv_conv_geom* geom, const float* bias, int act, const void* dact,
+                         float dslope, void* stream) {
+  MV_CHECK_ARG(cols && dst, "mv_col2im: null pointer");
+  MV_CHECK_ARG(act >= MV_ACT_NONE && act <= MV_ACT_SIGMOID, "mv_col2im: bad activation %d", act);
+  ConvGeom g;
+  const int rc = fill_geom(&g, geom, "mv_col2im");
+  if (rc != MV_OK) return rc;
+  const int64_t total = int64_t(g.n_img) * g.H * g.W * g.C;
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cols_dtype == MV_F32)
+    col2im_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(cols), static_cast<bf16*>(dst), g, bias, act,
+                                                 static_cast<const bf16*>(dact), dslope, geom->nchw ? 0 : 1);
+  else if (cols_dtype == MV_BF16)
+    col2im_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(cols), static_cast<bf16*>(dst), g, bias, act,
+                                                static_cast<const bf16*>(dact), dslope, geom->nchw ? 0 : 1);
+  else {
+    mv::set_error("mv_col2im: unsupported dtype %d", cols_dtype);
+    return MV_ERR_UNSUPPORTED;
+  }
+  MV_CHECK_LAUNCH("mv_col2im");
+  return MV_OK;
+}
+
+extern "C" int mv_chan_sum_nchw(const void* g, int n_img, int C, int HW, float* out, void* stream) {
+  MV_CHECK_ARG(g && out && n_img > 0 && C > 0 && HW > 0, "mv_chan_sum_nchw: bad arguments");
+  const int yb = std::min(n_img, std::max(1, num_sms() * 4 / C));
+  chan_sum_nchw_kernel<<<dim3(C, yb), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(g), n_img, C, HW, out);
+  MV_CHECK_LAUNCH("mv_chan_sum_nchw");
+  return MV_OK;
+}

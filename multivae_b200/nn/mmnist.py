@@ -11,6 +11,7 @@ import torch.nn.functional as F
 from ..containers import ModelOutput
 from . import functional as NF
 from .base_architectures import BaseDecoder, BaseEncoder
+from .default_architectures import _native
 
 
 class Unflatten(nn.Module):
@@ -33,6 +34,11 @@ class EncoderConvMMNIST_adapted(BaseEncoder):
         self.class_logvar = nn.Conv2d(128, self.latent_dim, 4, 2, 0)
 
     def forward(self, x):
+        if _native(x):
+            from .conv_native import conv_encoder
+            e = self.shared_encoder
+            mu, lv = conv_encoder(x, [e[0], e[2], e[4]], [self.class_mu, self.class_logvar])
+            return ModelOutput(embedding=mu.squeeze(), log_covariance=lv.squeeze())
         h = x
         for i in (0, 2, 4):
             h = NF.conv2d(h, self.shared_encoder[i].weight, self.shared_encoder[i].bias, stride=2, padding=1, act="relu")
@@ -53,6 +59,10 @@ class DecoderConvMMNIST(BaseDecoder):
 
     def forward(self, z):
         d = self.decoder
+        if _native(z):
+            from .conv_native import convt_decoder
+            h = convt_decoder(z.reshape(-1, z.size(-1)), d[0], "linear", [d[3], d[5], d[7]], "none", (128, 4, 4))
+            return ModelOutput(reconstruction=h.view(*z.size()[:-1], *h.size()[1:]))
         h = NF.linear(z.reshape(-1, z.size(-1)), d[0].weight, d[0].bias, act="relu").view(-1, 128, 4, 4)
         h = NF.conv_transpose2d(h, d[3].weight, d[3].bias, stride=2, padding=1, act="relu")
         h = NF.conv_transpose2d(h, d[5].weight, d[5].bias, stride=2, padding=1, output_padding=1, act="relu")

@@ -5,6 +5,7 @@ import torch.nn as nn
 from ..containers import ModelOutput
 from . import functional as NF
 from .base_architectures import BaseDecoder, BaseEncoder
+from .default_architectures import _native
 
 
 class Encoder_VAE_SVHN(BaseEncoder):
@@ -19,6 +20,10 @@ class Encoder_VAE_SVHN(BaseEncoder):
         self.c2 = nn.Conv2d(4 * f, self.latent_dim, 4, 2, 0)
 
     def forward(self, x):
+        if _native(x):
+            from .conv_native import conv_encoder
+            mu, lv = conv_encoder(x, [self.enc[0], self.enc[2], self.enc[4]], [self.c1, self.c2])
+            return ModelOutput(embedding=mu.squeeze(), log_covariance=lv.squeeze())
         h = x
         for i in (0, 2, 4):
             h = NF.conv2d(h, self.enc[i].weight, self.enc[i].bias, stride=2, padding=1, act="relu")
@@ -39,6 +44,11 @@ class Decoder_VAE_SVHN(BaseDecoder):
                                  nn.ConvTranspose2d(f, ch, 4, 2, 1), nn.Sigmoid())
 
     def forward(self, z):
+        if _native(z):
+            from .conv_native import convt_decoder
+            h = convt_decoder(z.reshape(-1, z.shape[-1]), self.dec[0], "convt", [self.dec[2], self.dec[4], self.dec[6]], "sigmoid",
+                              (4 * self.fBase, 4, 4))
+            return ModelOutput(reconstruction=h.reshape(*z.shape[:-1], *h.shape[1:]))
         h = z.reshape(-1, z.shape[-1], 1, 1)
         h = NF.conv_transpose2d(h, self.dec[0].weight, self.dec[0].bias, stride=1, padding=0, act="relu")
         h = NF.conv_transpose2d(h, self.dec[2].weight, self.dec[2].bias, stride=2, padding=1, act="relu")
