@@ -1,7 +1,9 @@
-"""Benchmark of the hot path: one MMVAE+ PolyMNIST training step (5 modalities, K=10, DReG, ResNet
-encoders/decoders, Adam) per "step" on synthetic batches, one process per GPU.
+"""Benchmark of the hot path: one training step (forward + backward + gradient all-reduce + Adam) per "step" on synthetic
+batches, one process per GPU.  Default workload = the north star (MMVAE+ PolyMNIST, 5 modalities, K=10, DReG, ResNet
+encoders/decoders); `--config cfg2|cfg3|cfg4|cfg5` runs the other BASELINE.json configurations on their own networks and
+per-GPU batch sizes with the same line schema.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config ns|cfg2|cfg3|cfg4|cfg5] [--batch B] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` = samples/s with the batch already resident in HBM; `e2e` =
 the same metric through `BaseTrainer.step_batch` with pinned-host inputs copied H2D and the loss read
@@ -28,20 +30,38 @@ import torch  # noqa: E402
 METRIC = "MMVAE+ PolyMNIST K=10 train samples/sec"
 M, K, L, LW, DIMS = 5, 10, 32, 32, (3, 28, 28)
 D = 3 * 28 * 28
-GFLOP_PER_SAMPLE = 166.15  # fwd+bwd, BASELINE.md section 3 (torch FlopCounterMode on the reference modules)
+
+# The BASELINE.json configurations.  `case` = the golden case of oracle/cases.py that defines the model, its
+# networks and hyper-parameters (the same spec the parity tests replay); gflop = fwd+bwd per sample.
+CONFIGS = {
+    "ns": dict(metric=METRIC, case="ns_mmvaeplus_resnet", batch=256, gflop=166.15,
+               name="MMVAE+ PolyMNIST M=5 K=10 L=32+32 DReG laplace(0.75) beta=2.5 ResNet enc/dec"),
+    "cfg2": dict(metric="MVAE MnistSvhn train samples/sec", case="cfg2_mvae_mnistsvhn", batch=512, gflop=0.1215,
+                 name="MVAE (PoE) MnistSvhn-shaped 2-modality L=20, MLP (mnist) + SVHN conv networks"),
+    "cfg3": dict(metric="MMVAE MnistSvhn K=10 train samples/sec", case="cfg3_mmvae_mnistsvhn", batch=256, gflop=0.6353,
+                 name="MMVAE (MoE, IWAE K=10) MnistSvhn-shaped 2-modality L=20 laplace(0.75), MLP (mnist) + SVHN conv networks"),
+    "cfg4": dict(metric="MoPoE PolyMNIST train samples/sec", case="cfg4_mopoe_polymnist", batch=256, gflop=0.2278,
+                 name="MoPoE PolyMNIST-shaped 5-modality (31 subsets) L=512 beta=2.5 laplace(0.75), conv-PolyMNIST networks"),
+    "cfg5": dict(metric="MMVAE+ CelebA-shaped K=10 train samples/sec", case="cfg5_mmvaeplus_celeba_b128", batch=128, gflop=0.7913,
+                 name="MMVAE+ CelebA-shaped (3x64x64 image + 40-dim attributes) K=10 L=32+32 DReG, default MLP networks"),
+}
 
 
-def workload_name(B):
-    return (f"MMVAE+ PolyMNIST M=5 K=10 L=32+32 DReG laplace(0.75) beta=2.5 ResNet enc/dec, "
-            f"per-GPU batch {B}, fwd+bwd+Adam")
+def workload_name(B, config="ns"):
+    return f"{CONFIGS[config]['name']}, per-GPU batch {B}, fwd+bwd+Adam"
 
 
-def synthetic_batch(B, pinned=False):
-    """U[0,1) images from per-modality generators."""
+def config_spec(config):
+    from oracle.cases import CASES
+    return CASES[CONFIGS[config]["case"]]
+
+
+def synthetic_batch(B, pinned=False, config="ns"):
+    """U[0,1) inputs from per-modality generators."""
     data = {}
-    for i in range(M):
-        t = torch.rand(B, *DIMS, generator=torch.Generator().manual_seed(1000 + i))
-        data[f"m{i}"] = t.pin_memory() if pinned else t
+    for i, (m, d) in enumerate(config_spec(config)["dims"].items()):
+        t = torch.rand(B, *d, generator=torch.Generator().manual_seed(1000 + i))
+        data[m] = t.pin_memory() if pinned else t
     return data
 
 
@@ -86,40 +106,37 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU path: the oracle port (restatement of the reference's training step) — baseline only
 # ------------------------------------------------------------------------------------------------
-def cpu_port_runner(B, state_dict=None):
-    """Returns (step_fn, nthreads): step_fn() runs forward + backward + Adam of the reference algorithm on
-    CPU, fp32, with all host threads."""
-    from oracle.port import elbo as E
-    from oracle.port import nets as N
+def cpu_port_runner(B, config="ns"):
+    """Returns (step_fn, nthreads): step_fn() runs forward + backward + Adam of the reference algorithm on CPU, fp32, with
+    all host threads, on the configuration's own model / networks at batch B."""
+    import copy
+
+    from oracle import replay
+    from oracle.port.nets import synth_state_dict
     nthreads = len(os.sched_getaffinity(0))
     torch.set_num_threads(nthreads)
-    if state_dict is None:
-        state_dict = north_star_model("cpu").state_dict()
-    p = {k: v.detach().float().cpu().clone() for k, v in state_dict.items()}
-    mods = [f"m{i}" for i in range(M)]
-    for k, v in p.items():
-        v.requires_grad_(not (k.startswith("mean_priors") or k == "logvars_priors.shared"))
+    spec = copy.deepcopy(config_spec(config))
+    spec["B"] = B
+    model = build_model(config, "cpu")
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    frozen = {k for k, p in model.named_parameters() if not p.requires_grad}
+    sd = synth_state_dict(shapes, seed=1)
+    p = {k: v.float().clone().requires_grad_(k not in frozen) for k, v in sd.items()}
     opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-3)
-    data = synthetic_batch(B)
-    enc = {m: (lambda x, m=m: N.encoder_resnet_mmnist(p, f"encoders.{m}.", x)) for m in mods}
-    dec = {m: (lambda z, m=m: N.decoder_resnet_mmnist(p, f"decoders.{m}.", z)) for m in mods}
     g = torch.Generator().manual_seed(2000)
+    shapes_noise = noise_shapes(spec)
+    rec = dict(state_shapes=shapes, sd_seed=1, grads={k: (None if k in frozen else 1) for k in shapes})
 
-    def lap(shape):
-        eps = torch.finfo(torch.float32).eps
-        u = torch.empty(shape).uniform_(eps - 1, 1, generator=g)
-        return -u.sign() * torch.log1p(-u.abs())
+    def draw(shape, kind):
+        if kind == "laplace":
+            eps = torch.finfo(torch.float32).eps
+            u = torch.empty(shape).uniform_(eps - 1, 1, generator=g)
+            return -u.sign() * torch.log1p(-u.abs())
+        return torch.empty(shape).normal_(generator=g)
 
     def step():
-        noise = {"u": {}, "w": {}, "prior": {}}
-        for c in mods:
-            noise["u"][c], noise["w"][c] = lap((K, B, L)), lap((K, B, LW))
-            noise["prior"][c] = {r: lap((K, B, LW)) for r in mods if r != c}
-        loss = E.mmvae_plus_forward(
-            enc, dec, data, noise, K=K, latent_dim=L, style_dim=LW, beta=2.5, kind="laplace_with_softmax",
-            loss="dreg_looser", dec_dist={m: "laplace" for m in mods}, dec_scale={m: 0.75 for m in mods},
-            rescale={m: 1 for m in mods}, prior_mean={m: p[f"mean_priors.{m}"] for m in mods + ["shared"]},
-            prior_logvar={m: p[f"logvars_priors.{m}"] for m in mods + ["shared"]})
+        rec["noise"] = [draw(s, k) for s, k in shapes_noise]
+        loss = replay.run_port_with_params(spec, rec, p)
         opt.zero_grad()
         loss.backward()
         opt.step()
@@ -128,8 +145,27 @@ def cpu_port_runner(B, state_dict=None):
     return step, nthreads
 
 
-def time_cpu(B, steps, warmup):
-    step, nthreads = cpu_port_runner(B)
+def noise_shapes(spec):
+    """(shape, kind) of the standard draws one forward pass consumes, in the reference's order (oracle/replay.split_noise)."""
+    B, cfg, mods = spec["B"], spec["cfg"], list(spec["dims"])
+    Ld = cfg["latent_dim"]
+    model = spec["model"]
+    kind = "laplace" if cfg.get("prior_and_posterior_dist", "normal") == "laplace_with_softmax" else "normal"
+    if model == "mmvaeplus":
+        Lw, Kk = cfg["modalities_specific_dim"], cfg["K"]
+        out = []
+        for _ in mods:
+            out += [((Kk, B, Ld), kind), ((Kk, B, Lw), kind)] + [((Kk, B, Lw), kind)] * (len(mods) - 1)
+        return out
+    if model == "mmvae":
+        return [((cfg["K"], B, Ld), kind)] * len(mods)
+    if model == "mvae":
+        return [((B, Ld), "normal")] * (1 + len(mods))
+    return [((B, Ld), "normal")]
+
+
+def time_cpu(B, steps, warmup, config="ns"):
+    step, nthreads = cpu_port_runner(B, config)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -142,27 +178,40 @@ def time_cpu(B, steps, warmup):
 # ------------------------------------------------------------------------------------------------
 # GPU path
 # ------------------------------------------------------------------------------------------------
-def north_star_model(device):
+def build_model(config, device):
+    """The configuration's model on its own networks (random init under torch.manual_seed(0))."""
+    import copy
+
     import multivae_b200 as mb
-    from multivae_b200.nn import DecoderResnetMMNIST, EncoderResnetMMNIST
-    mods = [f"m{i}" for i in range(M)]
-    cfg = mb.MMVAEPlusConfig(
-        n_modalities=M, input_dims={m: DIMS for m in mods}, K=K, latent_dim=L, modalities_specific_dim=LW, beta=2.5,
-        prior_and_posterior_dist="laplace_with_softmax", decoders_dist={m: "laplace" for m in mods},
-        decoder_dist_params={m: {"scale": 0.75} for m in mods}, learn_modality_prior=True, learn_shared_prior=False,
-        loss="dreg_looser")
+    from multivae_b200 import nn as NN
+    spec = config_spec(config)
+    cls, cfgcls = {"mmvaeplus": (mb.MMVAEPlus, mb.MMVAEPlusConfig), "mmvae": (mb.MMVAE, mb.MMVAEConfig), "mvtcae": (mb.MVTCAE, mb.MVTCAEConfig),
+                   "mvae": (mb.MVAE, mb.MVAEConfig), "mopoe": (mb.MoPoE, mb.MoPoEConfig)}[spec["model"]]
+    cfg = cfgcls(n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"]))
     torch.manual_seed(0)
-    enc = {m: EncoderResnetMMNIST(LW, L) for m in mods}
-    dec = {m: DecoderResnetMMNIST(L + LW) for m in mods}
-    return mb.MMVAEPlus(cfg, enc, dec).to(device)
+    enc = dec = None
+    if "arch" in spec:
+        Ld, Lw = spec["cfg"]["latent_dim"], spec["cfg"].get("modalities_specific_dim")
+        enc, dec = {}, {}
+        for m, a in spec["arch"].items():
+            c = mb.BaseAEConfig(input_dim=tuple(spec["dims"][m]), latent_dim=Ld)
+            enc[m], dec[m] = {"mlp": lambda: (NN.Encoder_VAE_MLP(c), NN.Decoder_AE_MLP(c)),
+                              "svhn": lambda: (NN.Encoder_VAE_SVHN(c), NN.Decoder_VAE_SVHN(c)),
+                              "conv_mmnist": lambda: (NN.EncoderConvMMNIST_adapted(c), NN.DecoderConvMMNIST(c)),
+                              "resnet_mmnist": lambda: (NN.EncoderResnetMMNIST(Lw or 0, Ld), NN.DecoderResnetMMNIST(Ld + (Lw or 0)))}[a]()
+    return cls(cfg, enc, dec).to(device)
 
 
-def elbo_rel_err(device, compute_dtype=torch.float32):
-    """|loss_gpu - loss_reference| / |loss_reference| on the north-star golden produced by the REAL reference
-    (tests/golden/elbo_ns_mmvaeplus_resnet.pt: ResNet encoders/decoders, K = 10, B = 4, recorded noise).  fp32: library
-    networks + native ELBO kernels; bf16: the tcgen05 encoders/decoders (bf16 operands) + native ELBO kernels."""
+def north_star_model(device):
+    return build_model("ns", device)
+
+
+def elbo_rel_err(device, compute_dtype=torch.float32, config="ns"):
+    """|loss_gpu - loss_reference| / |loss_reference| on the configuration's golden produced by the REAL reference
+    (tests/golden/elbo_<case>.pt: the configuration's own networks, recorded noise; north star: K = 10, B = 4).  fp32: library
+    networks + native ELBO kernels; bf16: the native tensor-core networks (bf16 operands) + native ELBO kernels."""
     from tests.gpu_checks import rel, run_product
-    out, _, rec = run_product("ns_mmvaeplus_resnet", device=device, compute_dtype=compute_dtype)
+    out, _, rec = run_product(CONFIGS[config]["case"], device=device, compute_dtype=compute_dtype)
     return rel(out.loss.detach().cpu(), rec["loss"])
 
 
@@ -171,6 +220,7 @@ def run_gpu(args):
 
     import multivae_b200 as mb
     from multivae_b200 import _cabi
+    from multivae_b200.nn import functional as NF
     from multivae_b200.trainer import BaseTrainer, BaseTrainerConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,15 +231,22 @@ def run_gpu(args):
                            "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    B = args.batch
-    model = north_star_model(device)
-    model.compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    host = synthetic_batch(B, pinned=True)
-    ds = mb.MultimodalBaseDataset(data=host)
-    tcfg = BaseTrainerConfig(per_device_train_batch_size=B, learning_rate=1e-3, optimizer_cls="Adam",
-                             world_size=world, rank=rank, local_rank=local_rank, use_cuda_graph=not args.no_graph)
-    trainer = BaseTrainer(model, ds, training_config=tcfg)
-    model.train()
+    config = args.config
+    B = args.batch or CONFIGS[config]["batch"]
+    spec = config_spec(config)
+    host = synthetic_batch(B, pinned=True, config=config)
+
+    def make_trainer(compute_dtype, graph):
+        model = build_model(config, device)
+        model.compute_dtype = compute_dtype
+        tcfg = BaseTrainerConfig(per_device_train_batch_size=B, learning_rate=1e-3, optimizer_cls="Adam", world_size=world, rank=rank,
+                                 local_rank=local_rank, use_cuda_graph=graph)
+        tr = BaseTrainer(model, mb.MultimodalBaseDataset(data=host), training_config=tcfg)
+        model.train()
+        return tr, tcfg
+
+    trainer, tcfg = make_trainer(torch.bfloat16 if args.dtype == "bf16" else torch.float32, not args.no_graph)
+    fwd_kw = dict(spec.get("fwd", {}))   # MVAE: a post-warm-up epoch so that the KL weight is not 0
     resident = mb.DatasetOutput(data={k: v.to(device) for k, v in host.items()})
     pinned = mb.DatasetOutput(data=host)
 
@@ -200,13 +257,15 @@ def run_gpu(args):
 
     host_ms = [0.0]
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps   # host enqueue time per step (no sync inside)
         e1.record()
         barrier()
@@ -215,14 +274,31 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    def step_resident():
-        trainer.step_batch(resident)
+    def step_resident(tr=None):
+        (tr or trainer).step_batch(resident, **fwd_kw)
 
+    # e2e: the H2D copies of the pinned inputs are enqueued in front of the step, the step's result (loss_sum) leaves through an
+    # asynchronous D2H copy into a pinned slot right behind it, and the host reads the PREVIOUS step's value once its event has
+    # fired - every step's inputs and result cross PCIe inside the timed region, but the host never stalls the GPU queue.
     last = {}
+    slots = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    events = [torch.cuda.Event() for _ in range(2)]
+    pending = []
+
+    def drain(keep):
+        while len(pending) > keep:
+            i = pending.pop(0)
+            events[i].synchronize()
+            last["loss"] = float(slots[i])
 
     def step_e2e():
-        out = trainer.step_batch(pinned)  # H2D of the five pinned image tensors inside
-        last["loss"] = float(out.loss_sum)  # D2H read of the step's result
+        out = trainer.step_batch(pinned, **fwd_kw)  # H2D of the pinned input tensors inside
+        i = len(last.setdefault("n", [])) % 2
+        last["n"].append(0)
+        drain(1)                                    # slot i was filled two steps ago: read before it is overwritten
+        slots[i].copy_(out.loss_sum.detach(), non_blocking=True)   # D2H read of the step's result
+        events[i].record()
+        pending.append(i)
 
     # untimed: W warm-up steps (eager), plus the CUDA-graph capture step and one replay when graphs are on
     for _ in range(args.warmup if args.no_graph else max(args.warmup, tcfg.graph_warmup_steps + 2)):
@@ -234,7 +310,7 @@ def run_gpu(args):
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times for the roofline (separate short pass so the events do not perturb `value`)
-    trainer.step_batch(resident, allow_graph=False)   # un-timed eager pass: lazy module loading of every kernel variant
+    trainer.step_batch(resident, allow_graph=False, **fwd_kw)   # un-timed eager pass: lazy module loading of every kernel variant
     timer = _cabi.KernelTimer()
     _cabi.set_timer(timer)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -243,7 +319,7 @@ def run_gpu(args):
     nprof = max(1, min(3, args.steps))
     n0 = _cabi.launch_count()
     for _ in range(nprof):
-        trainer.step_batch(resident, allow_graph=False)   # per-kernel events need host-launched kernels
+        trainer.step_batch(resident, allow_graph=False, **fwd_kw)   # per-kernel events need host-launched kernels
     # kernels of this library per step (the same launches are what the CUDA graph replays in the timed region)
     launches = (_cabi.launch_count() - n0) // nprof * args.steps
     e1.record()
@@ -253,44 +329,72 @@ def run_gpu(args):
     # e2e leg
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    drain(0)
+    ms_e2e = timed(step_e2e, args.steps, finish=lambda: drain(0))
+
+    # the same modules run by the library (torch eager -> cuDNN / cuBLAS) on the same GPU: the SURVEY 2.2 bar
+    eager = None
+    if args.torch_eager and world == 1:
+        eager = {}
+        del trainer
+        torch.cuda.empty_cache()
+        NF.set_backend("torch")
+        try:
+            for label, dt in (("bf16_autocast", torch.bfloat16), ("fp32", torch.float32)):
+                tr2, _ = make_trainer(dt, False)
+                for _ in range(3):
+                    step_resident(tr2)
+                n = max(3, min(args.steps, 10))
+                t = timed(lambda: step_resident(tr2), n)
+                eager[label] = {"samples_per_s": B * n / (t / 1e3), "ms_per_step": t / n}
+                del tr2
+                torch.cuda.empty_cache()
+        finally:
+            NF.set_backend("auto")
+        eager["what"] = ("this repo's modules with the layer backend forced to the library (ATen -> cuDNN / cuBLAS), eager launches, "
+                         "native ELBO kernels kept; same batch, same optimizer")
 
     if rank != 0:
         return
     value = world * B * args.steps / (ms / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
-    roof = roofline_from(summary, prof_ms, B, nprof, ms / args.steps)
+    roof = roofline_from(summary, prof_ms, B, nprof, ms / args.steps, config)
     rel = rel16 = None
     if not args.no_check:
         try:
-            rel = elbo_rel_err(device)
-            rel16 = elbo_rel_err(device, torch.bfloat16)
+            rel = elbo_rel_err(device, config=config)
+            rel16 = elbo_rel_err(device, torch.bfloat16, config=config)
         except Exception as e:  # the check must not hide the timing line
             rel = f"failed: {type(e).__name__}: {e}"
     cpu = None
     if not args.no_cpu:
-        v, spstep, nthreads = time_cpu(args.cpu_batch, steps=args.cpu_steps, warmup=1)
+        cb = args.cpu_batch or (8 if config == "ns" else B)
+        v, spstep, nthreads = time_cpu(cb, steps=args.cpu_steps, warmup=2, config=config)
         cpu = {"value": v, "unit": "samples/s", "cores": nthreads, "kind": "port",
-               "sample": f"same workload at batch {args.cpu_batch}: 1 warm-up + {args.cpu_steps} timed steps of "
+               "sample": f"same workload at batch {cb}: 2 warm-up + {args.cpu_steps} timed steps of "
                          f"fwd+bwd+Adam, fp32, oracle/port (CPU restatement of the reference), {spstep:.2f} s/step",
                "cpu_count": os.cpu_count()}
     peaks = measured_peaks()
+    in_bytes = sum(v.numel() * v.element_size() for v in host.values())
     line = {
-        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": CONFIGS[config]["metric"], "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": workload_name(B), "per_gpu_batch": B, "global_batch": B * world,
+        "config": {"workload": workload_name(B, config), "config": config, "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "optimizer": "Adam lr=1e-3 (fp32 master weights)",
-                   "l2": "no flush needed: each step streams > 10 GB of activations (>> 126 MB L2)",
+                   "l2": ("no flush needed: each step streams > 10 GB of activations (>> 126 MB L2)" if config == "ns" else
+                          "no flush: the step is a chain of dependent kernels over its own freshly written activations (what training does); "
+                          "weights stay L2-resident from step to step as they would in training"),
                    "nn_backend": mb.nn.functional.backend_summary()},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": M * B * D * 4, "d2h_bytes_per_step": 4, "last_loss": last.get("loss")},
+                "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4, "last_loss": last.get("loss")},
         "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": roof,
-        "step_fraction_of_tensor_ceiling": value / world / (peaks["bf16_tflops_sustained"] * 1e3 / GFLOP_PER_SAMPLE),
+        "step_fraction_of_tensor_ceiling": value / world / (peaks["bf16_tflops_sustained"] * 1e3 / CONFIGS[config]["gflop"]),
         "elbo_rel_err": rel, "elbo_rel_err_bf16_tensor_path": rel16,
         "cpu_baseline": cpu,
+        "torch_eager_same_gpu": eager,
     }
     EMIT(json.dumps(line))
 
@@ -315,16 +419,18 @@ def measured_traffic(name):
     return None if t is None else t["dram_read_bytes"] + t["dram_write_bytes"]
 
 
-def roofline_from(summary, prof_ms, B, nprof, graph_ms_per_step):
+def roofline_from(summary, prof_ms, B, nprof, graph_ms_per_step, config="ns"):
     """Roofline of the dominant native kernel from the live per-entry-point CUDA-event times.  Shares are kernel time per
     step (host-launched pass with events) over the CUDA-graph step time of the timed region."""
     from multivae_b200 import roofline as R
     peaks = measured_peaks()
     if not summary:
         return None
-    top = max(summary.items(), key=lambda kv: kv[1][1])
-    name, (calls, total_ms) = top
-    info = R.describe(name, B=B, M=M, K=K, D=D, L=L, LW=LW)
+    dims = dict(B=B, M=M, K=K, D=D, L=L, LW=LW)
+    desc = {k: R.describe(k, **dims) if (config == "ns" or "|" in k) else {"bound": "hbm", "work": 0} for k in summary}
+    known = [kv for kv in summary.items() if desc[kv[0]]["work"] > 0] or list(summary.items())
+    name, (calls, total_ms) = max(known, key=lambda kv: kv[1][1])
+    info = desc[name]
     per_launch_s = total_ms / calls / 1e3
     if info["bound"] == "hbm":
         achieved = info["work"] / per_launch_s / 1e9
@@ -332,47 +438,59 @@ def roofline_from(summary, prof_ms, B, nprof, graph_ms_per_step):
     else:
         achieved = info["work"] / per_launch_s / 1e12
         peak, unit = peaks["bf16_tflops_sustained"], "TFLOP/s"
-    shares = {k: round(v[1] / nprof / graph_ms_per_step, 4) for k, v in sorted(summary.items(), key=lambda kv: -kv[1][1])[:8]}
+    pretty = lambda k: k.split("|")[0]  # noqa: E731
+    shares = {}
+    for k, v in sorted(summary.items(), key=lambda kv: -kv[1][1])[:8]:
+        shares[pretty(k)] = round(shares.get(pretty(k), 0) + v[1] / nprof / graph_ms_per_step, 4)
     # the HBM-bound fused ELBO kernels next to it (north_star asks for both rooflines)
     elbo = {}
-    for sym in ("mv_moe_lpx_fwd_multi", "mv_moe_lpx_bwd_multi", "mv_moe_lpx_fwd", "mv_moe_lpx_bwd", "mv_moe_lw_fwd"):
-        if sym in summary:
-            c, t = summary[sym]
-            w = R.describe(sym, B=B, M=M, K=K, D=D, L=L, LW=LW)["work"]
-            elbo[sym] = {"avg_launch_us": t / c * 1e3, "achieved_GBps": w / (t / c / 1e3) / 1e9,
-                         "frac_of_measured_hbm": w / (t / c / 1e3) / 1e9 / peaks["hbm_gbs"], "bytes_per_launch": w}
+    for k, (c, t) in summary.items():
+        if k.split(":")[0].startswith(("mv_moe_lpx", "mv_moe_lw", "mv_poe")) and desc[k]["work"] > 0 and desc[k]["bound"] == "hbm":
+            w = desc[k]["work"]
+            e = elbo.setdefault(pretty(k).rstrip(":"), {"launches": 0, "ms": 0.0, "bytes": 0.0})
+            e["launches"] += c; e["ms"] += t; e["bytes"] += w * c
+    for e in elbo.values():
+        e["avg_launch_us"] = e["ms"] / e["launches"] * 1e3
+        e["achieved_GBps"] = e["bytes"] / (e["ms"] / 1e3) / 1e9
+        e["frac_of_measured_hbm"] = e["achieved_GBps"] / peaks["hbm_gbs"]
+        e["frac_of_nominal_8TBps"] = e["achieved_GBps"] / 8000.0
+        e["bytes_per_launch"] = e.pop("bytes") / e["launches"]
+        del e["ms"]
     # all tensor-core launches together: useful flops / summed kernel time
     tflops = tms = 0.0
     for k, (c, t) in summary.items():
-        inf = R.describe(k, B=B, M=M, K=K, D=D, L=L, LW=LW)
-        if inf["bound"] == "tensor":
-            tflops += inf["work"] * c
+        if desc[k]["bound"] == "tensor":
+            tflops += desc[k]["work"] * c
             tms += t
     tensor_all = {"useful_TFLOPs_per_s": tflops / (tms / 1e3) / 1e12 if tms else None,
                   "frac_of_sustained_peak": tflops / (tms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"] if tms else None,
                   "share_of_step": tms / nprof / graph_ms_per_step}
+    native_ms = sum(v[1] for v in summary.values()) / nprof
     if os.environ.get("MV_BENCH_DUMP"):
         with open(os.environ["MV_BENCH_DUMP"], "w") as f:
             json.dump({"prof_ms": prof_ms, "kernels": {k: {"calls": v[0], "ms": v[1]} for k, v in summary.items()}}, f, indent=1)
-    return {"kernel": name, "bound": info["bound"], "achieved": achieved, "peak": peak, "unit": unit,
-            "frac": achieved / peak, "peak_source": peaks["source"], "traffic": measured_traffic(name),
+    return {"kernel": pretty(name), "bound": info["bound"], "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak, "peak_source": peaks["source"], "traffic": measured_traffic(pretty(name)),
             "algorithmic_work_per_launch": info["work"], "avg_launch_us": per_launch_s * 1e6, "launches": calls,
-            "share_of_step": total_ms / nprof / graph_ms_per_step, "shares": shares, "elbo_kernels": elbo, "tensor_kernels_total": tensor_all}
+            "share_of_step": total_ms / nprof / graph_ms_per_step, "shares": shares, "elbo_kernels": elbo, "tensor_kernels_total": tensor_all,
+            "native_kernel_ms_per_step": native_ms}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, spstep, nthreads = time_cpu(args.cpu_batch, steps=args.steps, warmup=args.warmup)
+    config = args.config
+    cb = args.cpu_batch or (8 if config == "ns" else CONFIGS[config]["batch"])
+    v, spstep, nthreads = time_cpu(cb, steps=args.steps, warmup=max(args.warmup, 1), config=config)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": CONFIGS[config]["metric"], "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch),
-                   "sample": f"each step = the same training step at batch {args.cpu_batch} on the host CPU"},
+        "config": {"workload": workload_name(args.batch or CONFIGS[config]["batch"], config), "config": config,
+                   "sample": f"each step = the same training step at batch {cb} on the host CPU"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": nthreads, "kind": "port",
-                         "sample": f"batch {args.cpu_batch} per step, {args.steps} timed steps, fp32, all host threads"},
+                         "sample": f"batch {cb} per step, {args.steps} timed steps, fp32, all host threads"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     EMIT(json.dumps(line))
@@ -401,11 +519,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--config", default="ns", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the north star)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's own)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=2)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU baseline steps (default: 8 for the north star, else the configuration's own)")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--torch-eager", action="store_true", help="also time the same modules run by the library (torch eager) on this GPU")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")

@@ -238,9 +238,9 @@ int mv_act_bwd(const void* g, int g_dtype, const void* y, void* out, int64_t n, 
 
 /* ---------------------------------------------------------------------------------------------
  * Strided and transposed convolutions of the small convolutional networks (models/nn/svhn.py:7-70, mmnist.py:78-110,173-207) as
- * gather + mv_gemm.  The patch matrix `cols` is bf16 [n_img * grid_h * grid_w][ld] with columns ordered (channel, tap) = a torch
- * Conv2d / ConvTranspose2d weight flattened over its last three dimensions, so packed weights and weight gradients need no
- * permutation; columns >= C*kh*kw are zero padding.  `H, W, C, nchw` describe the image-side tensor (NHWC when nchw = 0).
+ * gather + mv_gemm.  The patch matrix `cols` is [n_img * grid_h * grid_w][ld] with columns ordered tap-major (t*C + c, channels
+ * contiguous: vector gathers on NHWC tensors) or channel-major (c*T + t = a torch Conv2d / ConvTranspose2d weight flattened over
+ * its last three dimensions), see tc_order; columns >= C*kh*kw are zero padding.  `H, W, C, nchw` describe the image-side tensor (NHWC when nchw = 0).
  *   mv_im2col  cols[(n, gy, gx), c*T + t] = src[n, gy*stride - pad + ky, gx*stride - pad + kx, c]  (0 outside), src fp32 or bf16
  *              (nn.Conv2d forward: grid = the convolution's output; nn.ConvTranspose2d backward: src = gradient of its output,
  *              grid = its input)
@@ -254,6 +254,7 @@ typedef struct mv_conv_geom {
   int32_t n_img, H, W, C, nchw;
   int32_t kh, kw, stride, pad;
   int32_t grid_h, grid_w, ld;
+  int32_t tc_order;   /* columns of the patch matrix: 1 = t*C + c (tap-major, channels contiguous), 0 = c*T + t (a torch weight flattened) */
 } mv_conv_geom;
 int mv_im2col(const void* src, int src_dtype, void* cols, const mv_conv_geom* geom, void* stream);
 int mv_col2im(const void* cols, int cols_dtype, void* dst, const mv_conv_geom* geom, const float* bias, int act, const void* dact,
@@ -311,6 +312,13 @@ typedef struct mv_pack_item {
   int32_t N, C, T, Npad, Cpad;
 } mv_pack_item;
 int mv_pack_conv_weights(const mv_pack_item* items, int n_items, void* stream);
+
+/* Weight hand-over for the tap-major column order, all layers of a network in one launch (mv_pack_item: src, dst_fwd, N, C, T,
+ * Cpad = row pitch of the packed matrix >= T*C; dst_dgrad / Npad unused):
+ *   mv_pack_tc        dst_fwd bf16 [N][Cpad]: dst[n, t*C + c] = src fp32 [N][C][T], columns >= T*C zero
+ *   mv_unpack_tc_add  dst_fwd fp32 [N][C][T] (a parameter's .grad) += src fp32 [N][Cpad] at [n, t*C + c] */
+int mv_pack_tc(const mv_pack_item* items, int n_items, void* stream);
+int mv_unpack_tc_add(const mv_pack_item* items, int n_items, void* stream);
 
 /* The reverse hand-over for the gradients of a whole network in one launch: dst[n, c, t] += src[t, n, c] for every item, where
  * src is the fp32 [T, Npad, Cpad] buffer mv_wgrad accumulated into (swapped != 0: [T, Cpad, Npad], the role-swapped image

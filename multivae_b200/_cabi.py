@@ -52,7 +52,7 @@ class GemmArgs(ctypes.Structure):
 
 class ConvGeom(ctypes.Structure):
     """mv_conv_geom of include/multivae_b200.h."""
-    _fields_ = [(k, ctypes.c_int32) for k in ("n_img", "H", "W", "C", "nchw", "kh", "kw", "stride", "pad", "grid_h", "grid_w", "ld")]
+    _fields_ = [(k, ctypes.c_int32) for k in ("n_img", "H", "W", "C", "nchw", "kh", "kw", "stride", "pad", "grid_h", "grid_w", "ld", "tc_order")]
 
 
 class PackItem(ctypes.Structure):
@@ -93,6 +93,8 @@ _PROTOS = {
     "mv_im2col": [c_void_p, c_int, c_void_p, ctypes.POINTER(ConvGeom), c_void_p],
     "mv_col2im": [c_void_p, c_int, c_void_p, ctypes.POINTER(ConvGeom), c_void_p, c_int, c_void_p, c_float, c_void_p],
     "mv_chan_sum_nchw": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "mv_pack_tc": [ctypes.POINTER(PackItem), c_int, c_void_p],
+    "mv_unpack_tc_add": [ctypes.POINTER(PackItem), c_int, c_void_p],
     "mv_colsum_any": [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p],
     "mv_act_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p],
     "mv_upsample2x_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -400,6 +400,7 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
 
 extern "C" int mv_colsum_any(const void* G, int64_t P, int ld, int N, float* out, void* stream) {
   MV_CHECK_ARG(G && out && P > 0 && N >= 8 && N % 8 == 0 && ld % 8 == 0, "mv_colsum_any: bad arguments (N=%d, ld=%d)", N, ld);
+  if (N <= 256 && 256 % (N / 8) == 0) return mv_colsum(G, P, ld, N, out, stream);   // narrow matrices: all 256 threads on rows
   const int col_blocks = (N / 8 + 31) / 32;
   int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
   const int64_t max_rb = (P + 63) / 64;

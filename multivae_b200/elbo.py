@@ -35,7 +35,8 @@ def lpx_fwd(lib, r, x, lpx, Cn, K, B, dist, scale, rescale, mask_r, accumulate):
                                        1 if accumulate else 0, C.stream()), "mv_moe_lpx_cat_fwd")
     else:
         C.check(lib.mv_moe_lpx_fwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(lpx), Cn, K, B, D, dist, scale, rescale, C.ptr(mask_r),
-                                   1 if accumulate else 0, C.stream()), "mv_moe_lpx_fwd")
+                                   1 if accumulate else 0, C.stream(), tag=f"|b={r.numel() * r.element_size() + x.numel() * 4 + Cn * K * B * 4}"),
+                "mv_moe_lpx_fwd")
 
 
 def lpx_bwd(lib, r, x, coef, g_loss, g, Cn, K, B, dist, scale, rescale, mask_r):
@@ -46,7 +47,8 @@ def lpx_bwd(lib, r, x, coef, g_loss, g, Cn, K, B, dist, scale, rescale, mask_r):
                                        rescale, C.ptr(mask_r), C.stream()), "mv_moe_lpx_cat_bwd")
     else:
         C.check(lib.mv_moe_lpx_bwd(C.ptr(r), C.dtype_code(r), C.ptr(x), C.ptr(coef), C.ptr(g_loss), C.ptr(g), Cn, K, B, D, dist, scale,
-                                   rescale, C.ptr(mask_r), C.stream()), "mv_moe_lpx_bwd")
+                                   rescale, C.ptr(mask_r), C.stream(),
+                                   tag=f"|b={2 * r.numel() * r.element_size() + x.numel() * 4 + Cn * K * B * 4}"), "mv_moe_lpx_bwd")
 
 
 class MoEElboFn(torch.autograd.Function):

@@ -9,8 +9,9 @@ GEMM (csrc/gemm.cu) around the gather kernels of csrc/im2col.cu — no cuDNN, no
       weight gradient             dW += x^T im2col(dY)
       data gradient               dx = im2col(dY) W^T * relu'(x)                    [mask fused into the GEMM epilogue]
 
-Activations are dense NHWC bf16 matrices [n * H * W, C]; the patch matrices use (channel, tap) column order = the torch weight
-layout flattened, so weights are only cast (one pack launch per stack) and weight gradients land in `.grad` without permutes.
+Activations are dense NHWC bf16 matrices [n * H * W, C]; the patch matrices use tap-major columns (t*C + c: the channels of a
+pixel stay contiguous, so the gathers move 16-byte vectors), weights are re-laid out to that order while they are cast to bf16
+(mv_pack_tc, one launch per stack) and weight gradients return to the torch layout in one launch (mv_unpack_tc_add).
 These networks are < 10 MFLOP per sample: the step is bound by launches and HBM, not by the tensor pipe."""
 import torch
 
@@ -22,16 +23,43 @@ from .linear_native import _pack_weights, _pad8, _to_bf16_padded, gemm
 _ACT = {"none": 0, "relu": 1, "lrelu": 2, "sigmoid": 3}
 
 
-def _geom(n_img, H, W, Cc, nchw, k, s, p, gh, gw, ld):
+def _geom(n_img, H, W, Cc, nchw, k, s, p, gh, gw, ld, tc=True):
     g = C.ConvGeom()
     g.n_img, g.H, g.W, g.C, g.nchw = n_img, H, W, Cc, int(nchw)
-    g.kh, g.kw, g.stride, g.pad, g.grid_h, g.grid_w, g.ld = k, k, s, p, gh, gw, ld
+    g.kh, g.kw, g.stride, g.pad, g.grid_h, g.grid_w, g.ld, g.tc_order = k, k, s, p, gh, gw, ld, int(tc)
     return g
+
+
+def _tc_items(pairs):
+    """(fp32 [N, C, kh, kw] or [N, C, T] tensor, packed [N, ld] tensor) pairs -> PackItem array for mv_pack_tc / mv_unpack_tc_add."""
+    items = (C.PackItem * len(pairs))()
+    for it, (w, packed) in zip(items, pairs):
+        assert w.dtype == torch.float32 and w.is_contiguous() and packed.is_contiguous()
+        it.src, it.dst_fwd, it.dst_dgrad = w.data_ptr(), packed.data_ptr(), None
+        it.N, it.C, it.T = w.shape[0], w.shape[1], w[0, 0].numel()
+        it.Npad, it.Cpad = w.shape[0], packed.shape[1]
+    return items
+
+
+def pack_tc(weights):
+    """fp32 conv weights [N, C, kh, kw] -> bf16 [N, pad8(T*C)] with tap-major columns, all in one launch."""
+    outs = [torch.empty(w.shape[0], _pad8(w[0].numel()), device=w.device, dtype=torch.bfloat16) for w in weights]
+    C.check(C.lib().mv_pack_tc(_tc_items([(w.detach(), o) for w, o in zip(weights, outs)]), len(weights), C.stream()), "mv_pack_tc")
+    return outs
+
+
+def unpack_tc_add(pairs):
+    """grad[n, c, t] += dW[n, t*C + c] for every (dW fp32 [N, ld], grad fp32 [N, C, kh, kw]) pair in one launch."""
+    items = _tc_items([(g, d) for d, g in pairs])
+    for it, (d, g) in zip(items, pairs):
+        it.src, it.dst_fwd = d.data_ptr(), g.data_ptr()
+    C.check(C.lib().mv_unpack_tc_add(items, len(pairs), C.stream()), "mv_unpack_tc_add")
 
 
 def im2col(src, g):
     cols = torch.empty(g.n_img * g.grid_h * g.grid_w, g.ld, device=src.device, dtype=torch.bfloat16)
-    C.check(C.lib().mv_im2col(C.ptr(src), C.dtype_code(src), C.ptr(cols), g, C.stream()), "mv_im2col")
+    C.check(C.lib().mv_im2col(C.ptr(src), C.dtype_code(src), C.ptr(cols), g, C.stream(),
+                              tag=f"|b={cols.numel() * 2 + src.numel() * src.element_size()}"), "mv_im2col")
     return cols
 
 
@@ -39,7 +67,8 @@ def col2im(cols, g, bias=None, act="none", dact=None, dslope=0.0):
     shape = (g.n_img, g.C, g.H, g.W) if g.nchw else (g.n_img * g.H * g.W, g.C)
     dst = torch.empty(shape, device=cols.device, dtype=torch.bfloat16)
     C.check(C.lib().mv_col2im(C.ptr(cols), C.dtype_code(cols), C.ptr(dst), g, None if bias is None else C.ptr(bias), _ACT[act],
-                              None if dact is None else C.ptr(dact), float(dslope), C.stream()), "mv_col2im")
+                              None if dact is None else C.ptr(dact), float(dslope), C.stream(),
+                              tag=f"|b={cols.numel() * cols.element_size() + dst.numel() * (2 if dact is None else 4)}"), "mv_col2im")
     return dst
 
 
@@ -68,7 +97,7 @@ class ConvEncoderFn(torch.autograd.Function):
         hw = [(params[2 * nc + 2 * j], params[2 * nc + 2 * j + 1]) for j in range(n_heads)]
         B, Cc, H, W = x.shape
         x = x.detach().contiguous()
-        packs = _pack_weights([w.reshape(w.shape[0], -1) for w, _ in cw] + [[w.reshape(w.shape[0], -1) for w, _ in hw]])
+        packs = pack_tc([w for w, _ in cw] + [w for w, _ in hw])
         cur, nchw = x, True
         cols_l, acts_l, geoms = [], [], []
         for i, ((w, b), (k, s, p)) in enumerate(zip(cw, convs)):
@@ -82,12 +111,15 @@ class ConvEncoderFn(torch.autograd.Function):
             cur, nchw, H, W, Cc = h, False, Ho, Wo, N
         kh = hw[0][0].shape[2]
         assert kh == H and hw[0][0].shape[3] == W, "the heads must cover the whole final feature map"
-        gh = _geom(B, H, W, Cc, False, kh, 1, 0, 1, 1, _pad8(Cc * H * W))
-        cols_h = im2col(cur, gh)
-        Nh = sum(w.shape[0] for w, _ in hw)
+        Kh = Cc * H * W
+        assert Kh % 8 == 0
+        gh = _geom(B, H, W, Cc, False, kh, 1, 0, 1, 1, Kh)
+        cols_h = cur.view(B, Kh)   # tap-major columns of a full-map patch ARE the NHWC activation: no gather
+        Wh = torch.cat(packs[nc:], 0)
+        Nh = Wh.shape[0]
         out = torch.empty(B, Nh, device=x.device, dtype=torch.float32)
-        gemm(cols_h, packs[nc], B, Nh, Cc * H * W, out, bias=torch.cat([b.detach().float() for _, b in hw]).contiguous(), out_kind=1, tag="heads")
-        ctx.save_for_backward(*cols_l, *acts_l, cols_h, *packs)
+        gemm(cols_h, Wh, B, Nh, Kh, out, bias=torch.cat([b.detach().float() for _, b in hw]).contiguous(), out_kind=1, tag="heads")
+        ctx.save_for_backward(*cols_l, *acts_l, Wh, *packs[:nc])
         ctx.geoms, ctx.gh, ctx.spec, ctx.params = geoms, gh, spec, params
         ctx.head_widths = [w.shape[0] for w, _ in hw]
         return out
@@ -97,38 +129,44 @@ class ConvEncoderFn(torch.autograd.Function):
         convs, n_heads = ctx.spec
         nc = len(convs)
         sv = ctx.saved_tensors
-        cols_l, acts_l, cols_h, packs = sv[:nc], sv[nc:2 * nc], sv[2 * nc], sv[2 * nc + 1:]
+        cols_l, acts_l, Wh, packs = sv[:nc], sv[nc:2 * nc], sv[2 * nc], sv[2 * nc + 1:]
         dev = g_out.device
         params = ctx.params
         targets, acc = _grad_slots(params, dev, [p.numel() for p in params])
         B = g_out.shape[0]
         d = _to_bf16_padded(g_out)
         gh = ctx.gh
-        Kh = gh.C * gh.H * gh.W
+        Kh = gh.ld
+        cols_h = acts_l[nc - 1].view(B, Kh)
+        # weight gradients are produced in the packed (tap-major) layout and handed over in ONE launch at the end
+        wsz = [params[2 * i].numel() for i in range(nc + n_heads)]
+        warena = HL.ZeroArena(sum(wsz) + 8 * len(wsz), dev)
+        dWp = [warena.take(params[2 * i].shape[0], params[2 * i][0].numel()) for i in range(nc + n_heads)]
         r = 0
         for j, n in enumerate(ctx.head_widths):
             dj = d[:, r:r + n]
             if (dj.data_ptr() % 16) or (dj.stride(0) % 8):
                 dj = _to_bf16_padded(dj)
-            gemm(dj, cols_h, n, Kh, B, acc[2 * nc + 2 * j].view(n, Kh), a_mn=True, b_mn=True, out_kind=2, tag="heads.w")
+            gemm(dj, cols_h, n, Kh, B, dWp[nc + j], a_mn=True, b_mn=True, out_kind=2, tag="heads.w")
             if n % 8 == 0:
                 _colsum(dj, n, acc[2 * nc + 2 * j + 1])
             else:
                 acc[2 * nc + 2 * j + 1].add_(dj.float().sum(0))
             r += n
-        dcols = torch.empty(B, gh.ld, device=dev, dtype=torch.float32)   # fp32: the gather below sums unrounded partial products
-        gemm(d, packs[nc], B, Kh, d.shape[1], dcols[:, :Kh], b_mn=True, out_kind=1, tag="heads.d")
+        dcols = torch.empty(B, Kh, device=dev, dtype=torch.float32)   # fp32: the gather below sums unrounded partial products
+        gemm(d, Wh, B, Kh, d.shape[1], dcols, b_mn=True, out_kind=1, tag="heads.d")
         dpre = col2im(dcols, gh, dact=acts_l[nc - 1], dslope=0.0)
         for i in range(nc - 1, -1, -1):
             g = ctx.geoms[i]
             N, K = acts_l[i].shape[1], g.C * g.kh * g.kw
             P = dpre.shape[0]
-            gemm(dpre, cols_l[i], N, K, P, acc[2 * i].view(N, K), a_mn=True, b_mn=True, out_kind=2, tag=f"conv{i}.w")
+            gemm(dpre, cols_l[i], N, K, P, dWp[i], a_mn=True, b_mn=True, out_kind=2, tag=f"conv{i}.w")
             _colsum(dpre, N, acc[2 * i + 1])
             if i > 0 or ctx.needs_input_grad[0]:
                 dcols = torch.empty(P, g.ld, device=dev, dtype=torch.float32)
                 gemm(dpre, packs[i], P, K, N, dcols[:, :K], b_mn=True, out_kind=1, tag=f"conv{i}.d")
                 dpre = col2im(dcols, g, dact=acts_l[i - 1], dslope=0.0) if i > 0 else col2im(dcols, g)
+        unpack_tc_add([(dWp[i], acc[2 * i].view(params[2 * i].shape)) for i in range(nc + n_heads)])
         g_x = dpre.float() if ctx.needs_input_grad[0] else None   # gradient of the input image (NCHW), only when asked for
         grads = (None,) * len(params) if targets is not None else tuple(a.view(p.shape) for a, p in zip(acc, params))
         return (g_x, None) + grads
@@ -149,9 +187,9 @@ class ConvTDecoderFn(torch.autograd.Function):
         Bt = z.shape[0]
         dev = z.device
         zb = _to_bf16_padded(z)
-        packs = _pack_weights([w0.reshape(w0.shape[0], -1)] + [w.reshape(w.shape[0], -1) for w, _ in tw])
+        packs = _pack_weights([w0.reshape(w0.shape[0], -1)]) + pack_tc([w for w, _ in tw])
         F0 = C0 * H0 * W0
-        g0 = _geom(Bt, H0, W0, C0, False, H0, 1, 0, 1, 1, F0)
+        g0 = _geom(Bt, H0, W0, C0, False, H0, 1, 0, 1, 1, F0, tc=False)   # the first layer keeps the torch feature order (c, y, x)
         cols0 = torch.empty(Bt, F0, device=dev, dtype=torch.float32)
         if first == "convt":
             gemm(zb, packs[0], Bt, F0, z.shape[1], cols0, b_mn=True, out_kind=1, tag="dec0")
@@ -195,6 +233,9 @@ class ConvTDecoderFn(torch.autograd.Function):
         else:
             dpre = torch.empty(y.shape, device=dev, dtype=torch.bfloat16)
             C.check(lib.mv_act_bwd(C.ptr(gc), C.dtype_code(gc), C.ptr(y), C.ptr(dpre), y.numel(), _ACT[final_act], 0.0, C.stream()), "mv_act_bwd")
+        wsz = [params[2 + 2 * i].numel() for i in range(nt)]
+        warena = HL.ZeroArena(sum(wsz) + 8 * nt, dev)
+        dWp = [warena.take(params[2 + 2 * i].shape[0], params[2 + 2 * i][0].numel()) for i in range(nt)]
         for i in range(nt - 1, -1, -1):
             gm = ctx.geoms[i]
             Co, NT = gm.C, gm.C * gm.kh * gm.kw
@@ -205,10 +246,11 @@ class ConvTDecoderFn(torch.autograd.Function):
             else:
                 _colsum(dpre, Co, acc[3 + 2 * i])
             dcols = im2col(dpre, gm)
-            gemm(x_in, dcols, Cin, NT, P_in, acc[2 + 2 * i].view(Cin, NT), a_mn=True, b_mn=True, out_kind=2, tag=f"convt{i}.w")
+            gemm(x_in, dcols, Cin, NT, P_in, dWp[i], a_mn=True, b_mn=True, out_kind=2, tag=f"convt{i}.w")
             dx = torch.empty(P_in, Cin, device=dev, dtype=torch.bfloat16)
             gemm(dcols, packs[1 + i], P_in, Cin, NT, dx, dact=x_in, dslope=0.0, tag=f"convt{i}.d")
             dpre = dx
+        unpack_tc_add([(dWp[i], acc[2 + 2 * i].view(params[2 + 2 * i].shape)) for i in range(nt)])
         # first layer: dpre is the gradient of its pre-activation in NHWC [Bt * H0 * W0, C0]
         g0 = ctx.g0
         F0 = C0 * H0 * W0

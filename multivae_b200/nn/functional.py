@@ -3,7 +3,7 @@
 Two execution paths exist, selected per call by `backend()`:
   * "native": hand-written sm_100a kernels (tcgen05 GEMM / implicit-GEMM convolution with fused
     epilogues) reached through the C-ABI — the product path for the architectures it covers;
-  * "torch": ATen (cuBLAS/cuDNN) ops for architectures whose native kernels are not written yet.
+  * "torch": ATen (cuBLAS/cuDNN) ops: the fp32 path of the parity checks and CPU-side module handling.
     This is a *library* path on the GPU, never a CPU fallback of the fused ELBO kernels.
 """
 import os
@@ -49,7 +49,10 @@ def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0
 
 
 def backend_summary():
-    """Which implementation each layer family runs on (reported by bench.py)."""
+    """Which implementation each layer family runs on with bf16 compute (reported by bench.py)."""
     from . import resnet_native as RN
     return {"elbo": "native sm_100a kernels (C-ABI)", "resnet_decoder": RN.status("decoder"),
-            "resnet_encoder": RN.status("encoder"), "other_layers": "torch (cuDNN/cuBLAS library calls)"}
+            "resnet_encoder": RN.status("encoder"),
+            "mlp": "native sm_100a: tcgen05 GEMM fwd / dgrad / wgrad with fused bias + ReLU / Sigmoid (mv_gemm)",
+            "strided_and_transposed_conv": "native sm_100a: im2col / col2im gathers around the tcgen05 GEMM (mv_im2col, mv_col2im, mv_gemm)",
+            "fp32_path": "library layers (cuDNN / cuBLAS), used only by the fp32 parity checks"}

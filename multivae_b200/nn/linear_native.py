@@ -36,7 +36,10 @@ def gemm(A, B, M, N, K, out, *, a_mn=False, b_mn=False, bias=None, act="none", a
         a.dact, a.dact_ld, a.dslope = dact.data_ptr(), dact.stride(0), float(dslope)
     assert out.stride(-1) == 1 and out.dtype == (torch.bfloat16 if out_kind == 0 else torch.float32)
     a.out, a.out_ld, a.out_kind = out.data_ptr(), out.stride(0), out_kind
-    kw = {} if tag is None else {"tag": tag}
+    kw = {}
+    if tag is not None:   # algorithmic work of this launch for bench.py's roofline (flops; operand + result bytes)
+        ob = M * N * (2 if out_kind == 0 else (4 if out_kind == 1 else 8))
+        kw["tag"] = f"{tag}|f={2 * M * N * K}|b={2 * (M * K + N * K) + ob}"
     C.check(C.lib().mv_gemm(a, C.stream(), **kw), "mv_gemm")
     return out
 
@@ -74,7 +77,7 @@ def _pack_weights(weights):
     for i0 in range(0, len(specs), 24):   # MV_PACK_MAX_ITEMS per launch
         n = min(24, len(specs) - i0)
         sub = (C.PackItem * n)(*[items[i0 + j] for j in range(n)])
-        C.check(C.lib().mv_pack_conv_weights(sub, n, C.stream()), "mv_pack_conv_weights")
+        C.check(C.lib().mv_pack_tc(sub, n, C.stream()), "mv_pack_tc")   # T = 1: a cast (+ zero padding of K to a multiple of 8)
     return outs
 
 

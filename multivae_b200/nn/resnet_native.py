@@ -5,7 +5,7 @@ stack (3 ResnetBlocks, 2 nearest upsamplings, the image head) runs as hand-writt
 the C-ABI — mv_tapgemm (forward + data gradients), mv_wgrad (weight gradients) and the HBM-bound helpers
 of csrc/halo_ops.cu — on activations kept in the shared-halo NHWC bf16 layout; fp32 master weights are
 packed to bf16 tap-major matrices once per step.  The fully connected input layer (1.6 of 213 MFLOP per
-image) is a library GEMM whose permuted weight makes it emit the halo layout directly.
+image) runs on the general tcgen05 GEMM (mv_gemm); its permuted weight makes it emit the halo layout directly.
 
 There is no fallback inside this path: if the C-ABI library is missing, it raises.
 """
@@ -33,7 +33,7 @@ def use_native(x):
 
 
 def status(which):
-    return "native sm_100a: tcgen05 tap-GEMM conv fwd/dgrad + tcgen05 wgrad + halo kernels (fc: cuBLAS)"
+    return "native sm_100a: tcgen05 tap-GEMM conv fwd/dgrad + tcgen05 wgrad + halo kernels; fc layers on the tcgen05 GEMM (mv_gemm)"
 
 
 # ---- low-level wrappers over the helper kernels -------------------------------------------------
@@ -330,30 +330,42 @@ def _fc_perm(device):
 
 
 class FcHaloFn(torch.autograd.Function):
-    """fc of the decoder emitting the 7x7 halo matrix directly: rows of the weight are gathered into halo order
-    (zero rows at halo positions), so `z @ Wp^T + bp` IS the [n_img*64, 256] activation matrix.  Library GEMMs
-    (1.6 of 213 MFLOP per image); the backward gathers the real rows back (no scatter-add)."""
+    """fc of the decoder emitting the 7x7 halo matrix directly: rows of the weight are gathered into halo order (zero rows at
+    halo positions), so `z @ Wp^T + bp` IS the [n_img*64, 256] activation matrix.  Native GEMMs (mv_gemm: forward with the bias in
+    the epilogue, data gradient with W read MN-major, weight gradient with both operands MN-major); the backward gathers the real
+    rows back (no scatter-add)."""
 
     @staticmethod
     def forward(ctx, z, weight, bias):
+        from .linear_native import _to_bf16_padded, gemm
         gather, scatter = _fc_perm(z.device)
         w_ext = torch.cat([weight.detach(), weight.new_zeros(1, weight.shape[1])], 0).to(torch.bfloat16)
-        b_ext = torch.cat([bias.detach(), bias.new_zeros(1)], 0).to(torch.bfloat16)
-        wp = w_ext[gather]
-        zb = z.detach().to(torch.bfloat16)
-        h0 = torch.addmm(b_ext[gather], zb, wp.t())
+        b_ext = torch.cat([bias.detach().float(), bias.new_zeros(1, dtype=torch.float32)], 0)
+        wp = w_ext[gather]                      # [64*256, L] bf16, halo order
+        zb = _to_bf16_padded(z)
+        n, L = zb.shape
+        h0 = torch.empty(n, wp.shape[0], device=z.device, dtype=torch.bfloat16)
+        gemm(zb, wp, n, wp.shape[0], L, h0, bias=b_ext[gather].contiguous(), tag="dec.fc")
         ctx.save_for_backward(zb, wp)
         ctx.scatter = scatter
         return h0
 
     @staticmethod
     def backward(ctx, g):
+        from .linear_native import gemm
         zb, wp = ctx.saved_tensors
-        g = g.reshape(zb.shape[0], -1).to(torch.bfloat16)
-        gz = (g @ wp).float() if ctx.needs_input_grad[0] else None
-        gw = (g.t() @ zb).float()[ctx.scatter]
-        gb = g.sum(0, dtype=torch.float32)[ctx.scatter]   # fp32 accumulation straight from the bf16 rows (no fp32 copy of g)
-        return gz, gw, gb
+        n, L = zb.shape
+        F_ = wp.shape[0]
+        g = g.reshape(n, F_).to(torch.bfloat16).contiguous()
+        gz = None
+        if ctx.needs_input_grad[0]:
+            gz = torch.empty(n, L, device=g.device, dtype=torch.float32)
+            gemm(g, wp, n, L, F_, gz, b_mn=True, out_kind=1, tag="dec.fc.d")
+        gw = torch.zeros(F_, L, device=g.device, dtype=torch.float32)
+        gemm(g, zb, F_, L, n, gw, a_mn=True, b_mn=True, out_kind=2, tag="dec.fc.w")
+        gb = torch.zeros(F_, device=g.device, dtype=torch.float32)
+        C.check(C.lib().mv_colsum_any(g.data_ptr(), n, F_, F_, gb.data_ptr(), C.stream()), "mv_colsum_any")
+        return gz, gw[ctx.scatter], gb[ctx.scatter]
 
 
 def decoder_params(dec):
@@ -441,31 +453,40 @@ class EncoderStackFn(torch.autograd.Function):
 
 
 class FcFromHaloFn(torch.autograd.Function):
-    """The two Linear heads (mu, log-variance) on the flattened 7x7x256 activation kept in halo order: the weight
-    columns are gathered into halo order (zeros at halo positions) — library GEMMs, 0.4 % of the encoder's flops."""
+    """The two Linear heads (mu, log-variance) on the flattened 7x7x256 activation kept in halo order: the weight columns are
+    gathered into halo order (zeros at halo positions).  Native GEMMs (mv_gemm), fp32 outputs."""
 
     @staticmethod
     def forward(ctx, h, w_mu, b_mu, w_lv, b_lv):
+        from .linear_native import gemm
         gather, scatter = _fc_perm(h.device)
         n_img = h.shape[0] // 64
         w = torch.cat([w_mu.detach(), w_lv.detach()], 0)
         wp = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).to(torch.bfloat16)[:, gather].contiguous()   # [2L, 16384]
         h2 = h.reshape(n_img, 64 * 256)
-        out = (h2 @ wp.t()).float() + torch.cat([b_mu.detach(), b_lv.detach()]).float()
+        N = wp.shape[0]
+        out = torch.empty(n_img, N, device=h.device, dtype=torch.float32)
+        gemm(h2, wp, n_img, N, 64 * 256, out, bias=torch.cat([b_mu.detach(), b_lv.detach()]).float().contiguous(), out_kind=1, tag="enc.fc")
         ctx.save_for_backward(h2, wp)
         ctx.scatter, ctx.split = scatter, w_mu.shape[0]
         return out[:, : w_mu.shape[0]].contiguous(), out[:, w_mu.shape[0]:].contiguous()
 
     @staticmethod
     def backward(ctx, g_mu, g_lv):
+        from .linear_native import _to_bf16_padded, gemm
         h2, wp = ctx.saved_tensors
+        n, F_ = h2.shape
+        N = wp.shape[0]
         g = torch.cat([g_mu, g_lv], 1)
         gb = g.sum(0, dtype=torch.float32)
-        g16 = g.to(torch.bfloat16)
-        gw = (g16.t() @ h2).float()[:, ctx.scatter]
-        gh = (g16 @ wp).reshape(-1, 256)
+        g16 = _to_bf16_padded(g)
+        gw = torch.zeros(N, F_, device=g.device, dtype=torch.float32)
+        gemm(g16, h2, N, F_, n, gw, a_mn=True, b_mn=True, out_kind=2, tag="enc.fc.w")
+        gh = torch.empty(n, F_, device=g.device, dtype=torch.bfloat16)
+        gemm(g16, wp, n, F_, N, gh, b_mn=True, tag="enc.fc.d")
+        gw = gw[:, ctx.scatter]
         k = ctx.split
-        return gh, gw[:k], gb[:k], gw[k:], gb[k:]
+        return gh.reshape(-1, 256), gw[:k], gb[:k], gw[k:], gb[k:]
 
 
 def encoder_params(enc, tag):

@@ -2,6 +2,8 @@
 formulas are the ones stated in DESIGN.md.  Tensor-core kernels count USEFUL flops (real pixels only — the
 halo rows the kernels also multiply are overhead, not work)."""
 
+RIDGE_FLOP_PER_BYTE = 208.0   # measured sustained bf16 peak / measured HBM copy bandwidth (MEASURED_PEAKS.json)
+
 # decoder layer tags (multivae_b200/nn/resnet_native.py) -> (H, Cin, Cout, taps)
 _DEC_LAYERS = {
     "b1.sc": (7, 256, 128, 1), "b1.c0": (7, 256, 128, 9), "b1.c1": (7, 128, 128, 9),
@@ -28,6 +30,13 @@ def _layer(tag):
 def describe(name, *, B, M, K, D, L, LW):
     """name = C-ABI symbol (optionally ':tag').  Returns {"bound", "work" (bytes or flops per launch)}."""
     sym, _, tag = name.partition(":")
+    if "|" in tag:   # the wrapper stated this launch's work itself: "<layer>|f=<flops>|b=<bytes>"
+        kv = dict(p.split("=") for p in tag.split("|")[1:])
+        f, b = float(kv.get("f", 0)), float(kv.get("b", 0))
+        # a contraction whose arithmetic intensity is below the ridge (~208 flop/B on this part) is an HBM kernel
+        if f > 0 and b > 0 and f / b >= RIDGE_FLOP_PER_BYTE:
+            return {"bound": "tensor", "work": f, "bytes": b}
+        return {"bound": "hbm", "work": b, "flops": f}
     rows = M * K * B  # (cond modality, importance sample, batch sample) rows of one reconstructed modality
     if sym in ("mv_tapgemm", "mv_wgrad") and _layer(tag):
         H, cin, cout, taps = _layer(tag)

@@ -84,6 +84,19 @@ def run_port(spec, rec, dtype=torch.float32, want_grads=True, details=None):
     for k in p:  # frozen prior parameters (requires_grad=False in the reference model)
         if "prior" in k and rec["grads"].get(k, 1) is None:
             p[k].requires_grad_(False)
+    loss, loss_sum, metrics = _forward(spec, rec, p, dtype, details)
+    if want_grads:
+        loss.backward()
+    return loss, loss_sum, metrics, p
+
+
+def run_port_with_params(spec, rec, p, dtype=torch.float32):
+    """One forward pass of the port on the caller's parameter dict (bench.py's CPU baseline keeps the parameters and an optimizer
+    across steps); rec needs "noise" only.  Returns the loss."""
+    return _forward(spec, rec, p, dtype, None)[0]
+
+
+def _forward(spec, rec, p, dtype, details):
     data, masks = make_data(spec)
     data = {k: v.to(dtype) for k, v in data.items()}
     noise_l = [e.to(dtype) for e in rec["noise"]]
@@ -131,6 +144,4 @@ def run_port(spec, rec, dtype=torch.float32, want_grads=True, details=None):
                                                   beta_style=cfg.get("beta_style", 1.0))
     else:
         raise ValueError(model)
-    if want_grads:
-        loss.backward()
-    return loss, loss_sum, metrics, p
+    return loss, loss_sum, metrics
