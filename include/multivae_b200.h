@@ -117,13 +117,15 @@ int mv_gauss_kl_bwd(const float* mu, const float* lv, const float* prior_mu, con
  * Outputs: lw, wk, coef [C,K,B]; loss_b [B] (per-sample loss, already negated and divided by n_mods);
  *   unit gradients (for d loss = 1): g_u [C,K,B,L], g_w [C,K,B,Lw] (direct terms only, NOT yet multiplied
  *   by the DReG wk); g_mu_u,g_sig_u [C,B,L], g_mu_w,g_sig_w [C,B,Lw] (zero-filled when detach_post != 0);
- *   g_pz_std [B,L+Lw] per-sample partials of d loss / d prior std. */
+ *   g_pz_std [B,L+Lw] per-sample partials of d loss / d prior std.
+ * skip_u_prior != 0 leaves log p(u) out of lw (and of g_u / g_pz_std): CMVAE's mixture-of-clusters prior over the shared code is
+ * added by the caller through `lpx` (cmvae_model.py:305-340); the private code keeps the fixed prior pz[L:]. */
 int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, const float* sig_u, const float* mu_w,
                   const float* sig_w, const float* pz_mean, const float* pz_std, const float* lpx,
                   const uint8_t* masks, float* lw, float* wk, float* coef, float* loss_b, float* g_u,
                   float* g_w, float* g_mu_u, float* g_sig_u, float* g_mu_w, float* g_sig_w, float* g_pz_std,
                   int C, int K, int B, int L, int Lw, int latent_kind, int loss_kind, float beta,
-                  int detach_post, void* stream);
+                  int detach_post, int skip_u_prior, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused posterior aggregation, PoE family (MVTCAE, MVAE, MoPoE).
@@ -162,7 +164,7 @@ int mv_poe_bwd(const float* mu, const float* lv, const uint8_t* masks, const uin
  * mv_tapgemm:  out[p, n] = epilogue( sum_t sum_c A[p + tap_off[t], c] * Wt[t*N_total + n, c] )
  *   Replaces (forward and data-gradient) nn.Conv2d 3x3 / 1x1 and nn.Linear of models/nn/mmnist.py:214-366
  *   (ResnetBlock :229-241, fc :289-295,339, conv_img :287,352-354) and default_architectures.py:31-39,237-241.
- *   epilogue:  y = act(acc + bias[n]);  if dact1: y *= (dact1[p,n] > 0 ? 1 : slope1)
+ *   epilogue:  y = act(acc + bias[n]);  if dact1 / dmask1: y *= (dact1[p,n] > 0 ? 1 : slope1)
  *              if out2 && out2_pre: out2[p,n] = y
  *              o = alpha*y + (res ? res[p,n] : 0);  out[p,n] = o
  *              if out2 && !out2_pre: out2[p,n] = alpha2 * o * (dact2 ? (dact2[p,n] > 0 ? 1 : slope2) : 1)
@@ -194,7 +196,11 @@ typedef struct mv_tapgemm_args {
    *   dmask2     read INSTEAD of dact2: the second output is alpha2 * o * (bit ? 1 : slope2); N_total = 64 only */
   void* out2_mask;
   const void* dmask2;
-  const void* dmask1;   /* read INSTEAD of dact1 (y *= bit ? 1 : slope1); 3x3 / 64-output layers only */
+  const void* dmask1;   /* read INSTEAD of dact1 (y *= bit ? 1 : slope1); 64-output layers only */
+  /* res_mask (3x3 / 64-output layers only): the residual is read as res[p, n] * (bit n of res_mask[p] ? res_scale_pos : res_scale_neg).
+   * Lets a producer store ONE tensor t = a * g * lrelu'(d) and the consumer recover g = t / (a * lrelu'(d)) from d's sign bits
+   * (the image head's data gradient writes only the pre-scaled gradient; the block's skip connection un-scales it here). */
+  const void* res_mask; float res_scale_pos, res_scale_neg;
 } mv_tapgemm_args;
 int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 

@@ -1,8 +1,10 @@
-"""multivae_b200 — B200-native training step for multimodal VAEs (MMVAE+, MMVAE, MoPoE, MVAE, MVTCAE)
+"""multivae_b200 — B200-native training step for multimodal VAEs (MMVAE+, MMVAE, MoPoE, MVAE, MVTCAE, CMVAE, CRMVAE)
 behind MultiVae's `Model(config, encoders, decoders).forward(inputs) -> ModelOutput` API."""
 from .configs import (  # noqa: F401
     BaseAEConfig,
     BaseMultiVAEConfig,
+    CMVAEConfig,
+    CRMVAEConfig,
     MMVAEConfig,
     MMVAEPlusConfig,
     MoPoEConfig,
@@ -17,6 +19,8 @@ from .containers import (  # noqa: F401
     set_inputs_to_device,
 )
 from .base import BaseMultiVAE  # noqa: F401
+from .cmvae import CMVAE  # noqa: F401
+from .crmvae import CRMVAE  # noqa: F401
 from .mmvae import MMVAE  # noqa: F401
 from .mmvae_plus import MMVAEPlus  # noqa: F401
 from .mopoe import MoPoE  # noqa: F401

@@ -38,6 +38,7 @@ class TapGemmArgs(ctypes.Structure):
         ("img_stride", ctypes.c_int32), ("Wp", ctypes.c_int32), ("W", ctypes.c_int32), ("H", ctypes.c_int32),
         ("n_img", ctypes.c_int32), ("out_mode", ctypes.c_int32), ("n_valid", ctypes.c_int32),
         ("out2_mask", c_void_p), ("dmask2", c_void_p), ("dmask1", c_void_p),
+        ("res_mask", c_void_p), ("res_scale_pos", c_float), ("res_scale_neg", c_float),
     ]
 
 
@@ -85,7 +86,7 @@ _PROTOS = {
     "mv_logmeanexp": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "mv_gauss_kl_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     "mv_gauss_kl_bwd": [c_void_p] * 9 + [c_int64, c_int, c_int, c_void_p],
-    "mv_moe_lw_fwd": [c_void_p] * 21 + [c_int] * 7 + [c_float, c_int, c_void_p],
+    "mv_moe_lw_fwd": [c_void_p] * 21 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p],
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "mv_tapgemm": [ctypes.POINTER(TapGemmArgs), c_void_p],

@@ -126,3 +126,27 @@ class MVAEConfig(BaseMultiVAEConfig):
 class MVTCAEConfig(BaseMultiVAEConfig):
     alpha: float = 0.1
     beta: float = 2.5
+
+
+@dataclass
+class CRMVAEConfig(BaseMultiVAEConfig):
+    beta: float = 2.5
+
+
+@dataclass
+class CMVAEConfig(BaseMultiVAEConfig):
+    K: int = 10
+    prior_and_posterior_dist: str = "laplace_with_softmax"
+    learn_modality_prior: bool = True
+    beta: float = 1.0
+    modalities_specific_dim: int = None
+    reconstruction_option: str = "joint_prior"
+    loss: str = "dreg_looser"
+    number_of_clusters: int = 10
+
+    def __post_init__(self):
+        super().__post_init__()
+        _choice("prior_and_posterior_dist", self.prior_and_posterior_dist,
+                ("laplace_with_softmax", "normal_with_softplus", "normal"))
+        _choice("loss", self.loss, ("iwae_looser", "dreg_looser"))
+        _choice("reconstruction_option", self.reconstruction_option, ("single_prior", "joint_prior"))

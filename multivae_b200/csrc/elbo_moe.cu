@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
     const uint8_t* __restrict__ masks, float* __restrict__ lw, float* __restrict__ wk, float* __restrict__ coef,
     float* __restrict__ loss_b, float* __restrict__ g_u, float* __restrict__ g_w, float* __restrict__ g_mu_u,
     float* __restrict__ g_sig_u, float* __restrict__ g_mu_w, float* __restrict__ g_sig_w, float* __restrict__ g_pz_std,
-    int C, int K, int B, int L, int Lw, int loss_kind, float beta, int detach_post) {
+    int C, int K, int B, int L, int Lw, int loss_kind, float beta, int detach_post, int skip_u_prior) {
   const int lane = threadIdx.x & 31;
   // one warp per (conditioning modality c, sample b): C times the parallelism of a warp per sample.  What the C warps of a
   // sample share (its loss, the prior-scale gradient, the posterior-parameter gradients of all modalities through the MoE
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
         for (int m = 0; m < kMaxC; ++m) lq[m] = 0.f;
         for (int l = lane; l < L; l += 32) {
           const float uu = u[row * L + l];
-          lpz += lat_lp<KIND>(uu, pz_mean[l], pz_std[l]);
+          if (!skip_u_prior) lpz += lat_lp<KIND>(uu, pz_mean[l], pz_std[l]);
 #pragma unroll
           for (int m = 0; m < kMaxC; ++m)
             if (m < C && avail[m])
@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
       for (int l = lane; l < L; l += 32) {
         const float uu = u[row * L + l];
         const float pm = pz_mean[l], ps = pz_std[l];
-        float gu = lat_dx<KIND>(uu, pm, ps);
-        atomicAdd(g_pz_std + int64_t(b) * LT + l, cb * lat_ds<KIND>(uu, pm, ps));
+        float gu = skip_u_prior ? 0.f : lat_dx<KIND>(uu, pm, ps);
+        if (!skip_u_prior) atomicAdd(g_pz_std + int64_t(b) * LT + l, cb * lat_ds<KIND>(uu, pm, ps));
 #pragma unroll
         for (int m = 0; m < kMaxC; ++m)
           if (m < C && avail[m]) {
@@ -731,7 +731,7 @@ extern "C" int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, 
                              const uint8_t* masks, float* lw, float* wk, float* coef, float* loss_b, float* g_u,
                              float* g_w, float* g_mu_u, float* g_sig_u, float* g_mu_w, float* g_sig_w, float* g_pz_std,
                              int C, int K, int B, int L, int Lw, int latent_kind, int loss_kind, float beta,
-                             int detach_post, void* stream) {
+                             int detach_post, int skip_u_prior, void* stream) {
   MV_CHECK_ARG(u && mu_u && sig_u && pz_mean && pz_std && lpx && lw && wk && coef && loss_b && g_u && g_mu_u &&
                    g_sig_u && g_pz_std, "mv_moe_lw_fwd: null pointer");
   MV_CHECK_ARG(Lw == 0 || (w && mu_w && sig_w && g_w && g_mu_w && g_sig_w), "mv_moe_lw_fwd: null private-latent pointer");
@@ -750,9 +750,9 @@ extern "C" int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, 
   }
   const int blocks = (C * B + 3) / 4;   // one warp per (conditioning modality, sample)
   if (latent_kind == MV_LATENT_LAPLACE)
-    moe_lw_kernel<MV_LATENT_LAPLACE><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post);
+    moe_lw_kernel<MV_LATENT_LAPLACE><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post, skip_u_prior);
   else if (latent_kind == MV_LATENT_NORMAL)
-    moe_lw_kernel<MV_LATENT_NORMAL><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post);
+    moe_lw_kernel<MV_LATENT_NORMAL><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post, skip_u_prior);
   else {
     mv::set_error("mv_moe_lw_fwd: unknown latent kind %d", latent_kind);
     return MV_ERR_UNSUPPORTED;

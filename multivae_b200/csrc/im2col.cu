@@ -169,6 +169,70 @@ __global__ void __launch_bounds__(256) col2im_vec_kernel(const TC* __restrict__ 
   }
 }
 
+// Few-channel tensors (the 3-channel images at either end of the networks, NCHW or NHWC), tap-major columns: one thread per
+// (patch row, tap) resp. per pixel, looping over the channels, so the index arithmetic (32-bit) is paid once per pixel and the
+// tap loops only visit the taps that can contribute (ky = (y + pad) mod stride, +stride, ...).
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_pix_kernel(const T* __restrict__ src, bf16* __restrict__ cols, const ConvGeom g) {
+  const int T_ = g.kh * g.kw;
+  const int64_t total = int64_t(g.n_img) * g.Gh * g.Gw * T_;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += int64_t(gridDim.x) * blockDim.x) {
+    const int t = int(e % T_);
+    const int row = int(e / T_);
+    const int ky = t / g.kw, kx = t - ky * g.kw;
+    const int gx = row % g.Gw;
+    const int r2 = row / g.Gw;
+    const int gy = r2 % g.Gh, n = r2 / g.Gh;
+    const int y = gy * g.stride - g.pad + ky, x = gx * g.stride - g.pad + kx;
+    const bool in = y >= 0 && y < g.H && x >= 0 && x < g.W;
+    const T* sp = src + n * g.sn + y * g.sy + x * g.sx;
+    bf16* cp = cols + int64_t(row) * g.ld + t * g.C;
+    for (int c = 0; c < g.C; ++c) cp[c] = __float2bfloat16_rn(in ? Vec<T>::load1(sp + c * g.sc) : 0.f);
+    if (t == T_ - 1)
+      for (int c = g.C * T_; c < g.ld; ++c) cols[int64_t(row) * g.ld + c] = __float2bfloat16_rn(0.f);
+  }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(256) col2im_pix_kernel(const TC* __restrict__ cols, bf16* __restrict__ dst, const ConvGeom g,
+                                                         const float* __restrict__ bias, int act, const bf16* __restrict__ dact,
+                                                         float dslope) {
+  const int total = g.n_img * g.H * g.W;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int x = e % g.W;
+    const int r = e / g.W;
+    const int y = r % g.H, n = r / g.H;
+    float acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = (bias && c < g.C) ? bias[c] : 0.f;
+    for (int ky = (y + g.pad) % g.stride; ky < g.kh; ky += g.stride) {
+      const int gy = (y + g.pad - ky) / g.stride;
+      if (y + g.pad - ky < 0) break;
+      if (gy >= g.Gh) continue;
+      for (int kx = (x + g.pad) % g.stride; kx < g.kw; kx += g.stride) {
+        const int gx = (x + g.pad - kx) / g.stride;
+        if (x + g.pad - kx < 0) break;
+        if (gx >= g.Gw) continue;
+        const TC* p = cols + (int64_t(n * g.Gh + gy) * g.Gw + gx) * g.ld + (ky * g.kw + kx) * g.C;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < g.C) acc[c] += Vec<TC>::load1(p + c);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= g.C) break;
+      float v = acc[c];
+      if (act == MV_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == MV_ACT_LRELU02) v = fmaxf(v, 0.2f * v);
+      else if (act == MV_ACT_SIGMOID) v = 1.f / (1.f + expf(-v));
+      const int64_t o = n * g.sn + y * g.sy + x * g.sx + c * g.sc;
+      if (dact) v *= __bfloat162float(dact[o]) > 0.f ? 1.f : dslope;
+      dst[o] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // Weight hand-over for the (tap, channel) column order, all layers of a network in one launch:
 //   pack:    dst bf16 [N][ld], dst[n, t*C + c] = src fp32 [N][C][T]   (columns >= T*C zero)
 //   unpack:  dst fp32 [N][C][T] += src fp32 [N][ld][t*C + c]
@@ -263,6 +327,11 @@ extern "C" int mv_im2col(const void* src, int src_dtype, void* cols, const mv_co
     const int64_t tv = total / 8;
     const int vb = int(std::min<int64_t>((tv + 255) / 256, int64_t(num_sms()) * 16));
     im2col_vec_kernel<<<vb, 256, 0, st>>>(static_cast<const bf16*>(src), static_cast<bf16*>(cols), g);
+  } else if (g.tc && g.C <= 4 && (src_dtype == MV_F32 || src_dtype == MV_BF16)) {
+    const int64_t tp = int64_t(g.n_img) * g.Gh * g.Gw * g.kh * g.kw;
+    const int pb = int(std::min<int64_t>((tp + 255) / 256, int64_t(num_sms()) * 16));
+    if (src_dtype == MV_F32) im2col_pix_kernel<float><<<pb, 256, 0, st>>>(static_cast<const float*>(src), static_cast<bf16*>(cols), g);
+    else im2col_pix_kernel<bf16><<<pb, 256, 0, st>>>(static_cast<const bf16*>(src), static_cast<bf16*>(cols), g);
   } else if (src_dtype == MV_F32) im2col_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(src), static_cast<bf16*>(cols), g);
   else if (src_dtype == MV_BF16) im2col_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(src), static_cast<bf16*>(cols), g);
   else {
@@ -293,6 +362,15 @@ extern "C" int mv_col2im(const void* cols, int cols_dtype, void* dst, const mv_c
                                                    static_cast<const bf16*>(dact), dslope);
     else
       col2im_vec_kernel<bf16><<<vb, 256, 0, st>>>(static_cast<const bf16*>(cols), static_cast<bf16*>(dst), g, bias, act,
+                                                  static_cast<const bf16*>(dact), dslope);
+  } else if (g.tc && g.C <= 4 && (cols_dtype == MV_F32 || cols_dtype == MV_BF16) && int64_t(g.n_img) * g.H * g.W < (int64_t(1) << 31)) {
+    const int64_t npix = int64_t(g.n_img) * g.H * g.W;
+    const int pb = int(std::min<int64_t>((npix + 255) / 256, int64_t(num_sms()) * 16));
+    if (cols_dtype == MV_F32)
+      col2im_pix_kernel<float><<<pb, 256, 0, st>>>(static_cast<const float*>(cols), static_cast<bf16*>(dst), g, bias, act,
+                                                   static_cast<const bf16*>(dact), dslope);
+    else
+      col2im_pix_kernel<bf16><<<pb, 256, 0, st>>>(static_cast<const bf16*>(cols), static_cast<bf16*>(dst), g, bias, act,
                                                   static_cast<const bf16*>(dact), dslope);
   } else if (cols_dtype == MV_F32)
     col2im_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(cols), static_cast<bf16*>(dst), g, bias, act,

@@ -40,7 +40,7 @@ constexpr int kC3MaxSide = 4;
 constexpr int kC3N = 192;
 constexpr uint32_t kC3WBox = 192u * 128u;   // one filter row of weights: 3 taps x 64 output channels x 64 input channels
 
-enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_DMASK1 = 32, C3_GENERIC = 0x80000000u };
+enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_DMASK1 = 32, C3_RESMASK = 64, C3_GENERIC = 0x80000000u };
 
 struct Conv3Params {
   int P, m_tiles, n_kc, row_shift, R;
@@ -50,6 +50,8 @@ struct Conv3Params {
   float neg, alpha, slope1;
   const uint64_t* dmask1;   // C3_DMASK1: sign bits of the activation-derivative source (instead of a bf16 side tile)
   uint64_t* mask2;          // C3_MASK2: sign bits of the activation, one 64-bit word per row (rows padded to whole tiles)
+  const uint64_t* rmask;    // C3_RESMASK: the residual is scaled by rs_pos / rs_neg according to these sign bits
+  float rs_pos, rs_neg;
   int inplace;              // first output written in place over the side tile (released by the group leader after the TMA store)
   int side_stages, n_stg;   // side-tile ring depth; staging tiles per epilogue group (outputs not written in place)
   int img_stride, Wp, W, n_img;
@@ -261,6 +263,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t out2_tile = (kInPlace && has_side) ? stg_s : stg_s + 16384u;
       unsigned long long dm = 0ull;   // this row's 64 sign bits: in flight while the MMAs of the tile still run
       if (c3_has<F>(p, C3_DMASK1) && inner && row < p.P) dm = p.dmask1[row];
+      if (c3_has<F>(p, C3_RESMASK) && inner && row < p.P) dm = p.rmask[row];   // (never together with C3_DMASK1)
       tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
 #pragma unroll
@@ -381,7 +384,14 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int i = 0; i < 8; ++i) o2[i] = pack_bf16(ia * y[2 * i], ia * y[2 * i + 1]);
         }
-        if (c3_has<F>(p, C3_RES)) {
+        if (c3_has<F>(p, C3_RES) && c3_has<F>(p, C3_RESMASK)) {
+          const uint32_t m16 = uint32_t(dm >> c0) & 0xffffu;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float s0 = vz * (((m16 >> (2 * i)) & 1u) ? p.rs_pos : p.rs_neg), s1 = vz * (((m16 >> (2 * i + 1)) & 1u) ? p.rs_pos : p.rs_neg);
+            o[i] = pack_bf16(fmaf(s0, bf16lo(sv[i]), y[2 * i]), fmaf(s1, bf16hi(sv[i]), y[2 * i + 1]));
+          }
+        } else if (c3_has<F>(p, C3_RES)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = pack_bf16(y[2 * i] + vz * bf16lo(sv[i]), y[2 * i + 1] + vz * bf16hi(sv[i]));
         } else {
@@ -680,6 +690,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   if (a->out2 && !a->out2_pre) return MV_OK;
   if (a->res && a->dact1) return MV_OK;
   if (a->dmask1 && a->dact1) return MV_OK;
+  if (a->res_mask && (!a->res || a->dmask1)) return MV_OK;
   if (a->dact2) return MV_OK;
   auto tma_ok = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 8 == 0); };
   if (!tma_ok(a->out, a->out_ld) || (a->out2 && !tma_ok(a->out2, a->out2_ld))) return MV_OK;
@@ -730,7 +741,9 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.slope1 = a->slope1;
   p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.n_img = a->n_img;
   p.flags = (a->bias ? C3_BIAS : 0u) | (a->res ? C3_RES : 0u) | (a->dact1 ? C3_DACT1 : 0u) | (a->out2 ? C3_OUT2 : 0u) |
-            (a->out2_mask ? C3_MASK2 : 0u) | (a->dmask1 ? C3_DMASK1 : 0u);
+            (a->out2_mask ? C3_MASK2 : 0u) | (a->dmask1 ? C3_DMASK1 : 0u) | (a->res_mask ? C3_RESMASK : 0u);
+  p.rmask = static_cast<const uint64_t*>(a->res_mask);
+  p.rs_pos = a->res_scale_pos; p.rs_neg = a->res_scale_neg;
   p.dmask1 = static_cast<const uint64_t*>(a->dmask1);
   p.mask2 = static_cast<uint64_t*>(a->out2_mask);
 
@@ -778,6 +791,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     case C3_DMASK1: MV_C3_LAUNCH(C3_DMASK1); break;
     case C3_BIAS | C3_MASK2: MV_C3_LAUNCH(C3_BIAS | C3_MASK2); break;
     case C3_RES: MV_C3_LAUNCH(C3_RES); break;
+    case C3_RES | C3_RESMASK: MV_C3_LAUNCH(C3_RES | C3_RESMASK); break;
     default: MV_C3_LAUNCH(C3_GENERIC); break;
   }
 #undef MV_C3_LAUNCH

@@ -98,7 +98,7 @@ constexpr int kThreads = 384;
 // Epilogue variants are compile-time flag sets (the runtime-flag version cost ~90 instructions per column).
 enum : uint32_t {
   EF_BIAS = 1, EF_RES = 2, EF_DACT1 = 4, EF_OUT2_PRE = 8, EF_OUT2_POST = 16, EF_DACT2 = 32, EF_SIGMOID = 64,
-  EF_NCHW = 128, EF_DMASK2 = 256, EF_GENERIC = 0x80000000u
+  EF_NCHW = 128, EF_DMASK2 = 256, EF_DMASK1 = 512, EF_GENERIC = 0x80000000u
 };
 template <uint32_t F>
 __device__ __forceinline__ bool has(const TapGemmParams& p, uint32_t bit) {
@@ -164,6 +164,11 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
         unpack8(side_vec(p, side_tile, 1, cb + g * 8, n + g * 8, r), d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
+      }
+      if (has<F>(p, EF_DMASK1)) {
+        const uint32_t m8 = (mask_word >> (g * 8)) & 0xffu;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] *= ((m8 >> e) & 1u) ? 1.f : p.slope1;
       }
       if (has<F>(p, EF_OUT2_PRE)) {
 #pragma unroll
@@ -472,7 +477,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
       // sign-mask word of this row: requested before the wait so that the L2 round trip hides behind the tile's MMAs
       unsigned long long mask_row = 0ull;
-      if ((p.epi_flags & EF_DMASK2) && r.valid) mask_row = p.dmask2[r.row];
+      if ((p.epi_flags & (EF_DMASK2 | EF_DMASK1)) && r.valid) mask_row = p.dmask2[r.row];
       tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
       for (int sub = 0; sub < nsub; ++sub) {
@@ -494,6 +499,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     case EF_RES: EPI(EF_RES); break;                                                    \
     case EF_OUT2_POST | EF_DACT2: EPI(EF_OUT2_POST | EF_DACT2); break;                  \
     case EF_OUT2_POST | EF_DMASK2: EPI(EF_OUT2_POST | EF_DMASK2); break;                \
+    case EF_DMASK1: EPI(EF_DMASK1); break;                                              \
     case EF_BIAS | EF_NCHW: EPI(EF_BIAS | EF_NCHW); break;                              \
     default: EPI(EF_GENERIC); break;                                                    \
   }
@@ -658,10 +664,12 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   p.epi_flags = (a->bias ? EF_BIAS : 0u) | (a->res ? EF_RES : 0u) | (a->dact1 ? EF_DACT1 : 0u) |
                 ((a->out2 && a->out2_pre) ? EF_OUT2_PRE : 0u) | ((a->out2 && !a->out2_pre) ? EF_OUT2_POST : 0u) |
                 ((a->out2 && !a->out2_pre && a->dact2) ? EF_DACT2 : 0u) | (a->act == MV_ACT_SIGMOID ? EF_SIGMOID : 0u) |
-                (a->out_mode == 1 ? EF_NCHW : 0u) | ((a->out2 && !a->out2_pre && a->dmask2) ? EF_DMASK2 : 0u);
-  p.dmask2 = static_cast<const unsigned long long*>(a->dmask2);
+                (a->out_mode == 1 ? EF_NCHW : 0u) | ((a->out2 && !a->out2_pre && a->dmask2) ? EF_DMASK2 : 0u) |
+                (a->dmask1 ? EF_DMASK1 : 0u);
+  p.dmask2 = static_cast<const unsigned long long*>(a->dmask2 ? a->dmask2 : a->dmask1);   // one sign-mask word per row, either use
   MV_CHECK_ARG(!a->dmask2 || (a->N_total == 64 && !a->dact2), "mv_tapgemm: dmask2 needs N_total = 64 and no dact2");
-  MV_CHECK_ARG(!a->dmask1, "mv_tapgemm: dmask1 is only available for 3x3 convolutions with 64 outputs in the halo layout");
+  MV_CHECK_ARG(!a->dmask1 || (a->N_total == 64 && !a->dact1 && !a->dmask2), "mv_tapgemm: dmask1 needs N_total = 64, no dact1 and no dmask2");
+  MV_CHECK_ARG(!a->res_mask, "mv_tapgemm: res_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   MV_CHECK_ARG(!a->out2_mask, "mv_tapgemm: out2_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   CUtensorMap tmA, tmW;
   const CUtensorMapSwizzle sw = CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;

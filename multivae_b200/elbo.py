@@ -72,6 +72,9 @@ class MoEElboFn(torch.autograd.Function):
             w, mu_w, sig_w = _f32c(w), _f32c(mu_w), _f32c(sig_w)
         masks = meta.get("masks")
         lpx = torch.empty(Cn, K, B, device=dev, dtype=torch.float32)
+        extra = None
+        if meta.get("has_extra"):
+            recons, extra = recons[:-1], recons[-1]
         recons = [r.contiguous() for r in recons]
         xs = meta["x"]
         for r, x in zip(recons, xs):
@@ -90,6 +93,8 @@ class MoEElboFn(torch.autograd.Function):
                 dist, scale, rescale, mrow = meta["recon"][i]
                 mask_r = None if masks is None else masks[mrow]
                 lpx_fwd(lib, r, x, lpx, Cn, K, B, dist, scale, rescale, mask_r, i > 0)
+        if meta.get("has_extra"):   # an additive per-(c, k, b) log-weight term computed by the caller (CMVAE's cluster-mixture prior)
+            lpx = lpx + _f32c(extra)
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         lw, wk, coef, loss_b = f(Cn, K, B), f(Cn, K, B), f(Cn, K, B), f(B)
         g_u, g_mu_u, g_sig_u = f(Cn, K, B, L), f(Cn, B, L), f(Cn, B, L)
@@ -102,7 +107,7 @@ class MoEElboFn(torch.autograd.Function):
                                   C.ptr(wk), C.ptr(coef), C.ptr(loss_b), C.ptr(g_u), C.ptr(g_w), C.ptr(g_mu_u),
                                   C.ptr(g_sig_u), C.ptr(g_mu_w), C.ptr(g_sig_w), C.ptr(g_pz), Cn, K, B, L, Lw,
                                   meta["latent_kind"], meta["loss_kind"], float(meta["beta"]),
-                                  1 if meta["detach"] else 0, C.stream()), "mv_moe_lw_fwd")
+                                  1 if meta["detach"] else 0, 1 if meta.get("skip_u_prior") else 0, C.stream()), "mv_moe_lw_fwd")
         meta["wk"], meta["lw"], meta["lpx"] = wk, lw, lpx
         ctx.meta = meta
         ctx.dims = (Cn, K, B, L, Lw)
@@ -140,11 +145,12 @@ class MoEElboFn(torch.autograd.Function):
             g_recons.append(g)
         s = g_loss
         det = meta["detach"]
+        g_extra = ((coef * s),) if meta.get("has_extra") else ()
         return (None, g_u * s if need[1] else None, (g_w * s) if (Lw and need[2]) else None,
                 None if (det or not need[3]) else g_mu_u * s, None if (det or not need[4]) else g_sig_u * s,
                 None if (det or not Lw or not need[5]) else g_mu_w * s,
                 None if (det or not Lw or not need[6]) else g_sig_w * s,
-                (g_pz.sum(0) * s) if need[7] else None, *g_recons)
+                (g_pz.sum(0) * s) if need[7] else None, *g_recons, *g_extra)
 
 
 def log_var_to_std(log_var, kind):

@@ -17,30 +17,13 @@ from .elbo import MoEElboFn, log_var_to_std, standard_noise
 from .nn.default_architectures import BaseDictDecodersMultiLatents, BaseDictEncoders_MultiLatents
 
 
-class MMVAEPlus(BaseMultiVAE):
-    def __init__(self, model_config, encoders=None, decoders=None):
-        if model_config.modalities_specific_dim is None:
-            raise AttributeError("The modalities_specific_dim attribute must be provided in the model config.")
-        super().__init__(model_config, encoders, decoders)
-        if model_config.prior_and_posterior_dist not in ("laplace_with_softmax", "normal", "normal_with_softplus"):
-            raise AttributeError(" The posterior_dist parameter must be either 'laplace_with_softmax','normal' or "
-                                 f"'normal_with_softplus'.  {model_config.prior_and_posterior_dist} was provided.")
-        self.mean_priors = nn.ParameterDict()
-        self.logvars_priors = nn.ParameterDict()
-        self.beta = model_config.beta
-        self.modalities_specific_dim = model_config.modalities_specific_dim
-        self.reconstruction_option = model_config.reconstruction_option
-        self.multiple_latent_spaces = True
-        self.style_dims = {m: self.modalities_specific_dim for m in self.encoders}
-        Lw, L = model_config.modalities_specific_dim, model_config.latent_dim
-        for mod in list(self.encoders.keys()):
-            self.mean_priors[mod] = nn.Parameter(torch.zeros(1, Lw), requires_grad=False)
-            self.logvars_priors[mod] = nn.Parameter(torch.zeros(1, Lw), requires_grad=model_config.learn_modality_prior)
-        self.mean_priors["shared"] = nn.Parameter(torch.zeros(1, L + Lw), requires_grad=False)
-        self.logvars_priors["shared"] = nn.Parameter(torch.zeros(1, L + Lw), requires_grad=model_config.learn_shared_prior)
-        self.model_name = "MMVAEPlus"
-        self.objective = model_config.loss
-        self.noise_source = None  # test hook: callable(shape, kind, device) -> standard draws
+class MoEPlusBase(BaseMultiVAE):
+    """Machinery shared by the mixture-of-experts models with shared + private latent codes (MMVAE+, CMVAE): encoders, K
+    reparameterised samples, the M*M decoder invocations batched into one call per decoder over the C*K*B rows, and the fused
+    lpx / lw kernels.  Subclasses provide the priors (`_cross_prior`, `_shared_prior`) and, optionally, an additive log-weight
+    term (`_extra_lw`)."""
+
+    skip_u_prior = False
 
     def default_encoders(self, model_config):
         return BaseDictEncoders_MultiLatents(model_config.input_dims, model_config.latent_dim,
@@ -49,6 +32,9 @@ class MMVAEPlus(BaseMultiVAE):
     def default_decoders(self, model_config):
         return BaseDictDecodersMultiLatents(model_config.input_dims, model_config.latent_dim,
                                             {m: model_config.modalities_specific_dim for m in model_config.input_dims})
+
+    def _extra_lw(self, U, beta):
+        return None
 
     def _noise(self, shape, device):
         kind = self.model_config.prior_and_posterior_dist
@@ -71,6 +57,16 @@ class MMVAEPlus(BaseMultiVAE):
         same as the reference's sequence of rsample calls (mmvaePlus_model.py:136-186).  Not used with an injected noise_source."""
         if self.noise_source is None:
             self._noise_pool = (standard_noise((n_elements,), self.model_config.prior_and_posterior_dist, device), 0)
+
+    @property
+    def post_dist(self):
+        import torch.distributions as td
+        return td.Laplace if self.model_config.prior_and_posterior_dist == "laplace_with_softmax" else td.Normal
+
+    prior_dist = post_dist
+
+    def _log_var_to_std(self, log_var):
+        return log_var_to_std(log_var, self.model_config.prior_and_posterior_dist)
 
     def forward(self, inputs, **kwargs):
         if self.objective not in C.LOSS:
@@ -107,8 +103,9 @@ class MMVAEPlus(BaseMultiVAE):
             w.append(mu_w[-1] + sw * self._noise((K, B, sw.shape[-1]), dev))
             for r in mods:
                 if r != c:
-                    sp = log_var_to_std(self.logvars_priors[r], kind)
-                    w_cross[(c, r)] = self.mean_priors[r] + sp * self._noise((K, B, sp.shape[-1]), dev)
+                    pm_r, plv_r = self._cross_prior(r)
+                    sp = log_var_to_std(plv_r, kind)
+                    w_cross[(c, r)] = pm_r + sp * self._noise((K, B, sp.shape[-1]), dev)
         self._noise_pool = None
         U, W = torch.stack(u), torch.stack(w)  # (C,K,B,L), (C,K,B,Lw)
 
@@ -121,16 +118,20 @@ class MMVAEPlus(BaseMultiVAE):
                 rec = self._logits(self.decoders[r](z.reshape(-1, z.shape[-1]))["reconstruction"])
             recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
 
-        pz_std = log_var_to_std(self.logvars_priors["shared"], kind).reshape(-1)
+        pz_mean, pz_std = self._shared_prior()
+        pz_std = pz_std.reshape(-1)
         rmeta = self._recon_meta(mods, mods)
         if rescale is not None:
             rmeta = [(d, sc, float(rescale), row) for d, sc, _, row in rmeta]
         meta = dict(x=[self._target(inputs, r, rec) for r, rec in zip(mods, recons)],
-                    pz_mean=self.mean_priors["shared"].detach().reshape(-1).float().contiguous(),
+                    pz_mean=pz_mean.detach().reshape(-1).float().contiguous(),
                     masks=self._stack_masks(inputs, mods), recon=rmeta,
-                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=self.beta if beta is None else beta, detach=detach)
+                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=self.beta if beta is None else beta, detach=detach,
+                    skip_u_prior=self.skip_u_prior)
+        extra = self._extra_lw(U, meta["beta"])
+        meta["has_extra"] = extra is not None
         loss = MoEElboFn.apply(meta, U, W, torch.stack(mu_u), torch.stack(sig_u), torch.stack(mu_w),
-                               torch.stack(sig_w), pz_std, *recons)
+                               torch.stack(sig_w), pz_std, *recons, *(() if extra is None else (extra,)))
         if detach:
             # DReG: the gradient reaching the samples is multiplied once more by wk (mmvaePlus_model.py:330-338)
             wk = meta["wk"].unsqueeze(-1)
@@ -139,17 +140,42 @@ class MMVAEPlus(BaseMultiVAE):
                 W.register_hook(lambda g: g * wk)
         return loss, meta
 
+
+class MMVAEPlus(MoEPlusBase):
+    def __init__(self, model_config, encoders=None, decoders=None):
+        if model_config.modalities_specific_dim is None:
+            raise AttributeError("The modalities_specific_dim attribute must be provided in the model config.")
+        super().__init__(model_config, encoders, decoders)
+        if model_config.prior_and_posterior_dist not in ("laplace_with_softmax", "normal", "normal_with_softplus"):
+            raise AttributeError(" The posterior_dist parameter must be either 'laplace_with_softmax','normal' or "
+                                 f"'normal_with_softplus'.  {model_config.prior_and_posterior_dist} was provided.")
+        self.mean_priors = nn.ParameterDict()
+        self.logvars_priors = nn.ParameterDict()
+        self.beta = model_config.beta
+        self.modalities_specific_dim = model_config.modalities_specific_dim
+        self.reconstruction_option = model_config.reconstruction_option
+        self.multiple_latent_spaces = True
+        self.style_dims = {m: self.modalities_specific_dim for m in self.encoders}
+        Lw, L = model_config.modalities_specific_dim, model_config.latent_dim
+        for mod in list(self.encoders.keys()):
+            self.mean_priors[mod] = nn.Parameter(torch.zeros(1, Lw), requires_grad=False)
+            self.logvars_priors[mod] = nn.Parameter(torch.zeros(1, Lw), requires_grad=model_config.learn_modality_prior)
+        self.mean_priors["shared"] = nn.Parameter(torch.zeros(1, L + Lw), requires_grad=False)
+        self.logvars_priors["shared"] = nn.Parameter(torch.zeros(1, L + Lw), requires_grad=model_config.learn_shared_prior)
+        self.model_name = "MMVAEPlus"
+        self.objective = model_config.loss
+        self.noise_source = None  # test hook: callable(shape, kind, device) -> standard draws
+
+    def _cross_prior(self, r):
+        """Prior of modality r's private code used for cross-modal reconstructions (mmvaePlus_model.py:172-184)."""
+        return self.mean_priors[r], self.logvars_priors[r]
+
+    def _shared_prior(self):
+        """Prior over cat[u, w] (mmvaePlus_model.py:97-108,249-250): (mean, std); the softmax of laplace_with_softmax runs over
+        all L + Lw dimensions of the shared prior."""
+        return self.mean_priors["shared"], log_var_to_std(self.logvars_priors["shared"], self.model_config.prior_and_posterior_dist)
+
     # ---- inference (mmvaePlus_model.py:365-533) ---------------------------------------------------------------------------
-    @property
-    def post_dist(self):
-        import torch.distributions as td
-        return td.Laplace if self.model_config.prior_and_posterior_dist == "laplace_with_softmax" else td.Normal
-
-    prior_dist = post_dist
-
-    def _log_var_to_std(self, log_var):
-        return log_var_to_std(log_var, self.model_config.prior_and_posterior_dist)
-
     def _style_prior(self, m, batch_size):
         """Prior parameters of modality m's private code for cross-modal generation (:424-437)."""
         if self.reconstruction_option == "single_prior":

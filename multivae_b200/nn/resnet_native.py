@@ -198,8 +198,10 @@ def _direct_targets(params):
     return tg
 
 
-def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=None, hm=None):
+def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=None, hm=None, g_out_from_dpre=None):
     """g_out: gradient of the block output; g_dpre = 0.1 * g_out * lrelu'(d) (produced upstream).
+    g_out_from_dpre = sign mask of d: g_out is NOT materialised (None); the skip connection recovers it in the conv0 data-gradient
+    epilogue as g_dpre * (bit ? 10 : 50) (blocks without a shortcut convolution, 64 channels).
     Returns (g_x, dW0, db0, dW1, db1, dWsc); with tg = (w0.grad, b0.grad, w1.grad, b1.grad, wsc.grad | None) the weight / bias
     gradients are accumulated into those tensors by the kernels and None is returned in their place."""
     taps = g.taps3x3()
@@ -230,6 +232,10 @@ def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=No
         for j, wd in enumerate(blk.w0d_halves):
             HL.tapgemm(g_hpre, wd, 9, taps, 64, g.P, res=g_short[:, 64 * j:64 * j + 64], out=g_x[:, 64 * j:64 * j + 64], geom=g,
                        tag=f"{tag}.c0d")
+    elif need_gx and g_out_from_dpre is not None:
+        assert blk.wsc is None
+        g_x = HL.tapgemm(g_hpre, blk.w0d, 9, taps, blk.cin, g.P, res=g_dpre, res_mask=g_out_from_dpre,
+                         res_scale=(1.0 / 0.1, 1.0 / (0.1 * _LRELU)), geom=g, tag=f"{tag}.c0d")
     elif need_gx:
         g_x = HL.tapgemm(g_hpre, blk.w0d, 9, taps, blk.cin, g.P, res=g_short, geom=g, tag=f"{tag}.c0d")
     return g_x, dW0, db0, dW1, db1, dWsc
@@ -283,12 +289,19 @@ class DecoderStackFn(torch.autograd.Function):
         else:
             arena = HL.ZeroArena(sum(_block_wgrad_floats(b) for b in (B1, B2, B3)) + 9 * 16 * B3.cout + 32, h0.device)
             dWh, dbh = HL.wgrad(o3, gh, 9, g28.taps3x3(), g28.P, tag="head", want_db=True, dW=arena.take(9, 16, B3.cout), db=arena.take(16))
-        g_dpre3 = torch.empty(g28.P, B3.cout, device=h0.device, dtype=torch.bfloat16)
-        dkw = dict(dmask2=d3) if d3.dtype == torch.int64 else dict(dact2=d3)
-        g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, slope2=_LRELU, geom=g28, tag="head.d",
-                          **dkw)
         T = (lambda i, j: None) if tg is None else (lambda i, j: tuple(tg[i:j]) + ((None,) if j - i == 4 else ()))
-        g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3", arena=arena, tg=T(10, 14), hm=hm3)
+        if d3.dtype == torch.int64 and B3.w0d_halves is None:
+            # ONE output: the pre-scaled gradient 0.1 * g * lrelu'(d3); the block's skip connection un-scales it from d3's sign
+            # bits in the conv0 data-gradient epilogue (saves writing and re-reading a 64-channel 28x28 tensor)
+            g_dpre3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, alpha=0.1, dmask1=d3, slope1=_LRELU, geom=g28, tag="head.d")
+            g_u2, dW30, db30, dW31, db31, _ = _block_bwd(None, g_dpre3, u2, h3, g28, B3, "b3", arena=arena, tg=T(10, 14), hm=hm3,
+                                                         g_out_from_dpre=d3)
+        else:
+            g_dpre3 = torch.empty(g28.P, B3.cout, device=h0.device, dtype=torch.bfloat16)
+            dkw = dict(dmask2=d3) if d3.dtype == torch.int64 else dict(dact2=d3)
+            g_o3 = HL.tapgemm(gh, whd, 9, g28.taps3x3(), B3.cout, g28.P, out2=g_dpre3, alpha2=0.1, slope2=_LRELU, geom=g28, tag="head.d",
+                              **dkw)
+            g_u2, dW30, db30, dW31, db31, _ = _block_bwd(g_o3, g_dpre3, u2, h3, g28, B3, "b3", arena=arena, tg=T(10, 14), hm=hm3)
         g_o2, g_dpre2 = _upsample_bwd(g_u2, d2, g14, B2.cout, 0.1)
         g_u1, dW20, db20, dW21, db21, dWsc2 = _block_bwd(g_o2, g_dpre2, u1, h2, g14, B2, "b2", arena=arena, tg=T(5, 10), hm=hm2)
         g_o1, g_dpre1 = _upsample_bwd(g_u1, d1, g7, B1.cout, 0.1)

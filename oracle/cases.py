@@ -32,6 +32,12 @@ CASES = {
     "mopoe_private_masked": dict(model="mopoe", dims=_DIMS3, B=9, masks=True, cfg=dict(latent_dim=5, beta=1.0, beta_style=0.5, modalities_specific_dim={"m0": 3, "m1": 2, "m2": 4}, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
     "mvtcae_categorical": dict(model="mvtcae", dims={"m0": (3, 8, 8), "m1": (1, 6, 6), "m2": (4, 5)}, B=6, onehot=["m2"], cfg=dict(latent_dim=5, alpha=0.1, beta=2.5, decoders_dist={"m0": "laplace", "m1": "bernoulli", "m2": "categorical"}, decoder_dist_params={"m0": {"scale": 0.75}, "m1": {}, "m2": {}}, uses_likelihood_rescaling=True)),
     "mmvaeplus_categorical": dict(model="mmvaeplus", dims={"m0": (3, 8, 8), "m2": (4, 5)}, B=5, onehot=["m2"], cfg=dict(K=3, latent_dim=5, modalities_specific_dim=3, beta=2.5, loss="dreg_looser", prior_and_posterior_dist="laplace_with_softmax", decoders_dist={"m0": "laplace", "m2": "categorical"}, decoder_dist_params={"m0": {"scale": 0.75}, "m2": {}})),
+    # CMVAE (MMVAE+ with a mixture-of-clusters prior) and CRMVAE (MVTCAE aggregation + unimodal reconstruction terms): SURVEY 8(f) rank 3
+    "cmvae_dreg": dict(model="cmvae", dims=_DIMS3, B=6, cfg=dict(K=4, latent_dim=5, modalities_specific_dim=3, beta=2.5, loss="dreg_looser", number_of_clusters=4, prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "cmvae_iwae_normal": dict(model="cmvae", dims=_DIMS3, B=5, cfg=dict(K=3, latent_dim=4, modalities_specific_dim=4, beta=1.0, loss="iwae_looser", number_of_clusters=3, prior_and_posterior_dist="normal", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "cmvae_masked": dict(model="cmvae", dims=_DIMS3, B=6, masks=True, cfg=dict(K=4, latent_dim=5, modalities_specific_dim=3, beta=2.5, loss="dreg_looser", number_of_clusters=4, prior_and_posterior_dist="laplace_with_softmax", decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
+    "crmvae": dict(model="crmvae", dims=_DIMS3, B=6, cfg=dict(latent_dim=5, beta=2.5, decoders_dist=_DIST3, decoder_dist_params=_PAR3, uses_likelihood_rescaling=True)),
+    "crmvae_masked": dict(model="crmvae", dims=_DIMS3, B=6, masks=True, cfg=dict(latent_dim=5, beta=1.0, decoders_dist=_DIST3, decoder_dist_params=_PAR3)),
     # ---- BASELINE.json configs at their real input shapes (default MLP architectures; every hyper-parameter written out — the values
     # are the reference configs' defaults / the example scripts' settings; small batches where the config's own is big)
     "cfg1_mvtcae_quickstart": dict(model="mvtcae", dims={"mnist": (1, 28, 28), "svhn": (3, 32, 32)}, B=32,

@@ -59,11 +59,12 @@ def reference_archs(spec):
 def run_case(name, spec):
     ref_harness.import_reference()
     from multivae.data.datasets.base import IncompleteDataset, MultimodalBaseDataset
-    from multivae.models import (MMVAE, MVAE, MVTCAE, MMVAEConfig, MMVAEPlus, MMVAEPlusConfig, MoPoE,
-                                 MoPoEConfig, MVAEConfig, MVTCAEConfig)
+    from multivae.models import (CMVAE, CRMVAE, MMVAE, MVAE, MVTCAE, CMVAEConfig, CRMVAEConfig, MMVAEConfig, MMVAEPlus,
+                                 MMVAEPlusConfig, MoPoE, MoPoEConfig, MVAEConfig, MVTCAEConfig)
 
     cls = {"mmvaeplus": (MMVAEPlus, MMVAEPlusConfig), "mmvae": (MMVAE, MMVAEConfig), "mvtcae": (MVTCAE, MVTCAEConfig),
-           "mvae": (MVAE, MVAEConfig), "mopoe": (MoPoE, MoPoEConfig)}[spec["model"]]
+           "mvae": (MVAE, MVAEConfig), "mopoe": (MoPoE, MoPoEConfig), "cmvae": (CMVAE, CMVAEConfig),
+           "crmvae": (CRMVAE, CRMVAEConfig)}[spec["model"]]
     import copy
     cfg = cls[1](n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"]))
     enc, dec = reference_archs(spec)
@@ -105,13 +106,16 @@ def run_case(name, spec):
     if spec["model"] == "mopoe":
         rec["subset_keys"] = list(model.subsets.keys())
     # per-term tensors for the MoE models: replay with the same noise
-    if spec["model"] in ("mmvaeplus", "mmvae"):
+    if spec["model"] in ("mmvaeplus", "mmvae", "cmvae"):
         model.zero_grad()
         q2 = ref_harness.NoiseQueue(draws=[e.clone() for e in q.log])
         with ref_harness.injected_noise(q2), torch.no_grad():
             if spec["model"] == "mmvaeplus":
                 emb, post, recs = model._compute_posteriors_and_embeddings(ds, detach=cfg.loss == "dreg_looser")
                 lws, _ = model._compute_k_lws(post, emb, recs, ds)
+            elif spec["model"] == "cmvae":
+                post, emb, recs = model._compute_posteriors_and_embeddings(ds, detach=cfg.loss == "dreg_looser")
+                lws, _, _ = model._compute_k_lws(post, emb, recs, ds)
             else:
                 o = model(ds, detailed_output=True, compute_loss=False)
                 qz = o["qz_xs_detach"] if cfg.loss == "dreg_looser" else o["qz_xs"]

@@ -136,7 +136,7 @@ def _moe_terms(kind, z_u, post_u, masks, mods):
 
 def mmvae_plus_forward(
     enc, dec, data, noise, *, K, latent_dim, style_dim, beta, kind, loss, dec_dist, dec_scale,
-    rescale, prior_mean, prior_logvar, masks=None, details=None,
+    rescale, prior_mean, prior_logvar, masks=None, details=None, cmvae=None,
 ):
     """One MMVAE+ forward.  enc[m](x)->(mu,lv,mu_w,lv_w); dec[m](z)->recon.
     prior_mean/prior_logvar: dict with per-modality (1,Lw) entries and "shared" (1,L+Lw).
@@ -170,12 +170,13 @@ def mmvae_plus_forward(
         n_mods = torch.sum(torch.stack(tuple(masks[m] for m in mods)).int(), dim=0)
     else:
         n_mods = torch.tensor([len(mods)])
-    pz_mean, pz_std = prior_mean["shared"], log_var_to_std(prior_logvar["shared"], kind)
+    if cmvae is None:
+        pz_mean, pz_std = prior_mean["shared"], log_var_to_std(prior_logvar["shared"], kind)
     lws = {}
     for c in mods:
         u, w = emb[c]["u"], emb[c]["w"]
         z = torch.cat([u, w], dim=-1)
-        lpz = latent_log_prob(kind, z, pz_mean, pz_std).sum(-1)
+        lpz = latent_log_prob(kind, z, pz_mean, pz_std).sum(-1) if cmvae is None else None
         lqu = torch.logsumexp(_moe_terms(kind, u, {m: post[m]["u"] for m in mods}, masks, mods), dim=0) - torch.log(n_mods)
         lqw = latent_log_prob(kind, w, *post[c]["w"]).sum(-1)
         lpx = 0
@@ -186,7 +187,20 @@ def mmvae_plus_forward(
             if masks is not None:
                 t = t * masks[r].float()
             lpx = lpx + t
-        lw = lpx + beta * (lpz - lqu - lqw)
+        if cmvae is None:
+            lw = lpx + beta * (lpz - lqu - lqw)
+        else:
+            # CMVAE (models/cmvae/cmvae_model.py:263-345): fixed prior p(w), mixture-of-clusters prior over u with the explicit
+            # expectation over q(c | u)
+            lpw = latent_log_prob(kind, w, cmvae["w_mean"], log_var_to_std(cmvae["w_logvar"], kind)).sum(-1)
+            n_c = len(cmvae["means"])
+            lpc = torch.log(F.softmax(cmvae["pc_logits"], dim=-1))
+            lpzc = torch.stack([latent_log_prob(kind, u, cmvae["means"][i], log_var_to_std(cmvae["logvars"][i], kind))
+                                for i in range(n_c)], dim=0).sum(-1)
+            qzc = torch.softmax(lpc.view(n_c, 1, 1) + lpzc, dim=0) + 1e-20
+            lw = 0
+            for ci, q_c in enumerate(qzc):
+                lw = lw + q_c * (lpx + beta * (lpc[ci] + lpzc[ci] + lpw - lqu - lqw - q_c.log()))
         if masks is not None:
             lw = lw * masks[c].float()
         lws[c] = lw
@@ -316,6 +330,55 @@ def mvtcae_forward(enc, dec, data, noise, *, alpha, beta, dec_dist, dec_scale, r
     rec_w, cvib_w, vib_w = (M - alpha) / M, alpha / M, 1 - alpha
     total = rec_w * loss_rec + beta * (cvib_w * kld_losses + vib_w * joint_kld)
     return total / ndata, total, res
+
+
+# --------------------------------------------------------------------------------------------
+# CRMVAE                                       models/crmvae/crmvae_model.py:44-180
+# --------------------------------------------------------------------------------------------
+def kl_gauss(mean, log_var, prior_mean, prior_log_var):
+    """models/base/base_utils.py:90-119."""
+    kl = 0.5 * (prior_log_var - log_var + torch.exp(log_var - prior_log_var) + ((mean - prior_mean) ** 2) / torch.exp(prior_log_var) - 1)
+    return kl.sum(dim=-1)
+
+
+def crmvae_forward(enc, dec, data, noise, *, beta, dec_dist, dec_scale, rescale, masks=None):
+    """noise["z"]: list of (B,L): the joint draw, then one per modality.  Returns (loss, loss_sum, metrics)."""
+    mods = list(data.keys())
+    outs, masked = {}, {}
+    for m in mods:
+        mu, lv = enc[m](data[m])
+        outs[m] = (mu, lv)
+        lvm = lv.clone()
+        if masks is not None:
+            lvm = lvm.masked_fill((1 - masks[m].int()).bool().unsqueeze(-1), torch.inf)
+        masked[m] = (mu, lvm)
+    jmu, jlv = poe(torch.stack([masked[m][0] for m in mods]), torch.stack([masked[m][1] for m in mods]))
+    it = iter(noise["z"])
+    z = {"joint": jmu + torch.exp(0.5 * jlv) * next(it)}
+    res = {}
+    joint_kld = kl_gauss(jmu, jlv, torch.zeros_like(jmu), torch.zeros_like(jlv))
+    res["joint_divergence"] = joint_kld.mean()
+    divergence = joint_kld
+    for m in mods:
+        mu, lv = outs[m]
+        z[m] = mu + torch.exp(0.5 * lv) * next(it)
+        k = kl_gauss(jmu, jlv, mu, lv)
+        if masks is not None:
+            k = k * masks[m].float()
+        divergence = divergence + k
+        res[f"kl_{m}"] = k.mean()
+    loss_rec = 0
+    for g in mods:
+        for src in ("joint", g):
+            rec = dec[g](z[src])
+            t = (-recon_log_prob(dec_dist[g], rec, data[g], dec_scale[g]) * rescale[g]).reshape(rec.size(0), -1).sum(-1)
+            if masks is not None:
+                t = masks[g].float() * t
+            loss_rec = loss_rec + t
+            res[f"recon_{g}_from_{src}"] = t.mean()
+    M = len(mods)
+    total = loss_rec / (2 * (M + 1)) + beta * divergence / (M + 1)
+    return total.sum(), total.sum(), res
 
 
 # --------------------------------------------------------------------------------------------

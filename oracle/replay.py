@@ -45,7 +45,7 @@ def default_nets(spec, p, dtype=torch.float32):
             else:
                 raise ValueError(a)
         return enc, dec
-    if spec["model"] == "mmvaeplus" or spec["cfg"].get("modalities_specific_dim") is not None:
+    if spec["model"] in ("mmvaeplus", "cmvae") or spec["cfg"].get("modalities_specific_dim") is not None:
         enc = {m: (lambda x, m=m: N.encoder_vae_mlp_style(p, f"encoders.{m}.", x)) for m in mods}
     else:
         enc = {m: (lambda x, m=m: N.encoder_vae_mlp(p, f"encoders.{m}.", x)) for m in mods}
@@ -58,7 +58,7 @@ def split_noise(spec, noise, mods_active=None):
     mods = mods_active or list(spec["dims"])
     it = iter(noise)
     model = spec["model"]
-    if model == "mmvaeplus":
+    if model in ("mmvaeplus", "cmvae"):
         out = {"u": {}, "w": {}, "prior": {}}
         for c in mods:
             out["u"][c] = next(it)
@@ -70,7 +70,7 @@ def split_noise(spec, noise, mods_active=None):
         return out
     if model == "mmvae":
         return {"z": {c: next(it) for c in mods}}
-    if model == "mvae":
+    if model in ("mvae", "crmvae"):
         return {"z": list(noise)}
     if model == "mopoe" and spec["cfg"].get("modalities_specific_dim") is not None:
         return {"z": next(it), "style": {m: next(it) for m in spec["dims"]}}   # shared, then one style draw per modality
@@ -81,8 +81,8 @@ def run_port(spec, rec, dtype=torch.float32, want_grads=True, details=None):
     """Returns (loss, loss_sum, metrics, params-with-grads)."""
     sd = synth_state_dict(rec["state_shapes"], seed=rec["sd_seed"])
     p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
-    for k in p:  # frozen prior parameters (requires_grad=False in the reference model)
-        if "prior" in k and rec["grads"].get(k, 1) is None:
+    for k in p:  # frozen prior / cluster-scale parameters (requires_grad=False in the reference model)
+        if ("prior" in k or "logvar_clusters" in k) and rec["grads"].get(k, 1) is None:
             p[k].requires_grad_(False)
     loss, loss_sum, metrics = _forward(spec, rec, p, dtype, details)
     if want_grads:
@@ -117,6 +117,19 @@ def _forward(spec, rec, p, dtype, details):
                                     kind=cfg["prior_and_posterior_dist"], loss=cfg["loss"], dec_dist=dd, dec_scale=ds,
                                     rescale=rs, prior_mean=pm, prior_logvar=pl, masks=masks, details=details)
         loss_sum = loss
+    elif model == "cmvae":
+        n_c = cfg.get("number_of_clusters", 10)
+        cm = dict(w_mean=p["w_mean_prior"], w_logvar=p["w_logvar_prior"], pc_logits=p["_pc_params"],
+                  means=[p[f"mean_clusters.{i}"] for i in range(n_c)], logvars=[p[f"logvar_clusters.{i}"] for i in range(n_c)])
+        loss = E.mmvae_plus_forward(enc, dec, data, noise, K=cfg["K"], latent_dim=cfg["latent_dim"],
+                                    style_dim=cfg["modalities_specific_dim"], beta=cfg.get("beta", 1.0),
+                                    kind=cfg["prior_and_posterior_dist"], loss=cfg["loss"], dec_dist=dd, dec_scale=ds,
+                                    rescale=rs, prior_mean={m: p[f"r_mean_priors.{m}"] for m in mods},
+                                    prior_logvar={m: p[f"r_logvars_priors.{m}"] for m in mods}, masks=masks, details=details, cmvae=cm)
+        loss_sum = loss
+    elif model == "crmvae":
+        loss, loss_sum, metrics = E.crmvae_forward(enc, dec, data, noise, beta=cfg.get("beta", 2.5), dec_dist=dd, dec_scale=ds,
+                                                   rescale=rs, masks=masks)
     elif model == "mmvae":
         loss = E.mmvae_forward(enc, dec, data, noise, K=cfg["K"], beta=cfg.get("beta", 1.0),
                                kind=cfg["prior_and_posterior_dist"], loss=cfg["loss"], dec_dist=dd, dec_scale=ds,

@@ -12,7 +12,8 @@ from oracle.replay import run_port
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODELS = {"mmvaeplus": (mb.MMVAEPlus, mb.MMVAEPlusConfig), "mmvae": (mb.MMVAE, mb.MMVAEConfig),
-          "mvtcae": (mb.MVTCAE, mb.MVTCAEConfig), "mvae": (mb.MVAE, mb.MVAEConfig), "mopoe": (mb.MoPoE, mb.MoPoEConfig)}
+          "mvtcae": (mb.MVTCAE, mb.MVTCAEConfig), "mvae": (mb.MVAE, mb.MVAEConfig), "mopoe": (mb.MoPoE, mb.MoPoEConfig),
+          "cmvae": (mb.CMVAE, mb.CMVAEConfig), "crmvae": (mb.CRMVAE, mb.CRMVAEConfig)}
 
 
 def load_golden(name):

@@ -181,3 +181,17 @@ def test_sign_mask_second_output_and_its_consumer(n_img):
     oa = HL.tapgemm(G, wd, 9, g.taps3x3(), c, g.P, out2=o2a, alpha2=0.1, dact2=d, geom=g)
     ob = HL.tapgemm(G, wd, 9, g.taps3x3(), c, g.P, out2=o2b, alpha2=0.1, dmask2=mask, geom=g)
     assert torch.equal(oa, ob) and torch.equal(o2a, o2b)
+    # single-output form of the same consumer: out = 0.1 * acc * lrelu'(d) from the sign bits (dmask1) ...
+    oc = HL.tapgemm(G, wd, 9, g.taps3x3(), c, g.P, alpha=0.1, dmask1=mask, slope1=0.2, geom=g)
+    _close(oc, o2a.float(), tol=1e-2)
+    # ... and a 3x3 convolution whose residual is recovered from it: res * (bit ? 10 : 50) = the un-scaled gradient `oa`
+    gh = _rnd(n_img, c, H, H, seed=47).bfloat16()
+    GH, _ = HL.to_halo(gh)
+    w2 = HL.pack_conv_weight_dgrad(_rnd(c, c, 3, 3, seed=48, scale=c ** -0.5).bfloat16())
+    ref = HL.tapgemm(GH, w2, 9, g.taps3x3(), c, g.P, res=oa, geom=g)
+    got = HL.tapgemm(GH, w2, 9, g.taps3x3(), c, g.P, res=oc, res_mask=mask, res_scale=(10.0, 50.0), geom=g)
+    _close(got, ref.float(), tol=1e-2)
+    halo = torch.ones(g.P, dtype=torch.bool, device="cuda")
+    v = halo[: n_img * g.S].view(n_img, H + 1, g.Wp)
+    v[:, 1:, :H] = False
+    assert float(got[halo].abs().max()) == 0.0 and float(oc[halo].abs().max()) == 0.0
