@@ -176,6 +176,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
+      if (nb >= p.N) {
+        // this warp's 64 columns lie entirely outside the matrix (N <= 64 tiles): nothing to compute or store
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
+        continue;
+      }
       if (EPI == GEPI_BF16 && stored) {
         if (lane == 0) tc::tma_store_wait_read<0>();   // this warp's previous store must have finished reading its slab
         __syncwarp();
@@ -200,8 +207,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);
             if (p.act == MV_ACT_SIGMOID) {
+              // the result is rounded to bf16 (8 mantissa bits) or feeds a Bernoulli / sigmoid decoder: the fast exponential and
+              // reciprocal (2 ulp of fp32) cost a fifth of the instructions of expf + IEEE division in this issue-bound epilogue
 #pragma unroll
-              for (int e = 0; e < 8; ++e) y[e] = 1.f / (1.f + expf(-y[e]));
+              for (int e = 0; e < 8; ++e) y[e] = __frcp_rn(1.f + __expf(-y[e]));
             }
             if (p.dact) {
               const int n = nb + cb + g * 8;
