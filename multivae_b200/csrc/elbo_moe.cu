@@ -336,9 +336,10 @@ __device__ __forceinline__ float lat_ds(float x, float mu, float s) {
 
 constexpr int kMaxC = 8;  // modalities handled by the latent kernel (reference configs: <= 5)
 
-// one warp per sample b
+// one block of kLwWarps warps per (conditioning modality, sample); the K importance samples are spread over its warps
+constexpr int kLwWarps = 8;
 template <int KIND>
-__global__ void __launch_bounds__(128) moe_lw_kernel(
+__global__ void __launch_bounds__(32 * kLwWarps) moe_lw_kernel(
     const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ mu_u,
     const float* __restrict__ sig_u, const float* __restrict__ mu_w, const float* __restrict__ sig_w,
     const float* __restrict__ pz_mean, const float* __restrict__ pz_std, const float* __restrict__ lpx,
@@ -346,12 +347,13 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
     float* __restrict__ loss_b, float* __restrict__ g_u, float* __restrict__ g_w, float* __restrict__ g_mu_u,
     float* __restrict__ g_sig_u, float* __restrict__ g_mu_w, float* __restrict__ g_sig_w, float* __restrict__ g_pz_std,
     int C, int K, int B, int L, int Lw, int loss_kind, float beta, int detach_post, int skip_u_prior) {
-  const int lane = threadIdx.x & 31;
-  // one warp per (conditioning modality c, sample b): C times the parallelism of a warp per sample.  What the C warps of a
-  // sample share (its loss, the prior-scale gradient, the posterior-parameter gradients of all modalities through the MoE
-  // term) is accumulated with atomics into buffers the host zero-fills before the launch.
-  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wi >= C * B) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // One block per (conditioning modality c, sample b), its warps take the K importance samples round-robin: C * min(K, 8)
+  // times the parallelism of a warp per sample (the kernel is a chain of dependent reductions: it wants warps, not bytes).
+  // What the warps of a sample share (its loss, the prior-scale gradient, the posterior-parameter gradients through the MoE
+  // term and of the private code) is accumulated with atomics into buffers the host zero-fills before the launch.
+  __shared__ float s_mx[kLwWarps];
+  const int wi = blockIdx.x;
   const int c = wi / B, b = wi - c * B;
   int nm = 0;
   bool avail[kMaxC];
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
   {
     // ---- pass 1: lw[c,k,b] for all k -----------------------------------------------------------
     float mx = -INFINITY;
-    for (int k = 0; k < K; ++k) {
+    for (int k = warp; k < K; k += kLwWarps) {
       const int64_t row = (int64_t(c) * K + k) * B + b;
       float val = 0.f;
       if (avail[c]) {
@@ -406,7 +408,10 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
       if (lane == 0) lw[row] = val;
       mx = fmaxf(mx, val);
     }
-    __syncwarp();
+    if (lane == 0) s_mx[warp] = mx;
+    __syncthreads();   // every warp's lw values (global) and maxima (shared) are visible to the whole block
+#pragma unroll
+    for (int i = 0; i < kLwWarps; ++i) mx = fmaxf(mx, s_mx[i]);
     // ---- softmax over k ------------------------------------------------------------------------
     // The weights are normalised exactly (wk = e_k / sum e) and the DReG term is evaluated relative to the maximum,
     // sum_k wk*lw = mx + sum_k wk*(lw - mx): with |lw| ~ 1e4 (D = 12288) the textbook form exp(lw - fl(logsumexp)) leaves
@@ -421,23 +426,24 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
       const int64_t row = (int64_t(c) * K + k) * B + b;
       const float v = lw[row];
       const float wgt = expf(v - mx) * inv_se;
-      wk[row] = wgt;
-      coef[row] = avail[c] ? -wgt * inv_nm : 0.f;
+      if (warp == 0) {   // every warp computes the same weights (it needs them below); warp 0 publishes them
+        wk[row] = wgt;
+        coef[row] = avail[c] ? -wgt * inv_nm : 0.f;
+      }
       term += wgt * (v - mx);
     }
     term = mx + warp_sum(term);
     if (loss_kind == MV_LOSS_IWAE) term = lse - logf(float(K));
-    if (avail[c]) loss_acc += term;
-    __syncwarp();
+    if (avail[c] && warp == 0) loss_acc += term;
     // ---- pass 2: unit gradients of the latent terms ----------------------------------------------
-    for (int k = 0; k < K; ++k) {
+    for (int k = warp; k < K; k += kLwWarps) {
       const int64_t row = (int64_t(c) * K + k) * B + b;
       if (!avail[c]) {
         for (int l = lane; l < L; l += 32) g_u[row * L + l] = 0.f;
         for (int l = lane; l < Lw; l += 32) g_w[row * Lw + l] = 0.f;
         continue;
       }
-      const float cb = coef[row] * beta;  // d loss / d (lpz - lqu - lqw)
+      const float cb = -expf(lw[row] - mx) * inv_se * inv_nm * beta;  // coef[row] * beta = d loss / d (lpz - lqu - lqw)
       // MoE responsibilities sm_m = softmax_m(lq_m)
       float lq[kMaxC];
 #pragma unroll
@@ -492,14 +498,14 @@ __global__ void __launch_bounds__(128) moe_lw_kernel(
         const float dx = lat_dx<KIND>(ww, mm, ss);
         g_w[row * Lw + l] = cb * (lat_dx<KIND>(ww, pm, ps) - dx);
         atomicAdd(g_pz_std + int64_t(b) * LT + L + l, cb * lat_ds<KIND>(ww, pm, ps));
-        if (!detach_post) {
-          g_mu_w[pi] += cb * dx;
-          g_sig_w[pi] -= cb * lat_ds<KIND>(ww, mm, ss);
+        if (!detach_post) {   // the block's warps (different k) share these addresses
+          atomicAdd(g_mu_w + pi, cb * dx);
+          atomicAdd(g_sig_w + pi, -cb * lat_ds<KIND>(ww, mm, ss));
         }
       }
     }
   }
-  if (lane == 0 && avail[c]) atomicAdd(loss_b + b, -loss_acc * inv_nm);
+  if (lane == 0 && warp == 0 && avail[c]) atomicAdd(loss_b + b, -loss_acc * inv_nm);
 }
 
 }  // namespace mv
@@ -748,11 +754,11 @@ extern "C" int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, 
     cudaMemsetAsync(g_mu_w, 0, sizeof(float) * size_t(C) * B * Lw, st);
     cudaMemsetAsync(g_sig_w, 0, sizeof(float) * size_t(C) * B * Lw, st);
   }
-  const int blocks = (C * B + 3) / 4;   // one warp per (conditioning modality, sample)
+  const int blocks = C * B;   // one block per (conditioning modality, sample)
   if (latent_kind == MV_LATENT_LAPLACE)
-    moe_lw_kernel<MV_LATENT_LAPLACE><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post, skip_u_prior);
+    moe_lw_kernel<MV_LATENT_LAPLACE><<<blocks, 32 * kLwWarps, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post, skip_u_prior);
   else if (latent_kind == MV_LATENT_NORMAL)
-    moe_lw_kernel<MV_LATENT_NORMAL><<<blocks, 128, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post, skip_u_prior);
+    moe_lw_kernel<MV_LATENT_NORMAL><<<blocks, 32 * kLwWarps, 0, st>>>(u, w, mu_u, sig_u, mu_w, sig_w, pz_mean, pz_std, lpx, masks, lw, wk, coef, loss_b, g_u, g_w, g_mu_u, g_sig_u, g_mu_w, g_sig_w, g_pz_std, C, K, B, L, Lw, loss_kind, beta, detach_post, skip_u_prior);
   else {
     mv::set_error("mv_moe_lw_fwd: unknown latent kind %d", latent_kind);
     return MV_ERR_UNSUPPORTED;
