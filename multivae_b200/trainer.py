@@ -81,6 +81,11 @@ def shard_indices(n, world_size, rank, shuffle=False, seed=0, epoch=0):
     return idx[rank:total:world_size]
 
 
+class StagedBatch(DatasetOutput):
+    """A batch whose host->device copy was started ahead of time by `BaseTrainer.prefetch` (device tensors in `data`, the event
+    `ready` fires when the copy has landed, `slot` is the staging set to hand back)."""
+
+
 class FlatGrads:
     """All parameter gradients as views of one flat fp32 buffer (the all-reduce bucket)."""
 
@@ -205,6 +210,44 @@ class BaseTrainer:
                             shuffle=cfg.shuffle, seed=cfg.seed, epoch=epoch)
         return self._batches_of(self.train_dataset, idx, cfg.per_device_train_batch_size)
 
+    def prefetch(self, inputs):
+        """Start the host->device copy of a (pinned) batch on a copy stream into one of two persistent staging sets and return a
+        StagedBatch for `step_batch`: called for batch i+1 right after batch i was launched, the PCIe transfer overlaps batch i's
+        compute instead of sitting between two steps (double buffering; the reference's DataLoader does the same with
+        `pin_memory` + non_blocking copies).  Batches with masks, CPU runs and non-tensor payloads are returned unchanged."""
+        if self.device.type != "cuda" or hasattr(inputs, "masks") or isinstance(inputs, StagedBatch):
+            return inputs
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stages, self._stage_free, self._stage_next = {}, {}, 0
+        sig = tuple((m, tuple(t.shape), t.dtype) for m, t in inputs.data.items())
+        slot = self._stage_next
+        self._stage_next ^= 1
+        key = (sig, slot)
+        if key not in self._stages:
+            self._stages[key] = {m: torch.empty(t.shape, dtype=t.dtype, device=self.device) for m, t in inputs.data.items()}
+        cs = self._copy_stream
+        if key in self._stage_free:
+            cs.wait_event(self._stage_free[key])   # the step that consumed this staging set last has copied it out
+        with torch.cuda.stream(cs):
+            for m, t in inputs.data.items():
+                self._stages[key][m].copy_(t, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        out = StagedBatch(data=self._stages[key])
+        out["ready"], out["slot"] = ready, key
+        return out
+
+    def _consume_staged(self, inputs):
+        """Make the current stream wait for a staged batch's copy; returns the device-resident batch."""
+        torch.cuda.current_stream().wait_event(inputs.ready)
+        return inputs
+
+    def _release_staged(self, inputs):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._stage_free[inputs.slot] = ev
+
     def _to_device(self, inputs):
         mv = lambda t: t.to(self.device, non_blocking=True)  # noqa: E731
         out = DatasetOutput(data={m: mv(t) for m, t in inputs.data.items()})
@@ -245,9 +288,17 @@ class BaseTrainer:
     def step_batch(self, inputs, epoch=1, batch_ratio=0.0, n_batches=1, allow_graph=True):
         """One batch of train_step (base_trainer.py:704-728) without the host read-back."""
         cfg = self.training_config
+        staged = isinstance(inputs, StagedBatch)
+        if staged:
+            self._consume_staged(inputs)
         if not (cfg.use_cuda_graph and allow_graph and self.device.type == "cuda"):
-            return self._eager_step(self._to_device(inputs), epoch, batch_ratio)
-        return self._graph_step(inputs, epoch, batch_ratio)
+            out = self._eager_step(self._to_device(inputs), epoch, batch_ratio)
+        else:
+            out = self._graph_step(inputs, epoch, batch_ratio)
+        if staged:
+            # eager: the step's kernels read the staging tensors directly; graph: they were copied into the static inputs
+            self._release_staged(inputs)
+        return out
 
     # ---- CUDA-graph replay of the step ------------------------------------------------------------
     def _graph_step(self, inputs, epoch, batch_ratio):
@@ -300,8 +351,12 @@ class BaseTrainer:
         batches = list(self.local_batches(epoch))
         epoch_loss = torch.zeros((), device=self.device, dtype=torch.float64)
         metrics = {}
+        nxt = self.prefetch(batches[0]) if batches else None
         for i, inputs in enumerate(batches):
-            out = self.step_batch(inputs, epoch=epoch, batch_ratio=i / len(batches), n_batches=len(batches))
+            cur = nxt
+            out = self.step_batch(cur, epoch=epoch, batch_ratio=i / len(batches), n_batches=len(batches))
+            if i + 1 < len(batches):
+                nxt = self.prefetch(batches[i + 1])   # the next batch's H2D copy overlaps this step's compute
             loss = out.loss_sum if hasattr(out, "loss_sum") else out.loss
             epoch_loss += loss.detach().double()
             for k, v in out.metrics.items():

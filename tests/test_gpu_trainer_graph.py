@@ -69,3 +69,30 @@ def test_graph_step_matches_eager_step(name):
         assert abs(a - b) <= 1e-4 * abs(a) + 1e-4, (name, le, lg)
     for k in se:
         assert torch.allclose(se[k], sg[k], rtol=1e-3, atol=1e-5), (name, k)
+
+
+def test_train_step_with_prefetched_batches_matches_plain_steps():
+    """train_step double-buffers the host->device copies (prefetch of batch i+1 during batch i): same trajectory as feeding the
+    batches one by one, eager and graph mode."""
+    cls, mk = CFGS["mvtcae"]
+    data = {m: torch.rand(48, *d, generator=torch.Generator().manual_seed(i)).pin_memory() for i, (m, d) in enumerate(DIMS.items())}
+    finals = []
+    for graph, via_train_step in ((False, False), (False, True), (True, True)):
+        torch.manual_seed(0)
+        model = cls(mk())
+        noise = FixedNoise()
+        model.noise_source = lambda shape, kind, dev, n=noise: (n.begin(), n(shape, kind, dev))[1]   # the same draw every step
+        ds = mb.MultimodalBaseDataset(data=data)
+        tr = BaseTrainer(model, ds, training_config=BaseTrainerConfig(per_device_train_batch_size=16, learning_rate=1e-3, use_cuda_graph=graph,
+                                                                      graph_warmup_steps=1, shuffle=False))
+        for epoch in (1, 2):
+            if via_train_step:
+                loss, _ = tr.train_step(epoch)
+                assert loss == loss
+            else:
+                for i in range(3):
+                    tr.step_batch(mb.DatasetOutput(data={m: t[16 * i:16 * i + 16] for m, t in data.items()}), epoch=epoch)
+        finals.append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+    for other in finals[1:]:
+        for k in finals[0]:
+            assert torch.allclose(finals[0][k], other[k], rtol=1e-3, atol=1e-5), k
