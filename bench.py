@@ -550,9 +550,18 @@ def main():
         sys.exit(subprocess.call(cmd))
     run_gpu(args)
     if world > 1:
+        import gc
+
         import torch.distributed as dist
+        gc.collect()                      # CUDA graphs that captured NCCL kernels are released before the communicator
+        torch.cuda.synchronize()
         if dist.is_initialized():
+            # the result line is out; never let communicator teardown hold the job (a watchdog ends the process if it stalls)
+            t = threading.Timer(30.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
             dist.destroy_process_group()
+            t.cancel()
 
 
 if __name__ == "__main__":

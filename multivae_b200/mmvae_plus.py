@@ -111,13 +111,14 @@ class MoEPlusBase(BaseMultiVAE):
 
         # one batched decoder call per reconstructed modality over all conditioning modalities
         recons = []
+        self._decoder_inputs = []   # the trainer hooks these: once all of them have a gradient, every decoder's backward is done
         for r in mods:
             wz = torch.stack([W[i] if c == r else w_cross[(c, r)] for i, c in enumerate(mods)])
-            z = torch.cat([U, wz], dim=-1)
+            z = torch.cat([U, wz], dim=-1).reshape(-1, U.shape[-1] + wz.shape[-1])
+            self._decoder_inputs.append(z)
             with self._nn_ctx():
-                rec = self._logits(self.decoders[r](z.reshape(-1, z.shape[-1]))["reconstruction"])
+                rec = self._logits(self.decoders[r](z)["reconstruction"])
             recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
-
         pz_mean, pz_std = self._shared_prior()
         pz_std = pz_std.reshape(-1)
         rmeta = self._recon_meta(mods, mods)

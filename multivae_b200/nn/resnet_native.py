@@ -361,6 +361,7 @@ class FcHaloFn(torch.autograd.Function):
         gemm(zb, wp, n, wp.shape[0], L, h0, bias=b_ext[gather].contiguous(), tag="dec.fc")
         ctx.save_for_backward(zb, wp)
         ctx.scatter = scatter
+        ctx.params = (weight, bias)
         return h0
 
     @staticmethod
@@ -378,6 +379,11 @@ class FcHaloFn(torch.autograd.Function):
         gemm(g, zb, F_, L, n, gw, a_mn=True, b_mn=True, out_kind=2, tag="dec.fc.w")
         gb = torch.zeros(F_, device=g.device, dtype=torch.float32)
         C.check(C.lib().mv_colsum_any(g.data_ptr(), n, F_, F_, gb.data_ptr(), C.stream()), "mv_colsum_any")
+        tgt = _direct_targets(ctx.params)
+        if tgt is not None:   # trainer opt-in: straight into the flat gradient buffer (final when this backward returns)
+            tgt[0].add_(gw[ctx.scatter])
+            tgt[1].add_(gb[ctx.scatter])
+            return gz, None, None
         return gz, gw[ctx.scatter], gb[ctx.scatter]
 
 

@@ -47,6 +47,8 @@ class BaseTrainerConfig:
     # batch order: the reference builds DataLoader(shuffle=True) / DistributedSampler(shuffle=True) (base_trainer.py:199-210)
     shuffle: bool = True
     seed: int = 0
+    # reduce the decoders' gradient slice on a side stream while the encoders' backward still runs (multi-GPU only)
+    overlap_allreduce: bool = True
     beta_schedule: Optional[list] = field(default=None)
 
     def __post_init__(self):
@@ -89,8 +91,13 @@ class StagedBatch(DatasetOutput):
 class FlatGrads:
     """All parameter gradients as views of one flat fp32 buffer (the all-reduce bucket)."""
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, first=()):
+        """`first`: parameters laid out at the front of the buffer (the decoders: their gradients are final before the encoders'
+        backward starts, so that slice can be reduced early); `split` = number of elements of that prefix."""
+        first_ids = {id(p) for p in first}
+        ps = [p for p in params if p.requires_grad]
+        self.params = [p for p in ps if id(p) in first_ids] + [p for p in ps if id(p) not in first_ids]
+        self.split = sum(p.numel() for p in self.params if id(p) in first_ids)
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -115,16 +122,19 @@ class FlatGrads:
                 p.grad = v
             o += p.numel()
 
-    def allreduce_mean(self, group=None):
-        """DDP semantics: grad = (1/W) * sum_r grad_r  (base_trainer.py:116-117)."""
+    def allreduce_mean(self, group=None, lo=0, hi=None):
+        """DDP semantics: grad = (1/W) * sum_r grad_r  (base_trainer.py:116-117), on elements [lo, hi) of the buffer."""
         w = dist.get_world_size(group)
         if w == 1:
             return
+        t = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
+        if t.numel() == 0:
+            return
         if self.flat.is_cuda:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
         else:  # gloo (CPU tests) has no AVG
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(w)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            t.div_(w)
 
 
 class BaseTrainer:
@@ -146,7 +156,9 @@ class BaseTrainer:
         self.device = self._setup_devices()
         self.model.to(self.device)
         self.model.device = self.device
-        self.flat = FlatGrads(self.model.parameters())
+        decs = getattr(self.model, "decoders", None)
+        self.flat = FlatGrads(self.model.parameters(), first=list(decs.parameters()) if decs is not None else ())
+        self._comm_stream = None
         self._graphs = {}
         self.set_optimizer()
         self._broadcast_parameters()
@@ -259,11 +271,20 @@ class BaseTrainer:
     def _optimizers_step(self, model_output):
         from .nn import resnet_native as RN
         self.flat.zero()
+        early = self._arm_early_allreduce()
         with RN.direct_grads(True):   # the native stacks may add their weight gradients straight into the flat buffer's views
             model_output.loss.backward()
         self.flat.rebind()
         if self.distributed:
-            self.flat.allreduce_mean()
+            if early is not None and early["fired"]:
+                # the decoder slice was reduced on the side stream while the encoders' backward ran: join, then the rest
+                early["handle"].remove()
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+                self.flat.allreduce_mean(lo=self.flat.split)
+            else:
+                if early is not None:
+                    early["handle"].remove()
+                self.flat.allreduce_mean()
         # parameters that received NO gradient (modalities missing from the whole batch) must not move: the reference's
         # zero_grad() leaves their .grad at None and the optimizer skips them (no stale-momentum / weight-decay update)
         skipped = []
@@ -276,6 +297,31 @@ class BaseTrainer:
         self.optimizer.step()
         if skipped:
             self.flat.rebind()
+
+    def _arm_early_allreduce(self):
+        """Overlap of the gradient exchange with the backward pass: the decoders' gradients (the front slice of the flat buffer,
+        the bulk of the payload) are final as soon as every decoder's backward has produced the gradient of its INPUT, long
+        before the encoders' backward ends.  A multi-tensor gradient hook on the decoder inputs (the model lists them in
+        `_decoder_inputs`; the native stacks write their weight gradients into the flat buffer inside their backward) launches the
+        all-reduce of that slice on a side stream; the step joins it before reducing the rest.  Works inside CUDA-graph capture
+        (the side stream forks from and rejoins the capturing stream).  Returns None when not applicable."""
+        zs = [z for z in (getattr(self.model, "_decoder_inputs", None) or []) if z.requires_grad]
+        if not (self.distributed and self.flat.flat.is_cuda and self.flat.split > 0 and zs and self.training_config.overlap_allreduce):
+            return None
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        state = {"fired": False}
+
+        def fire(_grads):
+            if state["fired"]:
+                return
+            state["fired"] = True
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                self.flat.allreduce_mean(hi=self.flat.split)
+
+        state["handle"] = torch.autograd.graph.register_multi_grad_hook(tuple(zs), fire, mode="all")
+        return state
 
     def _eager_step(self, inputs, epoch, batch_ratio, **extra):
         sched = self.training_config.beta_schedule
