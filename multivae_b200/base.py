@@ -132,6 +132,60 @@ class BaseMultiVAE(nn.Module):
     def prepare_step(self, epoch=1, batch_ratio=0.0):
         """Called by the trainer OUTSIDE graph capture/replay: refresh device scalars the step reads (MVAE's KL weight)."""
 
+    # The M encoders are independent and small (B images each, against C*K*B for a decoder): their kernels are bound by launch
+    # latency and ramp, not by the GPU.  On CUDA each modality's encoder runs on its own stream (forked from and joined to the
+    # current one, so it also works inside CUDA-graph capture); autograd replays every backward node on the stream of its
+    # forward, so the encoders' backward passes overlap in the same way.
+    parallel_encoders = True
+
+    def _run_encoders(self, inputs, mods, dev):
+        if not (self.parallel_encoders and dev.type == "cuda" and len(mods) > 1):
+            out = {}
+            for c in mods:
+                with self._nn_ctx():
+                    out[c] = self.encoders[c](inputs.data[c])
+            return out
+        streams = self.__dict__.setdefault("_enc_streams", {})
+        cur = torch.cuda.current_stream()
+        out = {}
+        for c in mods:
+            st = streams.get((c, dev.index))
+            if st is None:
+                st = streams[(c, dev.index)] = torch.cuda.Stream(device=dev)
+            st.wait_stream(cur)
+            with torch.cuda.stream(st), self._nn_ctx():
+                out[c] = self.encoders[c](inputs.data[c])
+        for c in mods:
+            cur.wait_stream(streams[(c, dev.index)])
+        return out
+
+    def _run_decoders(self, z_by_mod, dev):
+        """reconstruction = decoders[m](z) for every (m, z): like the encoders, small decoders (the MLP / strided-convolution
+        architectures on B or C*K*B rows) are bound by launch latency, so on CUDA each runs on its own stream.  The ResNet decoders
+        of the north star saturate the GPU on their own and stay on the current stream."""
+        from .nn.mmnist import DecoderResnetMMNIST
+        mods = list(z_by_mod)
+        heavy = any(isinstance(self.decoders[m], DecoderResnetMMNIST) for m in mods)
+        if heavy or not (self.parallel_encoders and dev.type == "cuda" and len(mods) > 1):
+            out = {}
+            for m in mods:
+                with self._nn_ctx():
+                    out[m] = self._logits(self.decoders[m](z_by_mod[m]).reconstruction)
+            return out
+        streams = self.__dict__.setdefault("_dec_streams", {})
+        cur = torch.cuda.current_stream()
+        out = {}
+        for m in mods:
+            st = streams.get((m, dev.index))
+            if st is None:
+                st = streams[(m, dev.index)] = torch.cuda.Stream(device=dev)
+            st.wait_stream(cur)
+            with torch.cuda.stream(st), self._nn_ctx():
+                out[m] = self._logits(self.decoders[m](z_by_mod[m]).reconstruction)
+        for m in mods:
+            cur.wait_stream(streams[(m, dev.index)])
+        return out
+
     def update(self):
         """Called by the trainer at the end of each epoch (base_trainer.py:738-741)."""
 

@@ -20,8 +20,8 @@ class CRMVAE(BaseMultiVAE):
     def forward(self, inputs, **kwargs):
         mods = list(inputs.data.keys())
         dev = inputs.data[mods[0]].device
-        with self._nn_ctx():
-            outs = [self.encoders[m](inputs.data[m]) for m in mods]
+        enc_out = self._run_encoders(inputs, mods, dev)
+        outs = [enc_out[m] for m in mods]
         mu = torch.stack([o.embedding.float() for o in outs])
         lv = torch.stack([o.log_covariance.float() for o in outs])
         M, B, L = mu.shape

@@ -54,18 +54,16 @@ class MMVAE(BaseMultiVAE):
         dev = inputs.data[mods[0]].device
         B = len(inputs.data[mods[0]])
         mus, sigs, zs = [], [], []
+        enc_out = self._run_encoders(inputs, mods, dev)
         for c in mods:
-            with self._nn_ctx():
-                o = self.encoders[c](inputs.data[c])
+            o = enc_out[c]
             s = log_var_to_std(o.log_covariance.float(), kind)
             mus.append(o.embedding.float()); sigs.append(s)
             zs.append(mus[-1] + s * self._noise((K, B, s.shape[-1]), dev))
         Z = torch.stack(zs)
-        recons = []
-        for r in mods:
-            with self._nn_ctx():
-                rec = self._logits(self.decoders[r](Z.reshape(-1, Z.shape[-1]))["reconstruction"])
-            recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
+        zflat = Z.reshape(-1, Z.shape[-1])
+        recs = self._run_decoders({r: zflat for r in mods}, dev)
+        recons = [recs[r].reshape(len(mods), K, B, *recs[r].shape[1:]) for r in mods]
         pz_std = log_var_to_std(self.prior_log_var, kind).reshape(-1)
         rmeta = self._recon_meta(mods, mods)
         if rescale is not None:

@@ -92,9 +92,9 @@ class MoEPlusBase(BaseMultiVAE):
         mu_u, sig_u, mu_w, sig_w, u, w, w_cross = [], [], [], [], [], [], {}
         L_, Lw_ = self.model_config.latent_dim, self.modalities_specific_dim
         self._begin_noise_pool(len(mods) * K * B * (L_ + Lw_ + (len(mods) - 1) * Lw_), dev)
+        enc_out = self._run_encoders(inputs, mods, dev)
         for c in mods:
-            with self._nn_ctx():
-                o = self.encoders[c](inputs.data[c])
+            o = enc_out[c]
             su = log_var_to_std(o.log_covariance.float(), kind)
             sw = log_var_to_std(o.style_log_covariance.float(), kind)
             mu_u.append(o.embedding.float()); sig_u.append(su)
@@ -110,15 +110,15 @@ class MoEPlusBase(BaseMultiVAE):
         U, W = torch.stack(u), torch.stack(w)  # (C,K,B,L), (C,K,B,Lw)
 
         # one batched decoder call per reconstructed modality over all conditioning modalities
-        recons = []
         self._decoder_inputs = []   # the trainer hooks these: once all of them have a gradient, every decoder's backward is done
+        z_by_mod = {}
         for r in mods:
             wz = torch.stack([W[i] if c == r else w_cross[(c, r)] for i, c in enumerate(mods)])
             z = torch.cat([U, wz], dim=-1).reshape(-1, U.shape[-1] + wz.shape[-1])
             self._decoder_inputs.append(z)
-            with self._nn_ctx():
-                rec = self._logits(self.decoders[r](z)["reconstruction"])
-            recons.append(rec.reshape(len(mods), K, B, *rec.shape[1:]))
+            z_by_mod[r] = z
+        recs = self._run_decoders(z_by_mod, dev)
+        recons = [recs[r].reshape(len(mods), K, B, *recs[r].shape[1:]) for r in mods]
         pz_mean, pz_std = self._shared_prior()
         pz_std = pz_std.reshape(-1)
         rmeta = self._recon_meta(mods, mods)

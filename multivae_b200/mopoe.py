@@ -53,8 +53,8 @@ class MoPoE(BaseMultiVAE):
     def forward(self, inputs, **kwargs):
         order = list(self.encoders.keys())
         dev = inputs.data[order[0]].device
-        with self._nn_ctx():
-            outs = [self.encoders[m](inputs.data[m]) for m in order]
+        enc_out = self._run_encoders(inputs, order, dev)
+        outs = [enc_out[m] for m in order]
         mu = torch.stack([o.embedding.float() for o in outs])
         lv = torch.stack([o.log_covariance.float() for o in outs])
         M, B, L = mu.shape
@@ -84,9 +84,10 @@ class MoPoE(BaseMultiVAE):
         kld = kl_b.mean()
         loss = 0
         one = self._const(("one", str(dev)), lambda: torch.tensor([1], dtype=torch.int32, device=dev))
+        z_by_mod, mrows = {}, {}
         for i, m in enumerate(order):
             full = z
-            mrow = inputs.masks[m].to(torch.uint8).contiguous() if hasattr(inputs, "masks") else None
+            mrows[m] = inputs.masks[m].to(torch.uint8).contiguous() if hasattr(inputs, "masks") else None
             if self.multiple_latent_spaces:
                 # modality-specific latent: sample + analytic KL(q(w_m|x_m) || N(0,I)) in one fused launch (a one-expert "PoE"
                 # without prior expert and eps = 0 is the Gaussian itself) - mopoe_model.py:171-225
@@ -100,13 +101,15 @@ class MoPoE(BaseMultiVAE):
                              eps=0.0, want_kldm=False)
                 zs, skl, _ = PoEFn.apply(smeta, smu.unsqueeze(0), slv.unsqueeze(0))
                 full = torch.cat([z, zs], dim=-1)
-                if mrow is not None:
+                if mrows[m] is not None:
                     skl = skl * inputs.masks[m].float()
                 kld = kld + skl.mean() * self.model_config.beta_style
-            with self._nn_ctx():
-                rec = self._logits(self.decoders[m](full).reconstruction)
+            z_by_mod[m] = full
+        recs = self._run_decoders(z_by_mod, dev)
+        for m in order:
+            rec = recs[m]
             dist, scale = self.recon_dists[m]
-            nll = ReconNLLFn.apply(rec, self._target(inputs, m, rec), mrow, dist, scale, float(self.rescale_factors[m]))
+            nll = ReconNLLFn.apply(rec, self._target(inputs, m, rec), mrows[m], dist, scale, float(self.rescale_factors[m]))
             results["recon_" + m] = nll.mean()
             loss = loss + results["recon_" + m]
         # the reference accumulates the style KLs in place into the tensor it also reports as "joint_divergence" (:166,222)

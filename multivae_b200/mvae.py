@@ -56,8 +56,7 @@ class MVAE(BaseMultiVAE):
                 for i in choice(np.arange(len(self.subsets)), size=self.k, replace=False):
                     subsets.append(self.subsets[i])
         dev = inputs.data[order[0]].device
-        with self._nn_ctx():
-            outs = {m: self.encoders[m](inputs.data[m]) for m in order}
+        outs = self._run_encoders(inputs, order, dev)
         mu = torch.stack([outs[m].embedding.float() for m in order])
         lv = torch.stack([outs[m].log_covariance.float() for m in order])
         M, B, L = mu.shape

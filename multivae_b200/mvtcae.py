@@ -18,8 +18,8 @@ class MVTCAE(BaseMultiVAE):
     def forward(self, inputs, **kwargs):
         mods = list(inputs.data.keys())
         dev = inputs.data[mods[0]].device
-        with self._nn_ctx():
-            outs = [self.encoders[m](inputs.data[m]) for m in mods]
+        enc_out = self._run_encoders(inputs, mods, dev)
+        outs = [enc_out[m] for m in mods]
         mu = torch.stack([o.embedding.float() for o in outs])
         lv = torch.stack([o.log_covariance.float() for o in outs])
         M, B, L = mu.shape
@@ -34,12 +34,12 @@ class MVTCAE(BaseMultiVAE):
         joint_kld = kl_b.sum()
         results["joint_divergence"] = joint_kld
         loss_rec = 0
+        recs = self._run_decoders({m: z for m in mods}, dev)
         for i, m in enumerate(mods):
             # the reference iterates self.encoders.keys(); with complete inputs the orders coincide
-            with self._nn_ctx():
-                rec = self.decoders[m](z).reconstruction
+            rec = recs[m]
             dist, scale = self.recon_dists[m]
-            nll = ReconNLLFn.apply(self._logits(rec), self._target(inputs, m, rec), None if masks is None else masks[i],
+            nll = ReconNLLFn.apply(rec, self._target(inputs, m, rec), None if masks is None else masks[i],
                                    dist, scale, float(self.rescale_factors[m]))
             results[m] = nll.sum()
             loss_rec = loss_rec + results[m]

@@ -317,6 +317,8 @@ class BaseTrainer:
                 return
             state["fired"] = True
             self._comm_stream.wait_stream(torch.cuda.current_stream())
+            for st in (getattr(self.model, "_dec_streams", None) or {}).values():   # decoders that ran on their own streams
+                self._comm_stream.wait_stream(st)
             with torch.cuda.stream(self._comm_stream):
                 self.flat.allreduce_mean(hi=self.flat.split)
 
