@@ -159,31 +159,32 @@ class BaseMultiVAE(nn.Module):
             cur.wait_stream(streams[(c, dev.index)])
         return out
 
-    def _run_decoders(self, z_by_mod, dev):
+    def _run_decoders(self, z_by_mod, dev, mod_of=None):
         """reconstruction = decoders[m](z) for every (m, z): like the encoders, small decoders (the MLP / strided-convolution
         architectures on B or C*K*B rows) are bound by launch latency, so on CUDA each runs on its own stream.  The ResNet decoders
         of the north star saturate the GPU on their own and stay on the current stream."""
         from .nn.mmnist import DecoderResnetMMNIST
-        mods = list(z_by_mod)
-        heavy = any(isinstance(self.decoders[m], DecoderResnetMMNIST) for m in mods)
-        if heavy or not (self.parallel_encoders and dev.type == "cuda" and len(mods) > 1):
+        mod_of = mod_of or (lambda k: k)   # keys are modality names unless the caller decodes a modality several times
+        keys = list(z_by_mod)
+        heavy = any(isinstance(self.decoders[mod_of(k)], DecoderResnetMMNIST) for k in keys)
+        if heavy or not (self.parallel_encoders and dev.type == "cuda" and len(keys) > 1):
             out = {}
-            for m in mods:
+            for k in keys:
                 with self._nn_ctx():
-                    out[m] = self._logits(self.decoders[m](z_by_mod[m]).reconstruction)
+                    out[k] = self._logits(self.decoders[mod_of(k)](z_by_mod[k]).reconstruction)
             return out
         streams = self.__dict__.setdefault("_dec_streams", {})
         cur = torch.cuda.current_stream()
         out = {}
-        for m in mods:
-            st = streams.get((m, dev.index))
+        for k in keys:
+            st = streams.get((k, dev.index))
             if st is None:
-                st = streams[(m, dev.index)] = torch.cuda.Stream(device=dev)
+                st = streams[(k, dev.index)] = torch.cuda.Stream(device=dev)
             st.wait_stream(cur)
             with torch.cuda.stream(st), self._nn_ctx():
-                out[m] = self._logits(self.decoders[m](z_by_mod[m]).reconstruction)
-        for m in mods:
-            cur.wait_stream(streams[(m, dev.index)])
+                out[k] = self._logits(self.decoders[mod_of(k)](z_by_mod[k]).reconstruction)
+        for k in keys:
+            cur.wait_stream(streams[(k, dev.index)])
         return out
 
     def update(self):

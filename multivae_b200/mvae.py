@@ -62,7 +62,8 @@ class MVAE(BaseMultiVAE):
         M, B, L = mu.shape
         has_masks = hasattr(inputs, "masks")
         masks = self._stack_masks(inputs, order)
-        total, metrics, len_batch = 0, {}, 0.0
+        # phase 1: the subset posteriors and their samples (one fused launch per subset)
+        jobs = []   # (subset, n, keep, z, kl_b) or (subset, 0, ...) for a subset no sample has a modality of
         for s in subsets:
             # samples with at least one available modality of the subset (_filter_inputs_with_masks, :115-135)
             if has_masks:
@@ -71,8 +72,7 @@ class MVAE(BaseMultiVAE):
                     keep = keep | inputs.masks[m].bool()
                 n = int(keep.sum())
                 if n == 0:
-                    total = total + torch.tensor(0.0, requires_grad=True, device=dev)
-                    len_batch = 0.0
+                    jobs.append((s, 0, None, None, None))
                     continue
                 wrow = keep.float().reshape(1, B).contiguous()
             else:
@@ -91,17 +91,26 @@ class MVAE(BaseMultiVAE):
             meta = dict(masks=masks, subsets=bits, sel=None, w=wrow, w_uniform=1.0, noise=noise.contiguous(),
                         prior_mode=1, stable=True, eps=0.0, want_kldm=False)  # prior expert always + stable_poe (:75-79)
             z, kl_b, _ = PoEFn.apply(meta, mu, lv)
+            jobs.append((s, n, keep, z, kl_b))
+        # phase 2: every (subset, modality) decoder pass, independent of each other (own streams for the small decoders)
+        recs = self._run_decoders({(j, m): job[3] for j, job in enumerate(jobs) if job[1] for m in self.decoders if m in job[0]}, dev,
+                                  mod_of=lambda k: k[1])
+        # phase 3: the subset ELBOs
+        total, metrics, len_batch = 0, {}, 0.0
+        for j, (s, n, keep, z, kl_b) in enumerate(jobs):
+            if n == 0:
+                total = total + torch.tensor(0.0, requires_grad=True, device=dev)
+                len_batch = 0.0
+                continue
             elbo = 0
             for m in self.decoders:
                 if m in s:
-                    with self._nn_ctx():
-                        rec = self.decoders[m](z).reconstruction
+                    rec = recs[(j, m)]
                     dist, scale = self.recon_dists[m]
                     mk = None
                     if has_masks:
                         mk = (inputs.masks[m].bool() & keep).to(torch.uint8).contiguous()
-                    nll = ReconNLLFn.apply(self._logits(rec), self._target(inputs, m, rec), mk, dist, scale,
-                                           float(self.rescale_factors[m]))
+                    nll = ReconNLLFn.apply(rec, self._target(inputs, m, rec), mk, dist, scale, float(self.rescale_factors[m]))
                     elbo = elbo + nll.sum()
             kld = kl_b.sum()
             elbo = elbo + kld * beta

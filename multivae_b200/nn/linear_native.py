@@ -99,6 +99,7 @@ class MLPChainFn(torch.autograd.Function):
         packs = _pack_weights([[w for w, _ in l] for l in layers])
         h = _to_bf16_padded(x2)
         saved_in = []
+        last_buf = None
         for li, (l, wb) in enumerate(zip(layers, packs)):
             N, K = wb.shape[0], l[0][0].shape[1]
             bias = l[0][1].detach().float() if len(l) == 1 else torch.cat([b.detach().float() for _, b in l])
@@ -109,10 +110,14 @@ class MLPChainFn(torch.autograd.Function):
                 gemm(h, wb, Bt, N, K, out, bias=bias.contiguous(), act=acts[li], out_kind=1, tag=f"fc{li}")
             else:
                 N8 = _pad8(N)
-                out = torch.empty(Bt, N8, device=dev, dtype=torch.bfloat16)[:, :N]
+                # ragged widths: the padding columns are never written by the clipped TMA store; zero them once so that whatever
+                # reads the whole [Bt, N8] buffer (the activation derivative of the last layer) sees finite values
+                buf = torch.empty(Bt, N8, device=dev, dtype=torch.bfloat16) if N8 == N else torch.zeros(Bt, N8, device=dev, dtype=torch.bfloat16)
+                out = buf[:, :N]
+                last_buf = buf
                 gemm(h, wb, Bt, N, K, out, bias=bias.contiguous(), act=acts[li], out_kind=0, tag=f"fc{li}")
             h = out
-        ctx.save_for_backward(*saved_in, *packs, h)
+        ctx.save_for_backward(*saved_in, *packs, h, last_buf if last_buf is not None else h)
         ctx.layers_meta = [[(w.shape[0], w.shape[1]) for w, _ in l] for l in layers]
         ctx.params = params
         ctx.spec = spec
@@ -125,7 +130,7 @@ class MLPChainFn(torch.autograd.Function):
         acts, groups, out_fp32 = ctx.spec
         n = ctx.n_layers
         saved = ctx.saved_tensors
-        ins, packs, y = saved[:n], saved[n:2 * n], saved[2 * n]
+        ins, packs, y, ybuf = saved[:n], saved[n:2 * n], saved[2 * n], saved[2 * n + 1]
         lib = C.lib()
         dev = g.device
         g2 = g.reshape(-1, g.shape[-1])
@@ -133,11 +138,18 @@ class MLPChainFn(torch.autograd.Function):
         targets = RN._direct_targets(ctx.params)   # .grad tensors when the trainer opted in, else None
         # gradient w.r.t. the last layer's pre-activation, as the bf16 GEMM operand
         if acts[-1] in ("sigmoid", "relu", "lrelu"):
-            assert Nl % 8 == 0 and y.stride(0) == Nl, "activated layers must have N % 8 == 0"
-            gc = g2.contiguous()
-            d = torch.empty(Bt, Nl, device=dev, dtype=torch.bfloat16)
-            C.check(lib.mv_act_bwd(C.ptr(gc), C.dtype_code(gc), C.ptr(y), C.ptr(d), Bt * Nl, _ACT_CODE[acts[-1]], 0.2 if acts[-1] == "lrelu" else 0.0,
-                                   C.stream()), "mv_act_bwd")
+            N8 = _pad8(Nl)
+            if N8 == Nl:
+                gc, yb = g2.contiguous(), y
+            else:   # ragged width: both operands as whole [Bt, N8] buffers (zero padding columns on both sides)
+                gc = torch.zeros(Bt, N8, device=dev, dtype=g2.dtype)
+                gc[:, :Nl].copy_(g2)
+                yb = ybuf   # the whole [Bt, N8] buffer behind y (zero padding columns)
+                assert yb.shape == (Bt, N8) and yb.is_contiguous()
+            dbuf = torch.empty(Bt, N8, device=dev, dtype=torch.bfloat16)
+            C.check(lib.mv_act_bwd(C.ptr(gc), C.dtype_code(gc), C.ptr(yb), C.ptr(dbuf), Bt * N8, _ACT_CODE[acts[-1]],
+                                   0.2 if acts[-1] == "lrelu" else 0.0, C.stream()), "mv_act_bwd")
+            d = dbuf[:, :Nl]
         else:
             d = _to_bf16_padded(g2)
         grads = [None] * len(ctx.params)
