@@ -127,6 +127,24 @@ int mv_moe_lw_fwd(const float* u, const float* w, const float* mu_u, const float
                   int C, int K, int B, int L, int Lw, int latent_kind, int loss_kind, float beta,
                   int detach_post, int skip_u_prior, void* stream);
 
+/* Reparameterised sampling of the MoE family in one launch per direction (replaces _log_var_to_std + the rsample / stack / cat glue
+ * of mmvaePlus_model.py:113-186 and mmvae_model.py:66-130, and their autograd twins):
+ *   sig_u = std(lv_u) [C,B,L], sig_w = std(lv_w) [C,B,Lw]    std_kind 0: softmax(lv) * dim + 1e-6, 1: exp(lv / 2), 2: softplus(lv) + 1e-6
+ *   U [C,K,B,L] = mu_u + sig_u * noise_u,  W [C,K,B,Lw] = mu_w + sig_w * noise_w
+ *   Z [C(recon r),C(cond c),K,B,L+Lw] = cat(U[c], r == c ? W[c] : prior_mean[r] + prior_std[r] * noise_x[c, j(r)])   decoder inputs
+ * noise_x [C,C-1,K,B,Lw] holds, for every conditioning modality, one standard draw per OTHER modality (in modality order).
+ * Lw = 0 (MMVAE): w / prior / Z pointers are NULL.  The backward sums the gradients reaching the samples (g_U, g_W: direct
+ * terms of the ELBO; g_Z: the decoders), multiplies them by the DReG weights wk [C,K,B] when given (mmvaePlus_model.py:330-338;
+ * prior samples are not weighted), adds the gradients arriving at sig_u / sig_w themselves and applies the derivative of std():
+ * outputs g_mu_*, g_lv_* (same shapes as the inputs) and g_prior_std [C,Lw] (summed over c, k, b). */
+int mv_moe_sample_fwd(const float* mu_u, const float* lv_u, const float* mu_w, const float* lv_w, const float* prior_mean,
+                      const float* prior_std, const float* noise_u, const float* noise_w, const float* noise_x, int std_kind,
+                      float* sig_u, float* sig_w, float* U, float* W, float* Z, int C, int K, int B, int L, int Lw, void* stream);
+int mv_moe_sample_bwd(const float* lv_u, const float* lv_w, const float* sig_u, const float* sig_w, const float* noise_u,
+                      const float* noise_w, const float* noise_x, const float* g_U, const float* g_W, const float* g_Z,
+                      const float* g_sig_u, const float* g_sig_w, const float* wk, int std_kind, float* g_mu_u, float* g_lv_u,
+                      float* g_mu_w, float* g_lv_w, float* g_prior_std, int C, int K, int B, int L, int Lw, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused posterior aggregation, PoE family (MVTCAE, MVAE, MoPoE).
  *   mu, lv      [M,B,L] f32  unimodal posterior parameters (encoder outputs)

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmultivae_b200.so")
 MV_F32, MV_BF16 = 0, 1
 DIST = {"normal": 0, "laplace": 1, "bernoulli": 2, "categorical": 3}
 LATENT = {"laplace_with_softmax": 0, "normal": 1, "normal_with_softplus": 1}
+STD_KIND = {"laplace_with_softmax": 0, "normal": 1, "normal_with_softplus": 2}   # _log_var_to_std variants
 LOSS = {"iwae_looser": 0, "dreg_looser": 1}
 ACT = {"none": 0, "relu": 1, "lrelu": 2, "sigmoid": 3}
 
@@ -87,6 +88,8 @@ _PROTOS = {
     "mv_gauss_kl_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
     "mv_gauss_kl_bwd": [c_void_p] * 9 + [c_int64, c_int, c_int, c_void_p],
     "mv_moe_lw_fwd": [c_void_p] * 21 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p],
+    "mv_moe_sample_fwd": [c_void_p] * 9 + [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_void_p],
+    "mv_moe_sample_bwd": [c_void_p] * 13 + [c_int] + [c_void_p] * 5 + [c_int] * 5 + [c_void_p],
     "mv_poe_fwd": [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float] +
                   [c_void_p] * 5 + [c_int] * 3 + [c_void_p],
     "mv_tapgemm": [ctypes.POINTER(TapGemmArgs), c_void_p],

@@ -153,6 +153,73 @@ class MoEElboFn(torch.autograd.Function):
                 (g_pz.sum(0) * s) if need[7] else None, *g_recons, *g_extra)
 
 
+class MoESampleFn(torch.autograd.Function):
+    """sig = std(log-variance), K reparameterised samples of every unimodal posterior and the decoder inputs of all (cond, recon)
+    modality pairs in one launch (mv_moe_sample_fwd / mv_moe_sample_bwd).
+
+    forward(meta, mu_u, lv_u, mu_w, lv_w, prior_mean, prior_std, e_u, e_w, e_x) ->  (sig_u, sig_w, U, W, Z)
+      mu_u, lv_u (C,B,L); mu_w, lv_w (C,B,Lw) or None; prior_mean, prior_std (C,Lw) of the private codes' priors;
+      e_u (C,K,B,L), e_w (C,K,B,Lw), e_x (C,C-1,K,B,Lw) standard draws;  Z (C_recon, C_cond, K, B, L+Lw).
+    meta is the dict MoEElboFn fills: the backward reads meta["wk"] (DReG: detach) to weight the samples' gradient."""
+
+    @staticmethod
+    def forward(ctx, meta, mu_u, lv_u, mu_w, lv_w, pm, sp, e_u, e_w, e_x):
+        lib = C.lib()
+        Cn, K, B, L = e_u.shape
+        Lw = 0 if mu_w is None else mu_w.shape[-1]
+        dev = mu_u.device
+        mu_u, lv_u, e_u = _f32c(mu_u), _f32c(lv_u), _f32c(e_u)
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        sig_u, U = f(Cn, B, L), f(Cn, K, B, L)
+        if Lw:
+            mu_w, lv_w, pm, sp, e_w = _f32c(mu_w), _f32c(lv_w), _f32c(pm), _f32c(sp), _f32c(e_w)
+            e_x = _f32c(e_x) if e_x is not None else None
+            sig_w, W, Z = f(Cn, B, Lw), f(Cn, K, B, Lw), f(Cn, Cn, K, B, L + Lw)
+        else:
+            sig_w = W = Z = None
+        kind = meta["std_kind"]
+        C.check(lib.mv_moe_sample_fwd(C.ptr(mu_u), C.ptr(lv_u), C.ptr(mu_w), C.ptr(lv_w), C.ptr(pm) if Lw else None, C.ptr(sp) if Lw else None,
+                                      C.ptr(e_u), C.ptr(e_w) if Lw else None, C.ptr(e_x) if Lw else None, kind, C.ptr(sig_u), C.ptr(sig_w),
+                                      C.ptr(U), C.ptr(W), C.ptr(Z), Cn, K, B, L, Lw, C.stream()), "mv_moe_sample_fwd")
+        ctx.meta, ctx.dims = meta, (Cn, K, B, L, Lw)
+        ctx.save_for_backward(lv_u, sig_u, e_u, *((lv_w, sig_w, e_w) if Lw else ()), *((e_x,) if (Lw and e_x is not None) else ()))
+        ctx.has_ex = bool(Lw and e_x is not None)
+        empty = torch.empty(0, device=dev)
+        return sig_u, (sig_w if Lw else empty), U, (W if Lw else empty), (Z if Lw else empty)
+
+    @staticmethod
+    def backward(ctx, g_sig_u, g_sig_w, g_U, g_W, g_Z):
+        lib = C.lib()
+        Cn, K, B, L, Lw = ctx.dims
+        meta = ctx.meta
+        sv = ctx.saved_tensors
+        lv_u, sig_u, e_u = sv[:3]
+        lv_w = sig_w = e_w = e_x = None
+        if Lw:
+            lv_w, sig_w, e_w = sv[3:6]
+            e_x = sv[6] if ctx.has_ex else None
+        c = lambda t: None if t is None else _f32c(t)  # noqa: E731
+        g_sig_u, g_U = c(g_sig_u), c(g_U)
+        if Lw:
+            g_sig_w, g_W, g_Z = c(g_sig_w), c(g_W), c(g_Z)
+        else:
+            g_sig_w = g_W = g_Z = None
+        wk = meta["wk"] if meta.get("detach") else None   # DReG: weight the samples' gradient once more (no tensor hooks needed)
+        dev = lv_u.device
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        g_mu_u, g_lv_u = f(Cn, B, L), f(Cn, B, L)
+        g_mu_w = g_lv_w = g_sp = None
+        if Lw:
+            g_mu_w, g_lv_w, g_sp = f(Cn, B, Lw), f(Cn, B, Lw), f(Cn, Lw)
+        C.check(lib.mv_moe_sample_bwd(C.ptr(lv_u), C.ptr(lv_w), C.ptr(sig_u), C.ptr(sig_w), C.ptr(e_u), C.ptr(e_w), C.ptr(e_x), C.ptr(g_U),
+                                      C.ptr(g_W), C.ptr(g_Z), C.ptr(g_sig_u), C.ptr(g_sig_w), C.ptr(wk), meta["std_kind"], C.ptr(g_mu_u),
+                                      C.ptr(g_lv_u), C.ptr(g_mu_w), C.ptr(g_lv_w), C.ptr(g_sp), Cn, K, B, L, Lw, C.stream()),
+                "mv_moe_sample_bwd")
+        need = ctx.needs_input_grad
+        return (None, g_mu_u if need[1] else None, g_lv_u if need[2] else None, g_mu_w if (Lw and need[3]) else None,
+                g_lv_w if (Lw and need[4]) else None, None, g_sp if (Lw and need[6]) else None, None, None, None)
+
+
 def log_var_to_std(log_var, kind):
     """mmvaePlus_model.py:113-123 / mmvae_model.py:66-74 (tiny (B,L) tensors; stays in torch)."""
     if kind == "laplace_with_softmax":

@@ -10,7 +10,7 @@ import torch.nn as nn
 from . import _cabi as C
 from .base import BaseMultiVAE
 from .containers import ModelOutput, drop_unused_modalities
-from .elbo import MoEElboFn, log_var_to_std, standard_noise
+from .elbo import MoEElboFn, MoESampleFn, log_var_to_std, standard_noise
 
 
 class MMVAE(BaseMultiVAE):
@@ -53,14 +53,17 @@ class MMVAE(BaseMultiVAE):
         mods = list(inputs.data.keys())
         dev = inputs.data[mods[0]].device
         B = len(inputs.data[mods[0]])
-        mus, sigs, zs = [], [], []
         enc_out = self._run_encoders(inputs, mods, dev)
-        for c in mods:
-            o = enc_out[c]
-            s = log_var_to_std(o.log_covariance.float(), kind)
-            mus.append(o.embedding.float()); sigs.append(s)
-            zs.append(mus[-1] + s * self._noise((K, B, s.shape[-1]), dev))
-        Z = torch.stack(zs)
+        mu = torch.stack([enc_out[c].embedding.float() for c in mods])
+        lv = torch.stack([enc_out[c].log_covariance.float() for c in mods])
+        L_ = mu.shape[-1]
+        if self.noise_source is not None:
+            e = torch.stack([self._noise((K, B, L_), dev) for _ in mods])
+        else:
+            e = standard_noise((len(mods), K, B, L_), kind, dev)
+        meta = dict(std_kind=C.STD_KIND[kind], detach=detach)
+        # std(log-variance) + the K reparameterised samples of every posterior in one launch (mv_moe_sample_fwd)
+        sig, _, Z, _, _ = MoESampleFn.apply(meta, mu, lv, None, None, None, None, e, None, None)
         zflat = Z.reshape(-1, Z.shape[-1])
         recs = self._run_decoders({r: zflat for r in mods}, dev)
         recons = [recs[r].reshape(len(mods), K, B, *recs[r].shape[1:]) for r in mods]
@@ -68,19 +71,17 @@ class MMVAE(BaseMultiVAE):
         rmeta = self._recon_meta(mods, mods)
         if rescale is not None:
             rmeta = [(d, sc, float(rescale), row) for d, sc, _, row in rmeta]
-        meta = dict(x=[self._target(inputs, r, rec) for r, rec in zip(mods, recons)],
+        meta.update(x=[self._target(inputs, r, rec) for r, rec in zip(mods, recons)],
                     pz_mean=self.prior_mean.detach().reshape(-1).float().contiguous(),
                     masks=self._stack_masks(inputs, mods), recon=rmeta,
-                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=1.0, detach=detach)
-        loss = MoEElboFn.apply(meta, Z, None, torch.stack(mus), torch.stack(sigs), None, None, pz_std, *recons)
-        if detach and Z.requires_grad:
-            wk = meta["wk"].unsqueeze(-1)
-            Z.register_hook(lambda g: g * wk)
+                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=1.0)
+        # DReG: MoESampleFn's backward multiplies the samples' gradient by meta["wk"] (filled in by the call below)
+        loss = MoEElboFn.apply(meta, Z, None, mu, sig, None, None, pz_std, *recons)
         extra = {}
         if detailed:   # the reference's detailed_output fields (mmvae_model.py:151-156)
-            extra = dict(qz_xs={c: self.post_dist(mus[i], sigs[i]) for i, c in enumerate(mods)},
-                         qz_xs_detach={c: self.post_dist(mus[i].detach(), sigs[i].detach()) for i, c in enumerate(mods)},
-                         zss={c: zs[i] for i, c in enumerate(mods)},
+            extra = dict(qz_xs={c: self.post_dist(mu[i], sig[i]) for i, c in enumerate(mods)},
+                         qz_xs_detach={c: self.post_dist(mu[i].detach(), sig[i].detach()) for i, c in enumerate(mods)},
+                         zss={c: Z[i] for i, c in enumerate(mods)},
                          recon={c: {r: recons[j][i] for j, r in enumerate(mods)} for i, c in enumerate(mods)})
         return loss, meta, extra
 

@@ -13,7 +13,7 @@ import torch.nn as nn
 from . import _cabi as C
 from .base import BaseMultiVAE
 from .containers import ModelOutput, drop_unused_modalities
-from .elbo import MoEElboFn, log_var_to_std, standard_noise
+from .elbo import MoEElboFn, MoESampleFn, log_var_to_std, standard_noise
 from .nn.default_architectures import BaseDictDecodersMultiLatents, BaseDictEncoders_MultiLatents
 
 
@@ -87,36 +87,38 @@ class MoEPlusBase(BaseMultiVAE):
         dev = inputs.data[mods[0]].device
         B = len(inputs.data[mods[0]])
 
-        # encoders + reparameterised samples, in the reference's noise-consumption order (per cond modality:
-        # u, w, then one prior draw per *other* modality: mmvaePlus_model.py:136-186)
-        mu_u, sig_u, mu_w, sig_w, u, w, w_cross = [], [], [], [], [], [], {}
+        # encoders, then ONE launch for std(log-variance), the K reparameterised samples of every posterior and the decoder
+        # inputs of all (conditioning, reconstructed) pairs (mv_moe_sample_fwd).  The standard draws are consumed in the
+        # reference's order (per conditioning modality: u, w, then one prior draw per *other* modality: mmvaePlus_model.py:136-186)
         L_, Lw_ = self.model_config.latent_dim, self.modalities_specific_dim
-        self._begin_noise_pool(len(mods) * K * B * (L_ + Lw_ + (len(mods) - 1) * Lw_), dev)
+        Cn = len(mods)
         enc_out = self._run_encoders(inputs, mods, dev)
-        for c in mods:
-            o = enc_out[c]
-            su = log_var_to_std(o.log_covariance.float(), kind)
-            sw = log_var_to_std(o.style_log_covariance.float(), kind)
-            mu_u.append(o.embedding.float()); sig_u.append(su)
-            mu_w.append(o.style_embedding.float()); sig_w.append(sw)
-            u.append(mu_u[-1] + su * self._noise((K, B, su.shape[-1]), dev))
-            w.append(mu_w[-1] + sw * self._noise((K, B, sw.shape[-1]), dev))
-            for r in mods:
-                if r != c:
-                    pm_r, plv_r = self._cross_prior(r)
-                    sp = log_var_to_std(plv_r, kind)
-                    w_cross[(c, r)] = pm_r + sp * self._noise((K, B, sp.shape[-1]), dev)
-        self._noise_pool = None
-        U, W = torch.stack(u), torch.stack(w)  # (C,K,B,L), (C,K,B,Lw)
+        mu_u = torch.stack([enc_out[c].embedding.float() for c in mods])
+        lv_u = torch.stack([enc_out[c].log_covariance.float() for c in mods])
+        mu_w = torch.stack([enc_out[c].style_embedding.float() for c in mods])
+        lv_w = torch.stack([enc_out[c].style_log_covariance.float() for c in mods])
+        if self.noise_source is not None:
+            eu, ew, ex = [], [], []
+            for c in mods:
+                eu.append(self._noise((K, B, L_), dev))
+                ew.append(self._noise((K, B, Lw_), dev))
+                ex += [self._noise((K, B, Lw_), dev) for r in mods if r != c]
+            e_u, e_w = torch.stack(eu), torch.stack(ew)
+            e_x = torch.stack(ex).view(Cn, Cn - 1, K, B, Lw_) if Cn > 1 else None
+        else:   # i.i.d. draws: one batched draw, three views of it (same distribution as the reference's sequence of rsample calls)
+            n_u, n_w, n_x = Cn * K * B * L_, Cn * K * B * Lw_, Cn * (Cn - 1) * K * B * Lw_
+            pool = standard_noise((n_u + n_w + n_x,), kind, dev)
+            e_u, e_w = pool[:n_u].view(Cn, K, B, L_), pool[n_u:n_u + n_w].view(Cn, K, B, Lw_)
+            e_x = pool[n_u + n_w:].view(Cn, Cn - 1, K, B, Lw_) if Cn > 1 else None
+        priors = [self._cross_prior(r) for r in mods]
+        pm = torch.cat([p_[0] for p_ in priors], dim=0)                               # (C, Lw)
+        sp = log_var_to_std(torch.cat([p_[1] for p_ in priors], dim=0), kind)         # std per modality prior (softmax over its Lw dims)
+        meta = dict(std_kind=C.STD_KIND[kind], detach=detach)
+        sig_u, sig_w, U, W, Z = MoESampleFn.apply(meta, mu_u, lv_u, mu_w, lv_w, pm, sp, e_u, e_w, e_x)
 
         # one batched decoder call per reconstructed modality over all conditioning modalities
-        self._decoder_inputs = []   # the trainer hooks these: once all of them have a gradient, every decoder's backward is done
-        z_by_mod = {}
-        for r in mods:
-            wz = torch.stack([W[i] if c == r else w_cross[(c, r)] for i, c in enumerate(mods)])
-            z = torch.cat([U, wz], dim=-1).reshape(-1, U.shape[-1] + wz.shape[-1])
-            self._decoder_inputs.append(z)
-            z_by_mod[r] = z
+        z_by_mod = {r: Z[i].reshape(-1, L_ + Lw_) for i, r in enumerate(mods)}
+        self._decoder_inputs = list(z_by_mod.values())   # the trainer hooks these: all have a gradient <=> every decoder's backward is done
         recs = self._run_decoders(z_by_mod, dev)
         recons = [recs[r].reshape(len(mods), K, B, *recs[r].shape[1:]) for r in mods]
         pz_mean, pz_std = self._shared_prior()
@@ -124,21 +126,16 @@ class MoEPlusBase(BaseMultiVAE):
         rmeta = self._recon_meta(mods, mods)
         if rescale is not None:
             rmeta = [(d, sc, float(rescale), row) for d, sc, _, row in rmeta]
-        meta = dict(x=[self._target(inputs, r, rec) for r, rec in zip(mods, recons)],
+        meta.update(x=[self._target(inputs, r, rec) for r, rec in zip(mods, recons)],
                     pz_mean=pz_mean.detach().reshape(-1).float().contiguous(),
                     masks=self._stack_masks(inputs, mods), recon=rmeta,
-                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=self.beta if beta is None else beta, detach=detach,
+                    latent_kind=C.LATENT[kind], loss_kind=C.LOSS[loss_name], beta=self.beta if beta is None else beta,
                     skip_u_prior=self.skip_u_prior)
         extra = self._extra_lw(U, meta["beta"])
         meta["has_extra"] = extra is not None
-        loss = MoEElboFn.apply(meta, U, W, torch.stack(mu_u), torch.stack(sig_u), torch.stack(mu_w),
-                               torch.stack(sig_w), pz_std, *recons, *(() if extra is None else (extra,)))
-        if detach:
-            # DReG: the gradient reaching the samples is multiplied once more by wk (mmvaePlus_model.py:330-338)
-            wk = meta["wk"].unsqueeze(-1)
-            if U.requires_grad:
-                U.register_hook(lambda g: g * wk)
-                W.register_hook(lambda g: g * wk)
+        # DReG: the gradient reaching the samples is multiplied once more by wk (mmvaePlus_model.py:330-338): MoESampleFn's backward
+        # reads meta["wk"], which the call below fills in
+        loss = MoEElboFn.apply(meta, U, W, mu_u, sig_u, mu_w, sig_w, pz_std, *recons, *(() if extra is None else (extra,)))
         return loss, meta
 
 
