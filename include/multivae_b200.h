@@ -322,6 +322,9 @@ int mv_avgpool3s2_fwd(const void* in, void* out, int n_img, int H, int W, int C,
 int mv_avgpool3s2_bwd(const void* g_out, const void* act, void* g_in, void* g_pre, int n_img, int H, int W, int C, float alpha,
                       float slope, void* stream);
 int mv_scale_dact(const void* g, const void* act, void* out, int64_t P, int C, float alpha, float slope, void* stream);
+/*   mv_lrelu_fwd       out = leaky_relu(x, slope) on a [P, C] matrix: the pre-activation `actvn(x)` of the CUB ResNet blocks
+ *                      (models/nn/cub.py:281-283, 296-299), whose shortcut reads the raw x */
+int mv_lrelu_fwd(const void* x, void* out, int64_t P, int C, float slope, void* stream);
 
 /* All convolution-weight packs of a network in one launch.  Each item turns an fp32 Conv2d weight [N, C, kh, kw] (T = kh*kw)
  * into the bf16 operand matrices of mv_tapgemm: dst_fwd [T * Npad, Cpad] (row t*Npad + n, column c) for the forward pass and

@@ -217,6 +217,17 @@ __global__ void __launch_bounds__(256) scale_dact_kernel(const bf16* __restrict_
   }
 }
 
+// out = leaky_relu(x)   ([P, C] bf16; halo rows are zero and stay zero): the pre-activation of the CUB ResNet blocks
+__global__ void __launch_bounds__(256) lrelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t nvec, float slope) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float f[8];
+    unpack8f(ld_stream(x + i * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : slope * f[e];
+    st_stream(out + i * 8, pack8f(f));
+  }
+}
+
 // out[n] += sum_p G[p, n]   (N <= 256, N % 8 == 0)
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ G, int64_t P, int ld, int N, float* __restrict__ out) {
   __shared__ float red[256 * 8];
@@ -317,6 +328,15 @@ extern "C" int mv_scale_dact(const void* g, const void* act, void* out, int64_t 
   scale_dact_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(g), static_cast<const bf16*>(act),
                                                                            static_cast<bf16*>(out), nvec, alpha, slope);
   MV_CHECK_LAUNCH("mv_scale_dact");
+  return MV_OK;
+}
+
+extern "C" int mv_lrelu_fwd(const void* x, void* out, int64_t P, int C, float slope, void* stream) {
+  MV_CHECK_ARG(x && out && P > 0 && C % 8 == 0, "mv_lrelu_fwd: bad arguments");
+  const int64_t nvec = P * (C / 8);
+  const int blocks = int(std::min<int64_t>((nvec + 255) / 256, int64_t(num_sms()) * 16));
+  lrelu_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), static_cast<bf16*>(out), nvec, slope);
+  MV_CHECK_LAUNCH("mv_lrelu_fwd");
   return MV_OK;
 }
 

@@ -44,6 +44,7 @@ enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 =
 
 struct Conv3Params {
   int P, m_tiles, n_kc, row_shift, R;
+  int n_box, box_rows;      // input window = n_box TMA boxes of box_rows rows
   int in_stages;
   uint32_t in_stage_bytes, w_bytes;
   const float* bias;
@@ -147,8 +148,10 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int kc = 0; kc < p.n_kc; ++kc) {
         tc::mbar_wait(&in_empty[is], iph ^ 1);
         if (tc::elect_one()) {
-          tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * 128u);
-          tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], kc * 64, p0 - p.row_shift);
+          tc::mbar_expect_tx(&in_full[is], uint32_t(p.n_box * p.box_rows) * 128u);
+          for (int bx = 0; bx < p.n_box; ++bx)   // windows taller than the 256-row TMA box limit arrive as two boxes
+            tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes + size_t(bx * p.box_rows) * 128u, &tmA, &in_full[is], kc * 64,
+                            p0 - p.row_shift + bx * p.box_rows);
         }
         __syncwarp();
         if (++is == p.in_stages) { is = 0; iph ^= 1; }
@@ -452,6 +455,7 @@ constexpr uint32_t kH3WBox = 48u * 128u;
 
 struct Head3Params {
   int P, m_tiles, row_shift, R, in_stages;
+  int n_box, box_rows;
   uint32_t in_stage_bytes;
   const float* bias;
   float neg;
@@ -500,8 +504,10 @@ head3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       tc::mbar_wait(&in_empty[is], iph ^ 1);
       if (tc::elect_one()) {
-        tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * 128u);
-        tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], 0, tile * kC3OutRows - 1 - p.row_shift);
+        tc::mbar_expect_tx(&in_full[is], uint32_t(p.n_box * p.box_rows) * 128u);
+        for (int bx = 0; bx < p.n_box; ++bx)
+          tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes + size_t(bx * p.box_rows) * 128u, &tmA, &in_full[is], 0,
+                          tile * kC3OutRows - 1 - p.row_shift + bx * p.box_rows);
       }
       __syncwarp();
       if (++is == p.in_stages) { is = 0; iph ^= 1; }
@@ -645,15 +651,17 @@ int head3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.m_tiles = int((a->P + kC3OutRows - 1) / kC3OutRows);
   p.row_shift = a->Wp;
   p.R = 128 + 2 * a->Wp;
-  if (p.R > 256) return MV_OK;
-  p.in_stage_bytes = (uint32_t(p.R) * 128u + 1023u) & ~1023u;
+  if (p.R > 512) return MV_OK;
+  p.n_box = p.R > 256 ? 2 : 1;   // windows taller than the 256-row TMA box limit (64-pixel-wide images): two boxes
+  p.box_rows = p.n_box == 1 ? p.R : (((p.R + 1) / 2 + 7) & ~7);
+  p.in_stage_bytes = (uint32_t(p.n_box * p.box_rows) * 128u + 1023u) & ~1023u;
   p.in_stages = kC3MaxStages;
   p.bias = a->bias;
   p.neg = a->act == MV_ACT_LRELU02 ? 0.2f : (a->act == MV_ACT_RELU ? 0.f : 1.f);
   p.out = static_cast<bf16*>(a->out);
   p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.H = a->H; p.n_img = a->n_img; p.n_valid = a->n_valid;
   CUtensorMap tmA, tmW;
-  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), 64, uint64_t(a->a_ld) * 2, uint32_t(p.R), 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
+  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), 64, uint64_t(a->a_ld) * 2, uint32_t(p.box_rows), 64, CU_TENSOR_MAP_SWIZZLE_128B) ||
       !tc::make_tmap_2d_bf16(&tmW, a->Wt, uint64_t(9) * 16, 64, 128, kH3N, 64, CU_TENSOR_MAP_SWIZZLE_128B)) {
     mv::set_error("mv_tapgemm(head3): cuTensorMapEncodeTiled failed");
     return MV_ERR_CUDA;
@@ -704,8 +712,10 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.n_kc = a->Cin / 64;
   p.row_shift = a->Wp;
   p.R = 128 + 2 * a->Wp;
-  if (p.R > 256) return MV_OK;
-  p.in_stage_bytes = (uint32_t(p.R) * 128u + 1023u) & ~1023u;
+  if (p.R > 512) return MV_OK;
+  p.n_box = p.R > 256 ? 2 : 1;   // windows taller than the 256-row TMA box limit (64-pixel-wide images): two boxes
+  p.box_rows = p.n_box == 1 ? p.R : (((p.R + 1) / 2 + 7) & ~7);
+  p.in_stage_bytes = (uint32_t(p.n_box * p.box_rows) * 128u + 1023u) & ~1023u;
   p.w_bytes = uint32_t(p.n_kc) * 3u * kC3WBox;
   const size_t fixed = 1024 + 2 * 4 * 2 * 64 * 4 + 64 * 4 + 2048 + (2 * kC3MaxStages + 5 + 2 * kC3MaxSide) * 8 + 16;
   const bool has_side = a->res || a->dact1;
@@ -731,6 +741,9 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     for (int ssn = has_side ? 3 : 0; ssn >= (has_side ? 2 : 0) && !G; --ssn)
       if (plan(1, n_out, ssn, in_min) <= kC3SmemLimit) { G = 1; p.n_stg = n_out; p.side_stages = ssn; }
   }
+  if (!G && plan(1, n_out, has_side ? 2 : 0, 2) <= kC3SmemLimit) {   // two-box windows (64-pixel-wide images): a double buffer
+    G = 1; p.n_stg = n_out; p.side_stages = has_side ? 2 : 0; in_min = 2;
+  }
   if (!G) return MV_OK;
   p.in_stages = int((kC3SmemLimit - plan(G, p.n_stg, p.side_stages, 0)) / p.in_stage_bytes);
   if (p.in_stages > kC3MaxStages) p.in_stages = kC3MaxStages;
@@ -748,7 +761,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.mask2 = static_cast<uint64_t*>(a->out2_mask);
 
   CUtensorMap tmA, tmW;
-  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.R), 64,
+  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.box_rows), 64,
                              CU_TENSOR_MAP_SWIZZLE_128B) ||
       !tc::make_tmap_2d_bf16(&tmW, a->Wt, uint64_t(9) * 64, uint64_t(a->Cin), uint64_t(a->Cin) * 2, kC3N, 64,
                              CU_TENSOR_MAP_SWIZZLE_128B)) {

@@ -40,6 +40,7 @@ struct TapGemmParams {
   int P, m_tiles, n_tiles, BN, N_total, n_kc, T;
   int tap_off[kMaxTaps];
   int halo_lo, R;
+  int n_box, box_rows;      // the input window is loaded as n_box TMA boxes of box_rows rows (R > 256: two boxes)
   int in_stages, w_stages, w_resident;
   uint32_t in_stage_bytes, w_stage_bytes;
   int acc_stride, tmem_cols;
@@ -311,8 +312,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < p.n_kc; ++kc) {
         tc::mbar_wait(&in_empty[is], iph ^ 1);
         if (tc::elect_one()) {
-          tc::mbar_expect_tx(&in_full[is], uint32_t(p.R) * ROWB);
-          tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes, &tmA, &in_full[is], kc * CK, p0 - p.halo_lo);
+          // windows taller than the 256-row TMA box limit (64-pixel-wide images) arrive as two boxes
+          tc::mbar_expect_tx(&in_full[is], uint32_t(p.n_box * p.box_rows) * ROWB);
+          for (int bx = 0; bx < p.n_box; ++bx)
+            tc::tma_load_2d(in_base + size_t(is) * p.in_stage_bytes + size_t(bx * p.box_rows) * ROWB, &tmA, &in_full[is], kc * CK,
+                            p0 - p.halo_lo + bx * p.box_rows);
         }
         __syncwarp();
         if (++is == p.in_stages) { is = 0; iph ^= 1; }
@@ -605,9 +609,11 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   }
   p.halo_lo = -lo;
   p.R = kBM - lo + hi;
-  MV_CHECK_ARG(p.R <= 256, "mv_tapgemm: tap offsets span %d rows (> 256-row TMA box)", p.R);
+  MV_CHECK_ARG(p.R <= 512, "mv_tapgemm: tap offsets span %d rows (> two 256-row TMA boxes)", p.R);
+  p.n_box = p.R > 256 ? 2 : 1;
+  p.box_rows = p.n_box == 1 ? p.R : (((p.R + 1) / 2 + 7) & ~7);   // whole 8-row swizzle groups per box
   const uint32_t rowb = CK * 2;
-  p.in_stage_bytes = (uint32_t(p.R) * rowb + 1023u) & ~1023u;
+  p.in_stage_bytes = (uint32_t(p.n_box * p.box_rows) * rowb + 1023u) & ~1023u;
   p.w_stage_bytes = uint32_t(a->BN) * rowb;
   const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxInStages + 2 * kMaxWStages + 4 + 2 * kMaxSideStages) * 8 + 16 +
                        size_t(kEpiWarps) * (a->BN < 32 ? 32 : a->BN) * 4 /*bias copies*/;
@@ -673,7 +679,7 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   MV_CHECK_ARG(!a->out2_mask, "mv_tapgemm: out2_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   CUtensorMap tmA, tmW;
   const CUtensorMapSwizzle sw = CK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
-  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.R), CK, sw) ||
+  if (!tc::make_tmap_2d_bf16(&tmA, a->A, uint64_t(a->a_rows), uint64_t(a->Cin), uint64_t(a->a_ld) * 2, uint32_t(p.box_rows), CK, sw) ||
       !tc::make_tmap_2d_bf16(&tmW, a->Wt, uint64_t(a->T) * a->N_total, uint64_t(a->Cin), uint64_t(a->Cin) * 2, uint32_t(a->BN), CK, sw)) {
     mv::set_error("mv_tapgemm: cuTensorMapEncodeTiled failed (A %p rows %lld ld %d, W %p)", a->A, (long long)a->a_rows, a->a_ld, a->Wt);
     return MV_ERR_CUDA;

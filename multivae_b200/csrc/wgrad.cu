@@ -41,6 +41,7 @@ struct WgradParams {
   uint32_t g_lbo;               // byte distance between the 64-column blocks of the N side
   uint32_t g_rows;              // rows of the G box (128, or 136 in pair mode)
   int halo_lo, R;
+  int n_box, box_rows;          // the X window is loaded as n_box TMA boxes of box_rows rows
   uint32_t x_chunk_bytes;       // bytes of one chunk buffer (R rows x 128 B, 1 KB aligned)
   uint32_t g_bytes, g_row_bytes, g_box_cols;
   uint32_t stage_bytes;
@@ -92,8 +93,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       tc::mbar_wait(&empty[s], ph ^ 1);
       if (tc::elect_one()) {
         uint8_t* st = smem + size_t(s) * p.stage_bytes;
-        tc::mbar_expect_tx(&full[s], uint32_t(p.n_chunks) * uint32_t(p.R) * 128u + p.g_bytes);
-        for (int c = 0; c < p.n_chunks; ++c) tc::tma_load_2d(st + size_t(c) * p.x_chunk_bytes, &tmX, &full[s], c * 64, kt * 128 - p.halo_lo);
+        tc::mbar_expect_tx(&full[s], uint32_t(p.n_chunks) * uint32_t(p.n_box * p.box_rows) * 128u + p.g_bytes);
+        for (int c = 0; c < p.n_chunks; ++c)
+          for (int bx = 0; bx < p.n_box; ++bx)   // windows taller than the 256-row TMA box limit arrive as two boxes
+            tc::tma_load_2d(st + size_t(c) * p.x_chunk_bytes + size_t(bx * p.box_rows) * 128u, &tmX, &full[s], c * 64,
+                            kt * 128 - p.halo_lo + bx * p.box_rows);
         const int nbox = p.N / int(p.g_box_cols);
         for (int b = 0; b < nbox; ++b)
           tc::tma_load_2d(st + g_off + size_t(b) * p.g_rows * p.g_row_bytes, &tmG, &full[s], b * int(p.g_box_cols), kt * 128);
@@ -229,7 +233,9 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   }
   p.halo_lo = -lo;
   p.R = 128 - lo + hi;
-  MV_CHECK_ARG(p.R <= 256, "mv_wgrad: tap offsets span %d rows", p.R);
+  MV_CHECK_ARG(p.R <= 512, "mv_wgrad: tap offsets span %d rows", p.R);
+  p.n_box = p.R > 256 ? 2 : 1;
+  p.box_rows = p.n_box == 1 ? p.R : (((p.R + 1) / 2 + 7) & ~7);
   p.n_chunks = Cin / 64;
   p.N = N;
   p.Ncols = N < 32 ? 32 : N;
@@ -242,7 +248,7 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   p.db = db ? db + n_offset : nullptr;
   p.n_ktiles = int((P + 127) / 128);
   // +8 rows of slack: the padding block of an odd tap count may read a few rows past the window
-  p.x_chunk_bytes = (uint32_t(p.R + 8) * 128u + 1023u) & ~1023u;
+  p.x_chunk_bytes = (uint32_t(p.n_box * p.box_rows + 8) * 128u + 1023u) & ~1023u;
   // Pair mode (Cin = 64, N = 64, a 3x3 tap pattern): the plain scheme issues N = 64 MMAs, which are bound by the operand
   // fetch (51 cycles against 32 of math, tests/cuda/mma_rate.cu).  Here the N side is the G tile AND the G tile shifted
   // by one row (N = 128, math-bound), the M side two X shifts per filter row:
@@ -352,7 +358,7 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
   MV_CHECK_ARG(p.stages >= 1, "mv_wgrad: stage does not fit shared memory");
   CUtensorMap tmX, tmG;
-  const bool ok = tc::make_tmap_2d_bf16(&tmX, X, uint64_t(x_rows), uint64_t(Cin), uint64_t(x_ld) * 2, uint32_t(p.R), 64,
+  const bool ok = tc::make_tmap_2d_bf16(&tmX, X, uint64_t(x_rows), uint64_t(Cin), uint64_t(x_ld) * 2, uint32_t(p.box_rows), 64,
                                         CU_TENSOR_MAP_SWIZZLE_128B) &&
                   tc::make_tmap_2d_bf16(&tmG, G, uint64_t(g_rows), uint64_t(N), uint64_t(g_ld) * 2, p.g_rows, p.g_box_cols,
                                         N >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);

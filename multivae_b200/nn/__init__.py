@@ -17,4 +17,5 @@ from .mmnist import (  # noqa: F401
     EncoderResnetMMNIST,
     ResnetBlock,
 )
+from .cub import CUB_Resnet_Decoder, CUB_Resnet_Encoder, CUB_ResnetBlock  # noqa: F401
 from .svhn import Decoder_VAE_SVHN, Encoder_VAE_SVHN  # noqa: F401

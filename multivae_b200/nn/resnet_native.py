@@ -324,19 +324,21 @@ class DecoderStackFn(torch.autograd.Function):
 _PERM_CACHE = {}
 
 
-def _fc_perm(device):
-    """(gather, scatter): `gather` [64*256] maps halo feature (y'*8 + x)*256 + c to fc row c*49 + (y'-1)*7 + x (halo
-    positions -> the extra all-zero row 12544); `scatter` [12544] is its inverse on the real rows."""
-    key = str(device)
+def _fc_perm(device, s0=7, ch=256):
+    """(gather, scatter) for an s0 x s0 x ch feature map: `gather` [(s0+1)^2 * ch] maps halo feature (y'*(s0+1) + x)*ch + c to fc
+    row c*s0^2 + (y'-1)*s0 + x (halo positions -> the extra all-zero row ch*s0^2); `scatter` [ch*s0^2] is its inverse on the
+    real rows."""
+    key = (str(device), s0, ch)
     if key not in _PERM_CACHE:
-        idx = torch.full((8, 8, 256), 256 * 49, dtype=torch.long)
-        c = torch.arange(256)
-        for y in range(1, 8):
-            for x in range(7):
-                idx[y, x] = c * 49 + (y - 1) * 7 + x
+        n_real = ch * s0 * s0
+        idx = torch.full((s0 + 1, s0 + 1, ch), n_real, dtype=torch.long)
+        c = torch.arange(ch)
+        yy = torch.arange(s0).view(s0, 1, 1)
+        xx = torch.arange(s0).view(1, s0, 1)
+        idx[1:, :s0] = c.view(1, 1, ch) * (s0 * s0) + yy * s0 + xx
         idx = idx.reshape(-1)
-        inv = torch.empty(256 * 49, dtype=torch.long)
-        pos = torch.nonzero(idx < 256 * 49).squeeze(1)
+        inv = torch.empty(n_real, dtype=torch.long)
+        pos = torch.nonzero(idx < n_real).squeeze(1)
         inv[idx[pos]] = pos
         _PERM_CACHE[key] = (idx.to(device), inv.to(device))
     return _PERM_CACHE[key]
@@ -349,9 +351,9 @@ class FcHaloFn(torch.autograd.Function):
     rows back (no scatter-add)."""
 
     @staticmethod
-    def forward(ctx, z, weight, bias):
+    def forward(ctx, z, weight, bias, s0=7, ch=256):
         from .linear_native import _to_bf16_padded, gemm
-        gather, scatter = _fc_perm(z.device)
+        gather, scatter = _fc_perm(z.device, s0, ch)
         w_ext = torch.cat([weight.detach(), weight.new_zeros(1, weight.shape[1])], 0).to(torch.bfloat16)
         b_ext = torch.cat([bias.detach().float(), bias.new_zeros(1, dtype=torch.float32)], 0)
         wp = w_ext[gather]                      # [64*256, L] bf16, halo order
@@ -383,8 +385,8 @@ class FcHaloFn(torch.autograd.Function):
         if tgt is not None:   # trainer opt-in: straight into the flat gradient buffer (final when this backward returns)
             tgt[0].add_(gw[ctx.scatter])
             tgt[1].add_(gb[ctx.scatter])
-            return gz, None, None
-        return gz, gw[ctx.scatter], gb[ctx.scatter]
+            return gz, None, None, None, None
+        return gz, gw[ctx.scatter], gb[ctx.scatter], None, None
 
 
 def decoder_params(dec):
@@ -401,7 +403,7 @@ def decoder_params(dec):
 def decoder_forward(dec, z, out_dtype=None):
     zz = z.reshape(-1, z.size(-1))
     n_img = zz.shape[0]
-    h0 = FcHaloFn.apply(zz, dec.fc.weight, dec.fc.bias).view(n_img * 64, 256)  # halo matrix at 7x7
+    h0 = FcHaloFn.apply(zz, dec.fc.weight, dec.fc.bias, 7, 256).view(n_img * 64, 256)  # halo matrix at 7x7
     recon = DecoderStackFn.apply(h0, n_img, *decoder_params(dec))
     recon = recon.view(*z.size()[:-1], *recon.shape[1:])
     return ModelOutput(reconstruction=recon)
@@ -476,18 +478,20 @@ class FcFromHaloFn(torch.autograd.Function):
     gathered into halo order (zeros at halo positions).  Native GEMMs (mv_gemm), fp32 outputs."""
 
     @staticmethod
-    def forward(ctx, h, w_mu, b_mu, w_lv, b_lv):
+    def forward(ctx, h, w_mu, b_mu, w_lv, b_lv, s0=7):
         from .linear_native import gemm
-        gather, scatter = _fc_perm(h.device)
-        n_img = h.shape[0] // 64
+        ch = h.shape[1]
+        S = (s0 + 1) * (s0 + 1)
+        gather, scatter = _fc_perm(h.device, s0, ch)
+        n_img = h.shape[0] // S
         w = torch.cat([w_mu.detach(), w_lv.detach()], 0)
-        wp = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).to(torch.bfloat16)[:, gather].contiguous()   # [2L, 16384]
-        h2 = h.reshape(n_img, 64 * 256)
+        wp = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).to(torch.bfloat16)[:, gather].contiguous()   # [2L, S*ch]
+        h2 = h.reshape(n_img, S * ch)
         N = wp.shape[0]
         out = torch.empty(n_img, N, device=h.device, dtype=torch.float32)
-        gemm(h2, wp, n_img, N, 64 * 256, out, bias=torch.cat([b_mu.detach(), b_lv.detach()]).float().contiguous(), out_kind=1, tag="enc.fc")
+        gemm(h2, wp, n_img, N, S * ch, out, bias=torch.cat([b_mu.detach(), b_lv.detach()]).float().contiguous(), out_kind=1, tag="enc.fc")
         ctx.save_for_backward(h2, wp)
-        ctx.scatter, ctx.split = scatter, w_mu.shape[0]
+        ctx.scatter, ctx.split, ctx.ch = scatter, w_mu.shape[0], ch
         return out[:, : w_mu.shape[0]].contiguous(), out[:, w_mu.shape[0]:].contiguous()
 
     @staticmethod
@@ -505,7 +509,7 @@ class FcFromHaloFn(torch.autograd.Function):
         gemm(g16, wp, n, F_, N, gh, b_mn=True, tag="enc.fc.d")
         gw = gw[:, ctx.scatter]
         k = ctx.split
-        return gh.reshape(-1, 256), gw[:k], gb[:k], gw[k:], gb[k:]
+        return gh.reshape(-1, ctx.ch), gw[:k], gb[:k], gw[k:], gb[k:], None
 
 
 def encoder_params(enc, tag):
@@ -527,6 +531,6 @@ def encoder_forward(enc, x):
             continue
         h = EncoderStackFn.apply(x, *encoder_params(enc, tag))
         mu, lv = FcFromHaloFn.apply(h, getattr(enc, f"fc_mu_{tag}").weight, getattr(enc, f"fc_mu_{tag}").bias,
-                                    getattr(enc, f"fc_lv_{tag}").weight, getattr(enc, f"fc_lv_{tag}").bias)
+                                    getattr(enc, f"fc_lv_{tag}").weight, getattr(enc, f"fc_lv_{tag}").bias, 7)
         out[keys[0]], out[keys[1]] = mu, lv
     return out

@@ -36,7 +36,7 @@ def reference_archs(spec):
         return None, None
     from multivae.models.base.base_config import BaseAEConfig
     from multivae.models.nn import default_architectures as da
-    from multivae.models.nn import mmnist, svhn
+    from multivae.models.nn import cub, mmnist, svhn
     L = spec["cfg"]["latent_dim"]
     Lw = spec["cfg"].get("modalities_specific_dim")
     enc, dec = {}, {}
@@ -129,7 +129,7 @@ def run_nets():
     ref_harness.import_reference()
     from multivae.models.base.base_config import BaseAEConfig
     from multivae.models.nn import default_architectures as da
-    from multivae.models.nn import mmnist, svhn
+    from multivae.models.nn import cub, mmnist, svhn
 
     def cfgd(input_dim, latent_dim, style_dim=None):
         c = BaseAEConfig(input_dim=input_dim, latent_dim=latent_dim)
@@ -147,7 +147,12 @@ def run_nets():
         "enc_mlp": (lambda: da.Encoder_VAE_MLP(cfgd((1, 28, 28), 20)), (2, 1, 28, 28), "x"),
         "enc_mlp_style": (lambda: da.Encoder_VAE_MLP_Style(cfgd((3, 8, 8), 8, 4)), (2, 3, 8, 8), "x"),
         "dec_mlp": (lambda: da.Decoder_AE_MLP(cfgd((1, 28, 28), 20)), (3, 20), "z"),
+        "enc_cub_resnet": (lambda: cub.CUB_Resnet_Encoder(latent_dim=32), (2, 3, 64, 64), "x"),
+        "dec_cub_resnet": (lambda: cub.CUB_Resnet_Decoder(latent_dim=32), (2, 32), "z"),
     }
+    only = [a[5:] for a in sys.argv[1:] if a.startswith("nets:")]
+    if only:
+        nets = {k: v for k, v in nets.items() if k in only}
     for name, (ctor, shp, kind) in nets.items():
         net = ctor()
         shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
@@ -171,7 +176,8 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or list(CASES) + ["nets"]
     for n in which:
-        if n == "nets":
-            run_nets()
+        if n == "nets" or n.startswith("nets:"):
+            if n == "nets" or n == [a for a in which if a.startswith("nets:")][0]:
+                run_nets()
         else:
             run_case(n, CASES[n])

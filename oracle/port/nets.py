@@ -107,6 +107,42 @@ def decoder_resnet_mmnist(p, pre, z):
     return h.view(*z.shape[:-1], *h.shape[1:])
 
 
+# ---- CUB 64 x 64 ResNets                                cub.py:144-293
+def cub_resnet_block(p, pre, x):
+    """Pre-activation block, cub.py:249-293: x_s + 0.1 * conv_1(actvn(conv_0(actvn(x))))."""
+    xs = F.conv2d(x, p[pre + "conv_s.weight"]) if (pre + "conv_s.weight") in p else x
+    dx = F.conv2d(F.leaky_relu(x, 0.2), p[pre + "conv_0.weight"], p[pre + "conv_0.bias"], padding=1)
+    dx = F.conv2d(F.leaky_relu(dx, 0.2), p[pre + "conv_1.weight"], p.get(pre + "conv_1.bias"), padding=1)
+    return xs + 0.1 * dx
+
+
+def _cub_block_ids(p, pre):
+    return sorted({int(k[len(pre + "resnet."):].split(".")[0]) for k in p if k.startswith(pre + "resnet.") and ".conv_0.weight" in k})
+
+
+def cub_resnet_encoder(p, pre, x):
+    """cub.py:185-193: conv_img, ResnetBlock, (AvgPool2d(3, 2, 1), ResnetBlock)*, heads on actvn(flattened features)."""
+    h = F.conv2d(x, p[pre + "conv_img.weight"], p[pre + "conv_img.bias"], padding=1)
+    for j, i in enumerate(_cub_block_ids(p, pre)):
+        if j > 0:
+            h = F.avg_pool2d(h, 3, stride=2, padding=1)
+        h = cub_resnet_block(p, f"{pre}resnet.{i}.", h)
+    h = F.leaky_relu(h.reshape(x.shape[0], -1), 0.2)
+    return _lin(p, pre + "fc_mu", h), _lin(p, pre + "fc_logvar", h)
+
+
+def cub_resnet_decoder(p, pre, z, s0=16):
+    """cub.py:238-246: fc, (ResnetBlock, Upsample(2))*, ResnetBlock, conv_img on actvn(features); no output activation."""
+    ids = _cub_block_ids(p, pre)
+    nf0 = p[f"{pre}resnet.{ids[0]}.conv_0.weight"].shape[1]
+    h = _lin(p, pre + "fc", z).view(z.shape[0], nf0, s0, s0)
+    for j, i in enumerate(ids):
+        h = cub_resnet_block(p, f"{pre}resnet.{i}.", h)
+        if j + 1 < len(ids):
+            h = F.interpolate(h, scale_factor=2)
+    return F.conv2d(F.leaky_relu(h, 0.2), p[pre + "conv_img.weight"], p[pre + "conv_img.bias"], padding=1)
+
+
 # ---- deterministic synthetic weights (shared by the golden generator and the tests) -------------
 def synth_state_dict(shapes, seed=0, dtype=torch.float32):
     """name->shape  ->  name->tensor, PyTorch-default-like fan-in scaling, independent of module

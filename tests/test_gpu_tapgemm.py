@@ -20,7 +20,9 @@ def _close(got, ref, tol=2e-2):
 
 
 @pytest.mark.parametrize("n_img,H,cin,cout", [(37, 28, 64, 64), (300, 28, 64, 64), (23, 14, 128, 64), (41, 7, 256, 128),
-                                              (19, 7, 128, 128), (9, 14, 64, 64)])
+                                              (19, 7, 128, 128), (9, 14, 64, 64),
+                                              # the CUB ResNet stages; 64-pixel rows: the input window spans two TMA boxes
+                                              (5, 64, 64, 64), (3, 32, 128, 64), (3, 32, 64, 128), (3, 16, 256, 128), (2, 16, 128, 256)])
 def test_conv3x3_forward_epilogues(n_img, H, cin, cout):
     from multivae_b200.nn import halo as HL
     x = _rnd(n_img, cin, H, H, seed=1).bfloat16()
@@ -42,7 +44,8 @@ def test_conv3x3_forward_epilogues(n_img, H, cin, cout):
     assert float(out[mask].abs().max()) == 0.0 and float(act[mask].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n_img,H,cin,cout", [(21, 28, 64, 64), (17, 14, 128, 64), (11, 7, 256, 128)])
+@pytest.mark.parametrize("n_img,H,cin,cout", [(21, 28, 64, 64), (17, 14, 128, 64), (11, 7, 256, 128), (4, 64, 64, 64), (3, 32, 128, 64),
+                                              (3, 16, 256, 128)])
 def test_conv3x3_dgrad_with_activation_derivative(n_img, H, cin, cout):
     from multivae_b200.nn import halo as HL
     gy = _rnd(n_img, cout, H, H, seed=5).bfloat16()
@@ -57,7 +60,7 @@ def test_conv3x3_dgrad_with_activation_derivative(n_img, H, cin, cout):
     _close(HL.from_halo(out, g), ref)
 
 
-@pytest.mark.parametrize("n_img,H,cin", [(37, 28, 64), (301, 28, 64), (23, 14, 128), (9, 14, 64), (5, 7, 64)])
+@pytest.mark.parametrize("n_img,H,cin", [(37, 28, 64), (301, 28, 64), (23, 14, 128), (9, 14, 64), (5, 7, 64), (4, 64, 64), (3, 32, 128)])
 @pytest.mark.parametrize("variant", ["bias_lrelu", "dact1", "res", "none"])
 def test_conv3x3_cout64_single_side_variants(n_img, H, cin, variant):
     """The three-taps-per-MMA kernel (csrc/tapconv3.cu) behind mv_tapgemm for 3x3 convolutions with 64 outputs."""
@@ -104,9 +107,9 @@ def test_conv1x1_and_two_outputs():
     _close(HL.from_halo(o2, g), 0.1 * ref * torch.where(d.float() > 0, 1.0, 0.2))
 
 
-def test_image_head_nchw_and_cin16():
+@pytest.mark.parametrize("n_img,H", [(33, 28), (3, 64)])
+def test_image_head_nchw_and_cin16(n_img, H):
     from multivae_b200.nn import halo as HL
-    n_img, H = 33, 28
     x = _rnd(n_img, 64, H, H, seed=12).bfloat16()
     w = _rnd(3, 64, 3, 3, seed=13, scale=0.05).bfloat16()
     b = _rnd(3, seed=14)

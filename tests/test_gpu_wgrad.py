@@ -14,7 +14,10 @@ def _rnd(*shape, seed=0, scale=1.0):
 
 @pytest.mark.parametrize("n_img,H,cin,cout,k", [(37, 28, 64, 64, 3), (300, 28, 64, 64, 3), (23, 14, 128, 64, 3),
                                                 (41, 7, 256, 128, 3), (19, 7, 128, 128, 3), (29, 14, 128, 64, 1),
-                                                (31, 7, 256, 128, 1), (33, 28, 64, 16, 3)])
+                                                (31, 7, 256, 128, 1), (33, 28, 64, 16, 3),
+                                                # CUB ResNet stages (64-pixel rows: two-box windows)
+                                                (4, 64, 64, 64, 3), (3, 64, 64, 16, 3), (3, 32, 128, 64, 3), (3, 32, 64, 128, 3),
+                                                (3, 16, 256, 128, 3), (2, 16, 128, 256, 3), (3, 32, 64, 128, 1), (3, 16, 128, 256, 1)])
 def test_conv_weight_gradient(n_img, H, cin, cout, k):
     from multivae_b200.nn import halo as HL
     x = _rnd(n_img, cin, H, H, seed=1).bfloat16()

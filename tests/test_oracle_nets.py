@@ -20,6 +20,8 @@ FWD = {
     "enc_mlp": lambda p, x: dict(zip(("embedding", "log_covariance"), N.encoder_vae_mlp(p, "", x))),
     "enc_mlp_style": lambda p, x: dict(zip(("embedding", "log_covariance", "style_embedding", "style_log_covariance"), N.encoder_vae_mlp_style(p, "", x))),
     "dec_mlp": lambda p, z: {"reconstruction": N.decoder_ae_mlp(p, "", z, (1, 28, 28))},
+    "enc_cub_resnet": lambda p, x: dict(zip(("embedding", "log_covariance"), N.cub_resnet_encoder(p, "", x))),
+    "dec_cub_resnet": lambda p, z: {"reconstruction": N.cub_resnet_decoder(p, "", z)},
 }
 
 
