@@ -255,6 +255,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t mask_s = tc::smem_u32(s_mask) + uint32_t(grp) * 1024u;
     const bool leader = (ew % GW) == 0 && lane == 0;   // issues the group's TMA stores
     int ss = grp % (p.side_stages > 0 ? p.side_stages : 1), sph = 0, prev_ss = -1, k = 0;
+    unsigned long long dm_next = 0ull;
     for (int it = grp; int(blockIdx.x) + it * int(gridDim.x) < p.m_tiles; it += G, ++k) {
       const int tile = int(blockIdx.x) + it * int(gridDim.x);
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
@@ -264,9 +265,16 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t side_tile = side_s + uint32_t(ss) * 16384u;
       const uint32_t out_tile = (kInPlace && has_side) ? side_tile : stg_s;
       const uint32_t out2_tile = (kInPlace && has_side) ? stg_s : stg_s + 16384u;
-      unsigned long long dm = 0ull;   // this row's 64 sign bits: in flight while the MMAs of the tile still run
-      if (c3_has<F>(p, C3_DMASK1) && inner && row < p.P) dm = p.dmask1[row];
-      if (c3_has<F>(p, C3_RESMASK) && inner && row < p.P) dm = p.rmask[row];   // (never together with C3_DMASK1)
+      // this row's 64 sign bits (C3_DMASK1 / C3_RESMASK, never together): requested ONE TILE AHEAD (first tile: here), so that
+      // the L2 / HBM round trip is over when the tile's accumulator arrives
+      unsigned long long dm = 0ull;
+      if (c3_has<F>(p, C3_DMASK1) || c3_has<F>(p, C3_RESMASK)) {
+        const uint64_t* mp = c3_has<F>(p, C3_DMASK1) ? p.dmask1 : p.rmask;
+        if (k == 0 && inner && row >= 0 && row < p.P) dm_next = mp[row];
+        dm = dm_next;
+        const int row_n = row + d_row;
+        if (tile + G * int(gridDim.x) < p.m_tiles && inner && row_n < p.P) dm_next = mp[row_n];
+      }
       tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
 #pragma unroll
@@ -354,17 +362,21 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             y[4 * g + 0] = al * (y[4 * g + 0] + b.x); y[4 * g + 1] = al * (y[4 * g + 1] + b.y);
             y[4 * g + 2] = al * (y[4 * g + 2] + b.z); y[4 * g + 3] = al * (y[4 * g + 3] + b.w);
           }
-        } else {
+        } else if (!c3_has<F>(p, C3_DMASK1)) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) y[e] *= al;
         }
         uint32_t o[8], o2[8];
+        if (p.neg != 1.f) {   // relu / leaky-relu as one max: slope 0 / 0.2 (1 = no activation: skipped, warp-uniform)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);   // none / relu / leaky-relu as one max: slope 1 / 0 / 0.2
+          for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);
+        }
         if (c3_has<F>(p, C3_DMASK1)) {
+          // alpha (not applied above when there is no bias) and lrelu'(bit) as ONE multiply per element
           const uint32_t m16 = uint32_t(dm >> c0) & 0xffffu;
+          const float f1 = c3_has<F>(p, C3_BIAS) ? 1.f : al, f0 = f1 * p.slope1;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] *= ((m16 >> e) & 1u) ? 1.f : p.slope1;
+          for (int e = 0; e < 16; ++e) y[e] *= ((m16 >> e) & 1u) ? f1 : f0;
         }
         if (c3_has<F>(p, C3_DACT1)) {
 #pragma unroll

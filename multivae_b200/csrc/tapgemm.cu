@@ -153,9 +153,11 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
         yv[0] += b0.x; yv[1] += b0.y; yv[2] += b0.z; yv[3] += b0.w;
         yv[4] += b1.x; yv[5] += b1.y; yv[6] += b1.z; yv[7] += b1.w;
       }
-      // none / relu / leaky-relu as one max: slope `neg` is 1 / 0 / 0.2
+      // relu / leaky-relu as one max: slope `neg` is 0 / 0.2 (1 = no activation: skipped, warp-uniform)
+      if (neg != 1.f) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv[e] = fmaxf(yv[e], neg * yv[e]);
+        for (int e = 0; e < 8; ++e) yv[e] = fmaxf(yv[e], neg * yv[e]);
+      }
       if (has<F>(p, EF_SIGMOID)) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[e] = 1.f / (1.f + __expf(-yv[e]));
@@ -166,7 +168,13 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[e] *= d[e] > 0.f ? 1.f : p.slope1;
       }
-      if (has<F>(p, EF_DMASK1)) {
+      if (F == EF_DMASK1) {
+        // the only epilogue work of this variant (data gradient of the image head): alpha * y * lrelu'(bit) as ONE multiply
+        const uint32_t m8 = (mask_word >> (g * 8)) & 0xffu;
+        const float f1 = p.alpha, f0 = p.alpha * p.slope1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = yv[e] * (((m8 >> e) & 1u) ? f1 : f0);
+      } else if (has<F>(p, EF_DMASK1)) {
         const uint32_t m8 = (mask_word >> (g * 8)) & 0xffu;
 #pragma unroll
         for (int e = 0; e < 8; ++e) yv[e] *= ((m8 >> e) & 1u) ? 1.f : p.slope1;
@@ -180,6 +188,8 @@ __device__ __forceinline__ void epi_apply(const TapGemmParams& p, const uint32_t
         unpack8(side_vec(p, side_tile, 0, cb + g * 8, n + g * 8, r), rr);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(p.alpha, yv[e], rr[e]);
+      } else if (F == EF_DMASK1) {
+        // (done above)
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = p.alpha * yv[e];
@@ -308,7 +318,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-      const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+      const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles;   // (no integer division in the common single-column-tile case)
+      const int p0 = mt * kBM, n0 = (tile - mt * p.n_tiles) * BN;
       for (int kc = 0; kc < p.n_kc; ++kc) {
         tc::mbar_wait(&in_empty[is], iph ^ 1);
         if (tc::elect_one()) {
@@ -338,7 +349,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.side_stages > 0) {
       int ss = 0, sph = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+        const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles;   // (no integer division in the common single-column-tile case)
+      const int p0 = mt * kBM, n0 = (tile - mt * p.n_tiles) * BN;
         const int nsub = (BN == 128 && p.seq_boxes) ? 2 : 1, nbox = int(p.stage_out_bytes >> 14);
         for (int sub = 0; sub < nsub; ++sub) {
           tc::mbar_wait(&side_empty[ss], sph ^ 1);
@@ -458,8 +470,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nsub = seq ? 2 : 1;
     int it = 0, ss = 0, sph = 0;
     bool stored = false;
+    unsigned long long mask_next = 0ull;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
-      const int p0 = (tile / p.n_tiles) * kBM, n0 = (tile % p.n_tiles) * BN;
+      const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles;   // (no integer division in the common single-column-tile case)
+      const int p0 = mt * kBM, n0 = (tile - mt * p.n_tiles) * BN;
       const int acc = it & 1, acc_ph = (it >> 1) & 1;
       RowCtx r;
       r.rloc = q * 32 + lane;
@@ -479,9 +493,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
       }
       const uint32_t taddr = tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16);
-      // sign-mask word of this row: requested before the wait so that the L2 round trip hides behind the tile's MMAs
+      // sign-mask word of this row: requested ONE TILE AHEAD (first tile: here), so that the L2 / HBM round trip is over when the
+      // tile's accumulator arrives (ncu: the epilogue used to wait ~15 % of its time on this load)
       unsigned long long mask_row = 0ull;
-      if ((p.epi_flags & (EF_DMASK2 | EF_DMASK1)) && r.valid) mask_row = p.dmask2[r.row];
+      if (p.epi_flags & (EF_DMASK2 | EF_DMASK1)) {
+        if (it == 0 && r.row < p.P) mask_next = p.dmask2[r.row];
+        mask_row = r.valid ? mask_next : 0ull;
+        const int tn = tile + int(gridDim.x);
+        if (tn < n_tiles_total) {
+          const int mtn = p.n_tiles == 1 ? tn : tn / p.n_tiles;
+          const int rown = mtn * kBM + r.rloc;
+          if (rown < p.P) mask_next = p.dmask2[rown];
+        }
+      }
       tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
       tc::fence_after_sync();
       for (int sub = 0; sub < nsub; ++sub) {
