@@ -53,6 +53,7 @@ def backend_summary():
     from . import resnet_native as RN
     return {"elbo": "native sm_100a kernels (C-ABI)", "resnet_decoder": RN.status("decoder"),
             "resnet_encoder": RN.status("encoder"),
+            "cub_resnets": "native sm_100a: the same tap-GEMM / wgrad / halo kernels (two-box TMA windows at 64 pixels) + mv_lrelu_fwd",
             "mlp": "native sm_100a: tcgen05 GEMM fwd / dgrad / wgrad with fused bias + ReLU / Sigmoid (mv_gemm)",
             "strided_and_transposed_conv": "native sm_100a: im2col / col2im gathers around the tcgen05 GEMM (mv_im2col, mv_col2im, mv_gemm)",
             "fp32_path": "library layers (cuDNN / cuBLAS), used only by the fp32 parity checks"}
