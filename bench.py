@@ -438,6 +438,9 @@ def roofline_from(summary, prof_ms, B, nprof, graph_ms_per_step, config="ns"):
     dims = dict(B=B, M=M, K=K, D=D, L=L, LW=LW)
     desc = {k: R.describe(k, **dims) if (config == "ns" or "|" in k) else {"bound": "hbm", "work": 0} for k in summary}
     known = [kv for kv in summary.items() if desc[kv[0]]["work"] > 0] or list(summary.items())
+    # dominant kernel = largest total time among entry points averaging >= 30 us per launch: in this host-launched pass an event pair
+    # around a shorter launch times the host's launch gap (ctypes call + tensor-map encodes), not the kernel
+    known = [kv for kv in known if kv[1][1] / kv[1][0] * 1e3 >= 30.0] or known
     name, (calls, total_ms) = max(known, key=lambda kv: kv[1][1])
     info = desc[name]
     per_launch_s = total_ms / calls / 1e3
@@ -481,7 +484,8 @@ def roofline_from(summary, prof_ms, B, nprof, graph_ms_per_step, config="ns"):
     return {"kernel": pretty(name), "bound": info["bound"], "achieved": achieved, "peak": peak, "unit": unit,
             "frac": achieved / peak, "peak_source": peaks["source"], "traffic": measured_traffic(pretty(name)),
             "algorithmic_work_per_launch": info["work"], "avg_launch_us": per_launch_s * 1e6, "launches": calls,
-            "share_of_step": total_ms / nprof / graph_ms_per_step, "shares": shares, "elbo_kernels": elbo, "tensor_kernels_total": tensor_all,
+            "share_of_step": total_ms / nprof / graph_ms_per_step, "shares": shares,
+            "selection": "largest total kernel time among entry points averaging >= 30 us per launch (shorter launches are timed by the host launch gap in this eager pass)", "elbo_kernels": elbo, "tensor_kernels_total": tensor_all,
             "native_kernel_ms_per_step": native_ms}
 
 

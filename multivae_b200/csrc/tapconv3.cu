@@ -59,6 +59,20 @@ struct Conv3Params {
   uint32_t flags;
 };
 
+// How the rows at the lane-quarter boundaries enter the +-1-row shift-add (see the epilogue): through rotating shuffles, or by a
+// correction after plain up / down shuffles.  Chosen per variant from tools/conv3_bench.py on a B200 (12800 images at 28x28).
+#ifndef MV_C3_ROTATE_MASK
+#define MV_C3_ROTATE_MASK 0xffffffffu
+#endif
+__host__ __device__ constexpr bool c3_rotate(uint32_t F) {
+  if (!(MV_C3_ROTATE_MASK & 1u)) return false;
+  // measured (us, correction -> rotation): bias|res|mask2 1152 -> 1099, dmask1 838 -> 758, res|resmask 1119 -> 1030, res 927 -> 851,
+  // generic 1319 -> 1179;  bias|mask2 838 -> 985, bias 928 -> 1002, bias|res|out2 1347 -> 1369, dact1 963 -> 1073
+  // (bias|res|out2 follows bias|res|mask2: the two produce bit-identical first outputs, which the tests rely on)
+  return F == (C3_BIAS | C3_RES | C3_MASK2) || F == (C3_BIAS | C3_RES | C3_OUT2) || F == C3_DMASK1 || F == (C3_RES | C3_RESMASK) ||
+         F == C3_RES || (F & C3_GENERIC) != 0;
+}
+
 template <uint32_t F>
 __device__ __forceinline__ bool c3_has(const Conv3Params& p, uint32_t bit) {
   return (F & C3_GENERIC) ? (p.flags & bit) != 0 : (F & bit) != 0;
@@ -315,24 +329,53 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (G == 1) asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
         else asm volatile("bar.sync %0, %1;" ::"r"(bar_a), "n"(32 * GW) : "memory");
         float y[16];
+        if constexpr (c3_rotate(F)) {
+          // Boundary rows ride on the shuffles themselves.  Lane 31's own E0 row is needed by nobody in this warp (it went to the
+          // quarter below through the exchange buffer): the lane replaces it by the E0 row of lane 31 of the quarter ABOVE, which a
+          // ROTATING shuffle then delivers to lane 0.  Likewise lane 0 replaces its E2 row by the E2 row of lane 0 of the quarter
+          // below, delivered to lane 31.  (Quarter 0 / lane 0 and quarter 3 / lane 31 are rows 0 and 127 of the MMA tile: not owned.)
+          // 32 fewer FADD issue slots per chunk than correcting after the shuffle, at the price of the shared-memory load latency in
+          // front of the shuffles: a win for the issue-bound variants (side input, masks), a loss for the leanest one (see c3_rotate).
+          if (lane == 31 && q > 0) {
+            const uint32_t src = xw + uint32_t(((q - 1) * 2 + 0) * 64 + c0) * 4u;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[e]), 1);
-          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[e]), 1);
-          y[e] = (up + __uint_as_float(e1[e])) + dn;
-        }
-        if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
-          // boundary lanes: the shuffled-in term came from the lane itself; replace it by the neighbouring quarter's row
-          const uint32_t src = lane == 0 ? xw + uint32_t(((q - 1) * 2 + 0) * 64 + c0) * 4u : xw + uint32_t(((q + 1) * 2 + 1) * 64 + c0) * 4u;
-          const uint32_t* own = lane == 0 ? e0 : e2;
+            for (int g = 0; g < 4; ++g)
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(e0[4 * g]), "=r"(e0[4 * g + 1]), "=r"(e0[4 * g + 2]), "=r"(e0[4 * g + 3]) : "r"(src + 16u * g) : "memory");
+          }
+          if (lane == 0 && q < 3) {
+            const uint32_t src = xw + uint32_t(((q + 1) * 2 + 1) * 64 + c0) * 4u;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t a, b, c, d;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src + 16u * g) : "memory");
-            y[4 * g + 0] += __uint_as_float(a) - __uint_as_float(own[4 * g + 0]);
-            y[4 * g + 1] += __uint_as_float(b) - __uint_as_float(own[4 * g + 1]);
-            y[4 * g + 2] += __uint_as_float(c) - __uint_as_float(own[4 * g + 2]);
-            y[4 * g + 3] += __uint_as_float(d) - __uint_as_float(own[4 * g + 3]);
+            for (int g = 0; g < 4; ++g)
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(e2[4 * g]), "=r"(e2[4 * g + 1]), "=r"(e2[4 * g + 2]), "=r"(e2[4 * g + 3]) : "r"(src + 16u * g) : "memory");
+          }
+          __syncwarp();
+          const int l_up = (lane + 31) & 31, l_dn = (lane + 1) & 31;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float up = __shfl_sync(0xffffffffu, __uint_as_float(e0[e]), l_up);
+            const float dn = __shfl_sync(0xffffffffu, __uint_as_float(e2[e]), l_dn);
+            y[e] = (up + __uint_as_float(e1[e])) + dn;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(e0[e]), 1);
+            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[e]), 1);
+            y[e] = (up + __uint_as_float(e1[e])) + dn;
+          }
+          if ((lane == 0 && q > 0) || (lane == 31 && q < 3)) {
+            // boundary lanes: the shuffled-in term came from the lane itself; replace it by the neighbouring quarter's row
+            const uint32_t src = lane == 0 ? xw + uint32_t(((q - 1) * 2 + 0) * 64 + c0) * 4u : xw + uint32_t(((q + 1) * 2 + 1) * 64 + c0) * 4u;
+            const uint32_t* own = lane == 0 ? e0 : e2;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t a, b, c, d;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src + 16u * g) : "memory");
+              y[4 * g + 0] += __uint_as_float(a) - __uint_as_float(own[4 * g + 0]);
+              y[4 * g + 1] += __uint_as_float(b) - __uint_as_float(own[4 * g + 1]);
+              y[4 * g + 2] += __uint_as_float(c) - __uint_as_float(own[4 * g + 2]);
+              y[4 * g + 3] += __uint_as_float(d) - __uint_as_float(own[4 * g + 3]);
+            }
           }
         }
         const uint32_t off0 = row_off + (uint32_t(((c0 >> 3) + 0) ^ (srow & 7)) << 4);
@@ -401,9 +444,10 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (c3_has<F>(p, C3_RES) && c3_has<F>(p, C3_RESMASK)) {
           const uint32_t m16 = uint32_t(dm >> c0) & 0xffffu;
+          const float rsp = vz * p.rs_pos, rsn = vz * p.rs_neg;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float s0 = vz * (((m16 >> (2 * i)) & 1u) ? p.rs_pos : p.rs_neg), s1 = vz * (((m16 >> (2 * i + 1)) & 1u) ? p.rs_pos : p.rs_neg);
+            const float s0 = ((m16 >> (2 * i)) & 1u) ? rsp : rsn, s1 = ((m16 >> (2 * i + 1)) & 1u) ? rsp : rsn;
             o[i] = pack_bf16(fmaf(s0, bf16lo(sv[i]), y[2 * i]), fmaf(s1, bf16hi(sv[i]), y[2 * i + 1]));
           }
         } else if (c3_has<F>(p, C3_RES)) {
