@@ -394,25 +394,43 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int e = 0; e < 8; ++e) sv[e] = 0u;
         }
-        // alpha and the bias are folded into one FMA per element: alpha * act(acc + b) = act(alpha * acc + alpha * b), alpha > 0
-        if (G == 1 && c3_has<F>(p, C3_BIAS)) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] = al * (y[e] + ab[e]);   // same expression as the shared-memory path: bit-identical results
-        } else if (c3_has<F>(p, C3_BIAS)) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
-            y[4 * g + 0] = al * (y[4 * g + 0] + b.x); y[4 * g + 1] = al * (y[4 * g + 1] + b.y);
-            y[4 * g + 2] = al * (y[4 * g + 2] + b.z); y[4 * g + 3] = al * (y[4 * g + 3] + b.w);
-          }
-        } else if (!c3_has<F>(p, C3_DMASK1)) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] *= al;
-        }
         uint32_t o[8], o2[8];
-        if (p.neg != 1.f) {   // relu / leaky-relu as one max: slope 0 / 0.2 (1 = no activation: skipped, warp-uniform)
+        if (c3_has<F>(p, C3_BIAS) && p.neg != 1.f) {
+          // bias + activation + alpha in three instructions per element: with t = acc + b,
+          //   alpha * lrelu_neg(t) = ca * t + cb * |t|,  ca = alpha (1 + neg) / 2,  cb = alpha (1 - neg) / 2   (relu: neg = 0)
+          const float ca = al * (0.5f + 0.5f * p.neg), cb = al * (0.5f - 0.5f * p.neg);
+          if (G == 1) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);
+            for (int e = 0; e < 16; ++e) { const float t = y[e] + ab[e]; y[e] = fmaf(fabsf(t), cb, t * ca); }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+              const float t0 = y[4 * g + 0] + b.x, t1 = y[4 * g + 1] + b.y, t2 = y[4 * g + 2] + b.z, t3 = y[4 * g + 3] + b.w;
+              y[4 * g + 0] = fmaf(fabsf(t0), cb, t0 * ca); y[4 * g + 1] = fmaf(fabsf(t1), cb, t1 * ca);   // (same expressions as G = 1:
+              y[4 * g + 2] = fmaf(fabsf(t2), cb, t2 * ca); y[4 * g + 3] = fmaf(fabsf(t3), cb, t3 * ca);   //  bit-identical results)
+            }
+          }
+        } else {
+          // alpha is folded through the (positively homogeneous) activation: alpha * act(acc + b) = act(alpha * (acc + b)), alpha > 0
+          if (G == 1 && c3_has<F>(p, C3_BIAS)) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) y[e] = al * (y[e] + ab[e]);   // same expression as the shared-memory path: bit-identical results
+          } else if (c3_has<F>(p, C3_BIAS)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+              y[4 * g + 0] = al * (y[4 * g + 0] + b.x); y[4 * g + 1] = al * (y[4 * g + 1] + b.y);
+              y[4 * g + 2] = al * (y[4 * g + 2] + b.z); y[4 * g + 3] = al * (y[4 * g + 3] + b.w);
+            }
+          } else if (!c3_has<F>(p, C3_DMASK1)) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) y[e] *= al;
+          }
+          if (p.neg != 1.f) {   // relu / leaky-relu as one max: slope 0 / 0.2 (1 = no activation: skipped, warp-uniform)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);
+          }
         }
         if (c3_has<F>(p, C3_DMASK1)) {
           // alpha (not applied above when there is no bias) and lrelu'(bit) as ONE multiply per element
