@@ -108,6 +108,14 @@ class BaseMultiVAE(nn.Module):
                 raise AttributeError(f"For modality {m}, decoder must inherit from BaseDecoder class. Refer to documentation.")
             self.decoders[m] = dec
 
+    def __getstate__(self):
+        """copy.deepcopy / pickling (the reference's trainer deep-copies the best model, base_trainer.py): the per-device caches —
+        side streams of the parallel encoders / decoders, device-resident constants — are rebuilt on demand, never copied."""
+        state = self.__dict__.copy()
+        for k in ("_enc_streams", "_dec_streams", "_const_cache"):
+            state.pop(k, None)
+        return state
+
     def _nn_ctx(self):
         """Context in which the encoders / decoders run (library layers: bf16 autocast when
         compute_dtype is bf16; the native tcgen05 layers read `compute_dtype` themselves)."""

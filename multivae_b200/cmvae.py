@@ -64,11 +64,13 @@ class CMVAE(MoEPlusBase):
         std = torch.cat([self.w_logvar_prior.new_ones(1, L), self._log_var_to_std(self.w_logvar_prior)], dim=-1)
         return mean, std
 
-    def _log_p_u_given_c(self, u):
-        """[n_clusters, *u.shape[:-1]]: log p(u | c) summed over the latent dimensions (cmvae_model.py:309-316)."""
+    def _log_p_u_given_c(self, u, n=None):
+        """[n, *u.shape[:-1]]: log p(u | c) summed over the latent dimensions for the first n clusters (training: n_clusters,
+        cmvae_model.py:299-304; cluster prediction: every cluster ever created, :572-581 — pruned ones carry zero weight)."""
         kind = self.model_config.prior_and_posterior_dist
-        mu = torch.stack([m for m in self.mean_clusters]).reshape(self.n_clusters, *([1] * (u.dim() - 1)), -1)
-        sg = torch.stack([self._log_var_to_std(lv) for lv in self.logvar_clusters]).reshape(self.n_clusters, *([1] * (u.dim() - 1)), -1)
+        n = self.n_clusters if n is None else n
+        mu = torch.stack([m for m in self.mean_clusters][:n]).reshape(n, *([1] * (u.dim() - 1)), -1)
+        sg = torch.stack([self._log_var_to_std(lv) for lv in self.logvar_clusters][:n]).reshape(n, *([1] * (u.dim() - 1)), -1)
         if kind == "laplace_with_softmax":
             return (-torch.log(2 * sg) - (u.unsqueeze(0) - mu).abs() / sg).sum(-1)
         return (-((u.unsqueeze(0) - mu) ** 2) / (2 * sg ** 2) - torch.log(sg) - 0.5 * np.log(2 * np.pi)).sum(-1)
@@ -131,15 +133,81 @@ class CMVAE(MoEPlusBase):
         return ModelOutput(z=z.detach(), one_latent_space=False, modalities_z={k: v.detach() for k, v in style_z.items()})
 
     def predict_clusters(self, inputs, **kwargs):
-        """Cluster of every sample: argmax of the product over modalities of q(c | mean of q(u | x_m)) (cmvae_model.py:547-600)."""
+        """Cluster of every sample (cmvae_model.py:546-619): per modality, one SAMPLE u ~ q(u | x_m), p(c | u) ∝ p(u | c) p(c), the
+        modality's vote = argmax_c; the result is the majority vote over the modalities (`torch.mode`).  `compute_lliks=True` also
+        returns the mean over modalities of sum_c p(c|u) (log p(u|c) + log p(c) - log p(c|u)) / latent_dim (used by the pruning)."""
         with torch.no_grad():
-            lpc = torch.log(self.pc_params).reshape(self.n_clusters, 1)
-            pc_zs, acc = {}, []
+            compute_norm_lliks = kwargs.pop("compute_lliks", False)
+            votes, pc_zs, norm_lliks = [], {}, []
+            lpc = torch.log(self.pc_params + 1e-20).view(-1, 1)
             for m in inputs.data:
                 with self._nn_ctx():
-                    mu = self.encoders[m](inputs.data[m]).embedding.float()
-                pc = torch.softmax(lpc + self._log_p_u_given_c(mu), dim=0)
-                pc_zs[m] = pc
-                acc.append(pc)
-            clusters = torch.stack(acc, dim=0).prod(0).argmax(0)
-        return ModelOutput(clusters=clusters, pc_zs=pc_zs)
+                    o = self.encoders[m](inputs.data[m])
+                mu, sigma = o.embedding.float(), self._log_var_to_std(o.log_covariance.float())
+                z = mu + sigma * self._noise(tuple(mu.shape), mu.device)
+                lpz_c = self._log_p_u_given_c(z, len(self.mean_clusters))   # (all clusters, batch)
+                pc_z = torch.softmax(lpc + lpz_c, dim=0)
+                votes.append(torch.argmax(pc_z, dim=0))
+                pc_zs[m] = pc_z
+                if compute_norm_lliks:
+                    norm_lliks.append(((lpz_c + lpc - pc_z.log()) * pc_z).sum(0).squeeze(-1) / self.latent_dim)
+            clusters = torch.mode(torch.stack(votes, dim=-1), dim=-1)[0]
+            if compute_norm_lliks:
+                return ModelOutput(clusters=clusters, pc_zs=pc_zs, norm_lliks=torch.stack(norm_lliks, dim=0).mean(0))
+            return ModelOutput(clusters=clusters, pc_zs=pc_zs)
+
+    def prune_clusters(self, train_data, batch_size=128):
+        """The paper's post-hoc selection of the number of clusters (cmvae_model.py:621-711): repeatedly measure the penalised
+        normalised entropy beta * H(p(c | u_m)) - normalised likelihood on `train_data`, remove the cluster with the least mass
+        (its logit becomes -inf), and finally keep the cluster set with the lowest value.  Returns the list of entropy values
+        indexed by the number of clusters."""
+        from scipy.stats import entropy
+        from torch.utils.data import DataLoader
+
+        from .containers import MultimodalBaseDataset
+        with torch.no_grad():
+            dev = self._pc_params.device
+            n = len(next(iter(train_data.data.values())))
+            n_cluster_params = [None] * (self.n_clusters + 1)
+            h_values = [torch.inf] * (self.n_clusters + 1)
+            while self.n_clusters >= 2:
+                mass = torch.zeros_like(self._pc_params)
+                h_data = []
+                for idx in DataLoader(range(n), batch_size=batch_size):
+                    batch = MultimodalBaseDataset(data={k: v[idx].to(dev) for k, v in train_data.data.items()})
+                    cp = self.predict_clusters(batch, compute_lliks=True)
+                    for i in range(len(mass)):
+                        mass[i] += (cp.clusters == i).int().sum()
+                    h_pzc = []
+                    for pc_z in cp.pc_zs.values():
+                        p = pc_z.squeeze(1).cpu().numpy() if pc_z.dim() > 2 else pc_z.cpu().numpy()
+                        h_pzc.append(torch.Tensor(entropy(p, axis=0) / np.log(np.count_nonzero(p, axis=0))).to(dev))
+                    h_data.append(self.model_config.beta * torch.stack(h_pzc, dim=0).mean(0) - cp.norm_lliks)
+                h = torch.cat(h_data, dim=-1).mean(-1)
+                h_values[self.n_clusters] = h
+                n_cluster_params[self.n_clusters] = self._pc_params.clone()
+                assert torch.all(mass[torch.argwhere(self._pc_params == -torch.inf)] == 0)
+                self.n_clusters = self.n_clusters - 1
+                mass[self._pc_params.isinf()] = torch.inf
+                self._pc_params[torch.argmin(mass)] = -torch.inf
+                assert torch.sum(~self._pc_params.isinf()) == self.n_clusters
+            self.n_clusters = int(torch.argmin(torch.Tensor(h_values)))
+            self._pc_params = torch.nn.Parameter(n_cluster_params[self.n_clusters])
+            return h_values
+
+    def compute_joint_nll(self, inputs, K=1000, batch_size_K=100, **kwargs):
+        """-sum_i ln p(x_i) from K // n_modalities importance samples per conditioning modality: the log-mean-exp of the training
+        log-weights (cluster-mixture prior included) with rescale = beta = 1 (cmvae_model.py:733-791), batched over the datapoints
+        and chunked over the samples instead of the reference's per-datapoint loop."""
+        from .elbo import logmeanexp
+        self.eval()
+        if hasattr(inputs, "masks"):
+            raise AttributeError("The compute_joint_nll method is not yet implemented for incomplete datasets.")
+        k_iwae = K // self.n_modalities
+        with torch.no_grad():
+            lws = []
+            for k0 in range(0, k_iwae, batch_size_K):
+                _, meta = self._elbo(inputs, min(batch_size_K, k_iwae - k0), "iwae_looser", rescale=1.0, beta=1.0)
+                lws.append(meta["lw"])                                   # (C, n, B)
+            lw = torch.cat(lws, dim=1)
+        return -logmeanexp(lw.reshape(-1, lw.shape[-1])).sum()

@@ -17,7 +17,8 @@ from oracle.cases import CASES, make_data  # noqa: E402
 from oracle.port.nets import synth_state_dict  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
-INFER_CASES = ["mvtcae", "mvae", "mopoe", "mopoe_private", "mmvae_dreg", "mmvae_iwae", "mmvaeplus_dreg", "mmvaeplus_normal"]
+INFER_CASES = ["mvtcae", "mvae", "mopoe", "mopoe_private", "mmvae_dreg", "mmvae_iwae", "mmvaeplus_dreg", "mmvaeplus_normal",
+               "cmvae_dreg", "crmvae"]
 NLL_K, NLL_BK, COND_K = 100, 20, 6
 
 
@@ -32,11 +33,12 @@ def _cpu(o):
 def run_case(name):
     ref_harness.import_reference()
     from multivae.data.datasets.base import MultimodalBaseDataset
-    from multivae.models import (MMVAE, MVAE, MVTCAE, MMVAEConfig, MMVAEPlus, MMVAEPlusConfig, MoPoE, MoPoEConfig, MVAEConfig,
-                                 MVTCAEConfig)
+    from multivae.models import (CMVAE, CRMVAE, MMVAE, MVAE, MVTCAE, CMVAEConfig, CRMVAEConfig, MMVAEConfig, MMVAEPlus, MMVAEPlusConfig,
+                                 MoPoE, MoPoEConfig, MVAEConfig, MVTCAEConfig)
     spec = CASES[name]
     cls = {"mmvaeplus": (MMVAEPlus, MMVAEPlusConfig), "mmvae": (MMVAE, MMVAEConfig), "mvtcae": (MVTCAE, MVTCAEConfig),
-           "mvae": (MVAE, MVAEConfig), "mopoe": (MoPoE, MoPoEConfig)}[spec["model"]]
+           "mvae": (MVAE, MVAEConfig), "mopoe": (MoPoE, MoPoEConfig), "cmvae": (CMVAE, CMVAEConfig),
+           "crmvae": (CRMVAE, CRMVAEConfig)}[spec["model"]]
     cfg = cls[1](n_modalities=len(spec["dims"]), input_dims=dict(spec["dims"]), **copy.deepcopy(spec["cfg"]))
     model = cls[0](cfg)
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
@@ -63,8 +65,17 @@ def run_case(name):
     record("joint_nll", lambda: model.compute_joint_nll(fresh(), K=NLL_K, batch_size_K=NLL_BK))
     if hasattr(model, "compute_joint_nll_paper"):
         record("joint_nll_paper", lambda: model.compute_joint_nll_paper(fresh(), K=30, batch_size_K=10))
+    if spec["model"] == "cmvae":
+        record("predict_clusters", lambda: model.predict_clusters(fresh()))
+        record("predict_clusters_lliks", lambda: model.predict_clusters(fresh(), compute_lliks=True))
     if spec["model"] == "mopoe":
         record("joint_nll_subset", lambda: model._compute_joint_nll_from_subset_encoding([mods[0], mods[2]], fresh(), K=40, batch_size_K=20))
+    if spec["model"] == "cmvae":
+        def prune():
+            m2 = copy.deepcopy(model)
+            hv = m2.prune_clusters(fresh(), batch_size=4)
+            return dict(h_values=torch.tensor([float(h) for h in hv]), n_clusters=torch.tensor(int(m2.n_clusters)), pc_params=m2._pc_params.detach().clone())
+        record("prune_clusters", prune)
     record("cond_nll", lambda: model.compute_cond_nll(fresh(), [mods[0]], [mods[1], mods[2]] if len(mods) > 2 else [mods[1]], k_iwae=COND_K))
     torch.save(rec, os.path.join(OUT, f"infer_{name}.pt"))
 

@@ -62,6 +62,11 @@ def _close(got, ref, rtol, what):
     if torch.is_tensor(ref):
         g = got.detach().float().cpu()
         assert g.shape == ref.shape, (what, g.shape, ref.shape)
+        ref = ref.detach().float()
+        fin = torch.isfinite(ref)
+        if not bool(fin.all()):      # infinities (pruned cluster logits, unvisited cluster counts) must sit at the same places
+            assert torch.equal(g[~fin], ref[~fin]), (what, "non-finite entries differ")
+            g, ref = g[fin], ref[fin]
         err = float((g - ref).abs().max()) / max(float(ref.abs().max()), 1e-6)
         assert err <= rtol, (what, err)
     elif isinstance(ref, (bool, type(None))):
@@ -81,7 +86,7 @@ def check_infer_case(name, device="cuda", rtol=2e-4):
     B = spec["B"]
     fresh = lambda: mb.MultimodalBaseDataset(data={k: v.to(device) for k, v in data.items()})  # noqa: E731
     fam = spec["model"]
-    private = fam == "mmvaeplus" or spec["cfg"].get("modalities_specific_dim") is not None
+    private = fam in ("mmvaeplus", "cmvae") or spec["cfg"].get("modalities_specific_dim") is not None
     done = []
 
     def run(key, fn, draws=None):
@@ -100,12 +105,24 @@ def check_infer_case(name, device="cuda", rtol=2e-4):
     run("predict", lambda: model.predict(fresh(), cond_mod=[mods[0]], gen_mod="all", N=2, flatten=False))
     run("predict_all_to_one", lambda: model.predict(fresh(), cond_mod="all", gen_mod=mods[1]))
     c = rec["calls"]["joint_nll"]
-    if fam == "mmvaeplus":
-        n_present = len(mods) - 1                      # the reference's popitem() quirk (mmvaePlus_model.py:497)
+    if fam in ("mmvaeplus", "cmvae"):
+        # MMVAE+: the reference's popitem() quirk drops the last modality (mmvaePlus_model.py:497); CMVAE keeps all (cmvae_model.py:752)
+        n_present = len(mods) - 1 if fam == "mmvaeplus" else len(mods)
         plan = _mmvaeplus_nll_plan(c["noise"], B, n_present * (2 + n_present - 1), NLL_K // len(mods), NLL_BK)
         run("joint_nll", lambda: model.compute_joint_nll(fresh(), K=NLL_K, batch_size_K=NLL_BK), plan)
     else:
         run("joint_nll", lambda: model.compute_joint_nll(fresh(), K=NLL_K, batch_size_K=NLL_BK))
+    if "predict_clusters" in rec["calls"]:
+        run("predict_clusters", lambda: model.predict_clusters(fresh()))
+    if "predict_clusters_lliks" in rec["calls"]:
+        run("predict_clusters_lliks", lambda: model.predict_clusters(fresh(), compute_lliks=True))
+    if "prune_clusters" in rec["calls"]:
+        def prune():
+            m2 = copy.deepcopy(model)
+            m2.noise_source = model.noise_source
+            hv = m2.prune_clusters(mb.MultimodalBaseDataset(data=data), batch_size=4)
+            return dict(h_values=torch.tensor([float(h) for h in hv]), n_clusters=torch.tensor(int(m2.n_clusters)), pc_params=m2._pc_params.detach().clone())
+        run("prune_clusters", prune)
     if "joint_nll_paper" in rec["calls"]:
         run("joint_nll_paper", lambda: model.compute_joint_nll_paper(fresh(), K=30, batch_size_K=10))
     if "joint_nll_subset" in rec["calls"]:
