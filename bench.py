@@ -323,7 +323,10 @@ def run_gpu(args):
     ms_e2e = timed(step_e2e, args.steps, finish=lambda: drain(0))
     ms_again = timed(step_resident, args.steps) if os.environ.get("MV_BENCH_DRIFT") else None   # drift check of the resident leg
 
-    # per-kernel device times for the roofline (separate short pass so the events do not perturb `value`)
+    # per-kernel device times for the roofline (separate short pass so the events do not perturb `value`).  It is host-launched on
+    # the current stream while the graph steps ran on the trainer's capture stream: autograd's stream-mismatch note does not apply
+    if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     trainer.step_batch(resident, allow_graph=False, **fwd_kw)   # un-timed eager pass: lazy module loading of every kernel variant
     timer = _cabi.KernelTimer()
     _cabi.set_timer(timer)
