@@ -49,3 +49,26 @@ def test_cub_resnets_train_inside_a_model():
     torch.manual_seed(1)
     ref = m(ds).loss
     assert abs(float(out.loss.detach()) - float(ref.detach())) <= 2e-2 * abs(float(ref.detach()))
+
+
+@pytest.mark.parametrize("lead", [(1,), (2, 3)])
+def test_cub_decoder_leading_dimensions_and_no_grad(lead):
+    """z of shape [B, L] or [K, B, L] (importance samples): the native decoder flattens the leading dimensions; under no_grad
+    (inference API) nothing is saved.  Compared with the library layers in fp32."""
+    from multivae_b200 import nn as N
+    from multivae_b200.nn import functional as NF
+    torch.manual_seed(3)
+    dec = N.CUB_Resnet_Decoder(8).cuda()
+    z = torch.randn(*lead, 8, device="cuda")
+    NF.set_backend("torch")
+    try:
+        ref = dec(z).reconstruction
+    finally:
+        NF.set_backend("native")
+    try:
+        with torch.no_grad():
+            got = dec(z).reconstruction
+    finally:
+        NF.set_backend("auto")
+    assert got.shape == ref.shape == (*lead, 3, 64, 64)
+    assert float((got.float() - ref).abs().max()) <= 3e-2 * float(ref.abs().max())
