@@ -795,18 +795,24 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   const bool has_side = a->res || a->dact1;
   // staging tiles per epilogue group: with a side input the first output is written in place over the side tile
   const int n_out = a->out2 ? 2 : 1;
-  // shared-memory plan.  Preferred: two epilogue groups (G = 2) with a 3-stage input ring and, if there is a side input,
-  // a side ring of 4 (then 3) tiles; otherwise one group (G = 1) with a side ring of 3 (then 2) tiles.
-  // shared-memory plans, in order of preference:
-  //   no side input:  two epilogue groups, 3-4 input stages
-  //   side input:     two groups, separate staging, side ring of 3, TWO input stages (each stage is a whole tile and the
-  //                   epilogue, not the MMA, sets the pace) - or one group with 3 input stages
+  // shared-memory plans, in order of preference (each input stage is a whole tile's window):
+  //   no side input:               two epilogue groups (G = 2), 3-4 input stages
+  //   side input, one output:      G = 2, output in place over the side tile, side ring of 4, 3 input stages
+  //   side input, two outputs:     G = 2, separate staging, side ring of 3, 2 input stages
+  //   otherwise (Cin = 128, tall windows): one group, side ring of 3 (then 2), 3 (then 2) input stages
   auto plan = [&](int G, int nstg, int side_stages, int in_stages) {
     return fixed + p.w_bytes + size_t(G) * size_t(nstg) * 16384 + size_t(side_stages) * 16384 + size_t(in_stages) * p.in_stage_bytes;
   };
   int G = 0, in_min = 3;
   const bool one_group = p.n_kc != 1;
   if (!one_group && !has_side && plan(2, n_out, 0, 3) <= kC3SmemLimit) { G = 2; p.n_stg = n_out; p.side_stages = 0; }
+  // single output + side input: the output is written IN PLACE over the side tile (same thread, same address) and stored from
+  // there, which frees the staging tiles for a third input stage (side ring of 4: a tile is held until its TMA store has read
+  // it).  Measured against separate staging with two input stages (tools/conv3_bench.py, 60 launches, us): bias|res|mask2
+  // 1228 -> 1133, res|resmask 1054 -> 987, res 884 -> 834, dact1 1005 -> 902: these variants wait on input prefetch depth.
+  if (!G && !one_group && has_side && !a->out2 && plan(2, 0, 4, 3) <= kC3SmemLimit) {
+    G = 2; p.n_stg = 0; p.side_stages = 4; in_min = 3; p.inplace = 1;
+  }
   if (!G && !one_group && has_side && plan(2, n_out, 3, 2) <= kC3SmemLimit) {
     G = 2; p.n_stg = n_out; p.side_stages = 3; in_min = 2;
   }
