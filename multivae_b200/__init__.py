@@ -25,6 +25,7 @@ from .mmvae import MMVAE  # noqa: F401
 from .mmvae_plus import MMVAEPlus  # noqa: F401
 from .mopoe import MoPoE  # noqa: F401
 from .mvae import MVAE  # noqa: F401
+from .metrics import EvaluatorConfig, LikelihoodsEvaluator, LikelihoodsEvaluatorConfig  # noqa: F401
 from .mvtcae import MVTCAE  # noqa: F401
 
 __version__ = "0.1.0"

@@ -111,3 +111,28 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_likelihoods_evaluator_batches_the_test_set_in_order():
+    """metrics/likelihoods/likelihoods.py:13-61: the evaluator walks the test set in order in batches of eval_config.batch_size and
+    divides the summed estimate by the number of datapoints (the estimator itself is stubbed here: no GPU)."""
+    import multivae_b200 as mb
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.seen = []
+
+        def compute_joint_nll(self, inputs, K, batch_size_K):
+            self.seen.append((inputs.data["a"][:, 0].tolist(), K, batch_size_K))
+            return inputs.data["a"].sum()
+
+    ds = mb.MultimodalBaseDataset(data={"a": torch.arange(10.0).view(10, 1), "b": torch.zeros(10, 2)})
+    m = Stub()
+    ev = mb.LikelihoodsEvaluator(m, ds, eval_config=mb.LikelihoodsEvaluatorConfig(batch_size=4, num_samples=12, batch_size_k=6))
+    ev.device = "cpu"
+    out = ev.eval()
+    assert [s[0] for s in m.seen] == [[0.0, 1.0, 2.0, 3.0], [4.0, 5.0, 6.0, 7.0], [8.0, 9.0]]
+    assert all(s[1:] == (12, 6) for s in m.seen)
+    assert float(out.joint_likelihood) == 4.5
+    assert ev.joint_nll_from_subset(["a"]) is None
