@@ -325,6 +325,15 @@ int mv_scale_dact(const void* g, const void* act, void* out, int64_t P, int C, f
 /*   mv_lrelu_fwd       out = leaky_relu(x, slope) on a [P, C] matrix: the pre-activation `actvn(x)` of the CUB ResNet blocks
  *                      (models/nn/cub.py:281-283, 296-299), whose shortcut reads the raw x */
 int mv_lrelu_fwd(const void* x, void* out, int64_t P, int C, float slope, void* stream);
+/* Index gathers of the fully connected layers that read / write the halo layout (the `fc` of DecoderResnetMMNIST, models/nn/mmnist.py:339,
+ * and the `fc_mu / fc_lv` heads of EncoderResnetMMNIST, :289-295; the same layers of nn/cub.py).  idx: device int64.
+ *   mode 0 (rows):    out[j, c] = src[idx[j], c]  (0 where idx[j] >= src_rows)      mode 1 (columns): out[r, j] = src[r, idx[j]]
+ *   mv_gather_cast  fp32 -> bf16 GEMM operand; columns [out_cols, out_ld) are written as zeros
+ *   mv_gather_f32   fp32 -> fp32, out = beta * out + gathered (beta = 0: plain store): gradients back in the parameter's layout */
+int mv_gather_cast(const float* src, int64_t src_rows, int64_t src_cols, int64_t src_ld, const int64_t* idx, int64_t out_rows,
+                   int64_t out_cols, int mode, void* out_bf16, int64_t out_ld, void* stream);
+int mv_gather_f32(const float* src, int64_t src_rows, int64_t src_cols, int64_t src_ld, const int64_t* idx, int64_t out_rows,
+                  int64_t out_cols, int mode, float* out, int64_t out_ld, float beta, void* stream);
 
 /* All convolution-weight packs of a network in one launch.  Each item turns an fp32 Conv2d weight [N, C, kh, kw] (T = kh*kw)
  * into the bf16 operand matrices of mv_tapgemm: dst_fwd [T * Npad, Cpad] (row t*Npad + n, column c) for the forward pass and

@@ -109,6 +109,8 @@ _PROTOS = {
     "mv_avgpool3s2_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p],
     "mv_scale_dact": [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_void_p],
     "mv_lrelu_fwd": [c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p],
+    "mv_gather_cast": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p],
+    "mv_gather_f32": [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_float, c_void_p],
     "mv_pack_conv_weights": [ctypes.POINTER(PackItem), c_int, c_void_p],
     "mv_unpack_wgrad_add": [ctypes.POINTER(UnpackItem), c_int, c_void_p],
     "mv_wgrad_slice": [c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),

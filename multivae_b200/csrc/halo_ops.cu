@@ -331,6 +331,69 @@ extern "C" int mv_scale_dact(const void* g, const void* act, void* out, int64_t 
   return MV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Index gathers of the fully connected layers that read / write the halo layout (nn/resnet_native.py FcHaloFn, FcFromHaloFn):
+// the fp32 master weight is laid out in halo order as a bf16 GEMM operand in ONE launch (instead of cat + cast + index kernels),
+// and the fp32 gradient in halo order is gathered back into the parameter's layout (optionally accumulating).
+//   mode 0 (rows):     out[j, c] = src[idx[j], c]        idx[j] >= src_rows  ->  0
+//   mode 1 (columns):  out[r, j] = src[r, idx[j]]        idx[j] >= src_cols  ->  0
+// ---------------------------------------------------------------------------------------------------------------------
+namespace mv {
+template <typename TO, bool ACC>
+__global__ void __launch_bounds__(256) gather2d_kernel(const float* __restrict__ src, int64_t src_rows, int64_t src_cols, int64_t src_ld,
+                                                       const int64_t* __restrict__ idx, int64_t out_rows, int64_t out_cols, int mode,
+                                                       TO* __restrict__ out, int64_t out_ld, int64_t out_cols_padded, float beta) {
+  const int64_t total = out_rows * out_cols_padded;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / out_cols_padded, c = i - r * out_cols_padded;
+    float v = 0.f;
+    if (c < out_cols) {
+      if (mode == 0) {
+        const int64_t sr = idx[r];
+        if (sr < src_rows) v = src[sr * src_ld + c];
+      } else {
+        const int64_t sc = idx[c];
+        if (sc < src_cols) v = src[r * src_ld + sc];
+      }
+    }
+    TO* o = out + r * out_ld + c;
+    if constexpr (ACC) {
+      if (c < out_cols) *o = beta * float(*o) + v;
+    } else {
+      *o = TO(v);
+    }
+  }
+}
+}  // namespace mv
+
+extern "C" int mv_gather_cast(const float* src, int64_t src_rows, int64_t src_cols, int64_t src_ld, const int64_t* idx, int64_t out_rows,
+                              int64_t out_cols, int mode, void* out_bf16, int64_t out_ld, void* stream) {
+  MV_CHECK_ARG(src && idx && out_bf16 && out_rows > 0 && out_cols > 0 && out_ld >= out_cols && (mode == 0 || mode == 1),
+               "mv_gather_cast: bad arguments");
+  const int64_t total = out_rows * out_ld;   // padding columns [out_cols, out_ld) are written as zeros
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  mv::gather2d_kernel<bf16, false><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, src_rows, src_cols, src_ld, idx, out_rows, out_cols, mode, static_cast<bf16*>(out_bf16), out_ld, out_ld, 0.f);
+  MV_CHECK_LAUNCH("mv_gather_cast");
+  return MV_OK;
+}
+
+extern "C" int mv_gather_f32(const float* src, int64_t src_rows, int64_t src_cols, int64_t src_ld, const int64_t* idx, int64_t out_rows,
+                             int64_t out_cols, int mode, float* out, int64_t out_ld, float beta, void* stream) {
+  MV_CHECK_ARG(src && idx && out && out_rows > 0 && out_cols > 0 && out_ld >= out_cols && (mode == 0 || mode == 1),
+               "mv_gather_f32: bad arguments");
+  const int64_t total = out_rows * out_cols;
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  if (beta == 0.f)
+    mv::gather2d_kernel<float, false><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_rows, src_cols, src_ld, idx, out_rows,
+                                                                                            out_cols, mode, out, out_ld, out_cols, 0.f);
+  else
+    mv::gather2d_kernel<float, true><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_rows, src_cols, src_ld, idx, out_rows,
+                                                                                           out_cols, mode, out, out_ld, out_cols, beta);
+  MV_CHECK_LAUNCH("mv_gather_f32");
+  return MV_OK;
+}
+
 extern "C" int mv_lrelu_fwd(const void* x, void* out, int64_t P, int C, float slope, void* stream) {
   MV_CHECK_ARG(x && out && P > 0 && C % 8 == 0, "mv_lrelu_fwd: bad arguments");
   const int64_t nvec = P * (C / 8);

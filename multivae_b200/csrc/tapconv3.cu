@@ -61,11 +61,7 @@ struct Conv3Params {
 
 // How the rows at the lane-quarter boundaries enter the +-1-row shift-add (see the epilogue): through rotating shuffles, or by a
 // correction after plain up / down shuffles.  Chosen per variant from tools/conv3_bench.py on a B200 (12800 images at 28x28).
-#ifndef MV_C3_ROTATE_MASK
-#define MV_C3_ROTATE_MASK 0xffffffffu
-#endif
 __host__ __device__ constexpr bool c3_rotate(uint32_t F) {
-  if (!(MV_C3_ROTATE_MASK & 1u)) return false;
   // measured (us, correction -> rotation): bias|res|mask2 1152 -> 1099, dmask1 838 -> 758, res|resmask 1119 -> 1030, res 927 -> 851,
   // generic 1319 -> 1179;  bias|mask2 838 -> 985, bias 928 -> 1002, bias|res|out2 1347 -> 1369, dact1 963 -> 1073
   // (bias|res|out2 follows bias|res|mask2: the two produce bit-identical first outputs, which the tests rely on)

@@ -344,6 +344,32 @@ def _fc_perm(device, s0=7, ch=256):
     return _PERM_CACHE[key]
 
 
+def _gather_cast(src, idx, mode, out_rows, out_cols):
+    """fp32 matrix -> bf16 GEMM operand [out_rows, out_cols] gathered by `idx` along rows (mode 0) or columns (mode 1), with a
+    16-byte row pitch (mv_gather_cast: one launch instead of cat + cast + index kernels)."""
+    src = src.detach()
+    assert src.dtype == torch.float32 and src.stride(1) == 1 and idx.dtype == torch.int64
+    ld = (out_cols + 7) // 8 * 8
+    out = torch.empty(out_rows, ld, device=src.device, dtype=torch.bfloat16)
+    C.check(C.lib().mv_gather_cast(src.data_ptr(), src.shape[0], src.shape[1], src.stride(0), idx.data_ptr(), out_rows, out_cols, mode,
+                                   out.data_ptr(), ld, C.stream()), "mv_gather_cast")
+    return out[:, :out_cols]
+
+
+def _gather_f32(src, src_cols, idx, mode, out_rows, out_cols, into=None):
+    """fp32 gather (see _gather_cast) of the first src_cols columns of `src`; `into`: accumulate into that contiguous tensor
+    (a parameter's .grad) instead of returning a new one."""
+    src = src.detach()
+    if src.dim() == 1:
+        src = src.unsqueeze(1)
+    assert src.dtype == torch.float32 and src.stride(1) == 1
+    out = torch.empty(out_rows, out_cols, device=src.device, dtype=torch.float32) if into is None else into
+    assert out.is_contiguous() and out.numel() == out_rows * out_cols
+    C.check(C.lib().mv_gather_f32(src.data_ptr(), src.shape[0], src_cols, src.stride(0), idx.data_ptr(), out_rows, out_cols, mode,
+                                  out.data_ptr(), out_cols, 0.0 if into is None else 1.0, C.stream()), "mv_gather_f32")
+    return out
+
+
 class FcHaloFn(torch.autograd.Function):
     """fc of the decoder emitting the 7x7 halo matrix directly: rows of the weight are gathered into halo order (zero rows at
     halo positions), so `z @ Wp^T + bp` IS the [n_img*64, 256] activation matrix.  Native GEMMs (mv_gemm: forward with the bias in
@@ -354,13 +380,13 @@ class FcHaloFn(torch.autograd.Function):
     def forward(ctx, z, weight, bias, s0=7, ch=256):
         from .linear_native import _to_bf16_padded, gemm
         gather, scatter = _fc_perm(z.device, s0, ch)
-        w_ext = torch.cat([weight.detach(), weight.new_zeros(1, weight.shape[1])], 0).to(torch.bfloat16)
-        b_ext = torch.cat([bias.detach().float(), bias.new_zeros(1, dtype=torch.float32)], 0)
-        wp = w_ext[gather]                      # [64*256, L] bf16, halo order
+        F_ = gather.numel()
+        wp = _gather_cast(weight.float(), gather, 0, F_, weight.shape[1])          # [(s0+1)^2 * ch, L] bf16, halo order
+        bp = _gather_f32(bias.float(), 1, gather, 0, F_, 1).view(F_)
         zb = _to_bf16_padded(z)
         n, L = zb.shape
-        h0 = torch.empty(n, wp.shape[0], device=z.device, dtype=torch.bfloat16)
-        gemm(zb, wp, n, wp.shape[0], L, h0, bias=b_ext[gather].contiguous(), tag="dec.fc")
+        h0 = torch.empty(n, F_, device=z.device, dtype=torch.bfloat16)
+        gemm(zb, wp, n, F_, L, h0, bias=bp, tag="dec.fc")
         ctx.save_for_backward(zb, wp)
         ctx.scatter = scatter
         ctx.params = (weight, bias)
@@ -382,11 +408,12 @@ class FcHaloFn(torch.autograd.Function):
         gb = torch.zeros(F_, device=g.device, dtype=torch.float32)
         C.check(C.lib().mv_colsum_any(g.data_ptr(), n, F_, F_, gb.data_ptr(), C.stream()), "mv_colsum_any")
         tgt = _direct_targets(ctx.params)
+        R = ctx.scatter.numel()
         if tgt is not None:   # trainer opt-in: straight into the flat gradient buffer (final when this backward returns)
-            tgt[0].add_(gw[ctx.scatter])
-            tgt[1].add_(gb[ctx.scatter])
+            _gather_f32(gw, L, ctx.scatter, 0, R, L, into=tgt[0])
+            _gather_f32(gb, 1, ctx.scatter, 0, R, 1, into=tgt[1])
             return gz, None, None, None, None
-        return gz, gw[ctx.scatter], gb[ctx.scatter], None, None
+        return gz, _gather_f32(gw, L, ctx.scatter, 0, R, L), _gather_f32(gb, 1, ctx.scatter, 0, R, 1).view(R), None, None
 
 
 def decoder_params(dec):
@@ -484,8 +511,12 @@ class FcFromHaloFn(torch.autograd.Function):
         S = (s0 + 1) * (s0 + 1)
         gather, scatter = _fc_perm(h.device, s0, ch)
         n_img = h.shape[0] // S
-        w = torch.cat([w_mu.detach(), w_lv.detach()], 0)
-        wp = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1).to(torch.bfloat16)[:, gather].contiguous()   # [2L, S*ch]
+        Fp, k_mu, k_lv = gather.numel(), w_mu.shape[0], w_lv.shape[0]
+        wp = torch.empty(k_mu + k_lv, Fp, device=h.device, dtype=torch.bfloat16)                       # [2L, S*ch], halo column order
+        for w, r0 in ((w_mu, 0), (w_lv, k_mu)):
+            w = w.detach().float()
+            C.check(C.lib().mv_gather_cast(w.data_ptr(), w.shape[0], w.shape[1], w.stride(0), gather.data_ptr(), w.shape[0], Fp, 1,
+                                           wp[r0:].data_ptr(), Fp, C.stream()), "mv_gather_cast")
         h2 = h.reshape(n_img, S * ch)
         N = wp.shape[0]
         out = torch.empty(n_img, N, device=h.device, dtype=torch.float32)
@@ -507,9 +538,10 @@ class FcFromHaloFn(torch.autograd.Function):
         gemm(g16, h2, N, F_, n, gw, a_mn=True, b_mn=True, out_kind=2, tag="enc.fc.w")
         gh = torch.empty(n, F_, device=g.device, dtype=torch.bfloat16)
         gemm(g16, wp, n, F_, N, gh, b_mn=True, tag="enc.fc.d")
-        gw = gw[:, ctx.scatter]
-        k = ctx.split
-        return gh.reshape(-1, ctx.ch), gw[:k], gb[:k], gw[k:], gb[k:], None
+        k, Fr = ctx.split, ctx.scatter.numel()
+        gw_mu = _gather_f32(gw[:k], F_, ctx.scatter, 1, k, Fr)
+        gw_lv = _gather_f32(gw[k:], F_, ctx.scatter, 1, N - k, Fr)
+        return gh.reshape(-1, ctx.ch), gw_mu, gb[:k], gw_lv, gb[k:], None
 
 
 def encoder_params(enc, tag):

@@ -132,3 +132,27 @@ def test_native_mlp_chain_gradients_vs_torch_fp32_large():
     for a, c, b, name in zip(got, auto, want, ["z", "w0", "b0", "w1", "b1"]):
         rel, rel_lib = float((a - b).norm() / b.norm()), float((c - b).norm() / b.norm())
         assert rel <= 1.25 * rel_lib + 1e-3, (name, rel, rel_lib)
+
+
+def test_gather_kernels_vs_torch_indexing():
+    """mv_gather_cast / mv_gather_f32 (the halo-order layout of the fc weights and its inverse on the gradients): row and column
+    gathers with out-of-range indices reading as zeros, padded row pitch, accumulation."""
+    from multivae_b200.nn.resnet_native import _gather_cast, _gather_f32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.randn(37, 21, device="cuda", generator=g)
+    idx_r = torch.randint(0, 38, (50,), device="cuda", generator=g)           # 37 = "zero row"
+    ext = torch.cat([src, src.new_zeros(1, 21)], 0)
+    got = _gather_cast(src, idx_r, 0, 50, 21)
+    assert got.shape == (50, 21) and got.stride(0) == 24
+    assert torch.equal(got, ext[idx_r].bfloat16())
+    idx_c = torch.randint(0, 22, (30,), device="cuda", generator=g)           # 21 = "zero column"
+    extc = torch.cat([src, src.new_zeros(37, 1)], 1)
+    assert torch.equal(_gather_cast(src, idx_c, 1, 37, 30), extc[:, idx_c].bfloat16())
+    assert torch.equal(_gather_f32(src, 21, idx_r, 0, 50, 21), ext[idx_r])
+    assert torch.equal(_gather_f32(src, 21, idx_c, 1, 37, 30), extc[:, idx_c])
+    base = torch.randn(50, 21, device="cuda", generator=g)
+    acc = base.clone()
+    _gather_f32(src, 21, idx_r, 0, 50, 21, into=acc)
+    assert torch.allclose(acc, base + ext[idx_r])
+    v = torch.randn(37, device="cuda", generator=g)
+    assert torch.equal(_gather_f32(v, 1, idx_r.clamp(max=36), 0, 50, 1).view(50), v[idx_r.clamp(max=36)])
