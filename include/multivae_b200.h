@@ -219,6 +219,10 @@ typedef struct mv_tapgemm_args {
    * Lets a producer store ONE tensor t = a * g * lrelu'(d) and the consumer recover g = t / (a * lrelu'(d)) from d's sign bits
    * (the image head's data gradient writes only the pre-scaled gradient; the block's skip connection un-scales it here). */
   const void* res_mask; float res_scale_pos, res_scale_neg;
+  /* fused 1x1 term (plain 3x3 convolutions with 64 inputs and 64 outputs only): out[p, n] additionally gets sum_c A2[p, c] * W2[n, c]
+   * (A2 bf16 [P][a2_ld], 64 columns used; W2 bf16 [64][64] K-major).  The data gradient of a ResnetBlock with a learned shortcut
+   * (models/nn/mmnist.py:243-251), conv_0^T(g_h) + shortcut^T(g_out), in one launch: no separate 1x1 kernel, no residual tensor. */
+  const void* A2; int32_t a2_ld; const void* W2;
 } mv_tapgemm_args;
 int mv_tapgemm(const mv_tapgemm_args* args, void* stream);
 

@@ -40,6 +40,7 @@ class TapGemmArgs(ctypes.Structure):
         ("n_img", ctypes.c_int32), ("out_mode", ctypes.c_int32), ("n_valid", ctypes.c_int32),
         ("out2_mask", c_void_p), ("dmask2", c_void_p), ("dmask1", c_void_p),
         ("res_mask", c_void_p), ("res_scale_pos", c_float), ("res_scale_neg", c_float),
+        ("A2", c_void_p), ("a2_ld", ctypes.c_int32), ("W2", c_void_p),
     ]
 
 

@@ -40,7 +40,9 @@ constexpr int kC3MaxSide = 4;
 constexpr int kC3N = 192;
 constexpr uint32_t kC3WBox = 192u * 128u;   // one filter row of weights: 3 taps x 64 output channels x 64 input channels
 
-enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_DMASK1 = 32, C3_RESMASK = 64, C3_GENERIC = 0x80000000u };
+enum : uint32_t { C3_BIAS = 1, C3_RES = 2, C3_DACT1 = 4, C3_OUT2 = 8, C3_MASK2 = 16, C3_DMASK1 = 32, C3_RESMASK = 64,
+                  C3_A2 = 128,   // fused 1x1 term: the side ring feeds the MMA warp (A2 tiles), W2 sits behind the 3x3 weights
+                  C3_GENERIC = 0x80000000u };
 
 struct Conv3Params {
   int P, m_tiles, n_kc, row_shift, R;
@@ -66,7 +68,7 @@ __host__ __device__ constexpr bool c3_rotate(uint32_t F) {
   // generic 1319 -> 1179;  bias|mask2 838 -> 985, bias 928 -> 1002, bias|res|out2 1347 -> 1369, dact1 963 -> 1073
   // (bias|res|out2 follows bias|res|mask2: the two produce bit-identical first outputs, which the tests rely on)
   return F == (C3_BIAS | C3_RES | C3_MASK2) || F == (C3_BIAS | C3_RES | C3_OUT2) || F == C3_DMASK1 || F == (C3_RES | C3_RESMASK) ||
-         F == C3_RES || (F & C3_GENERIC) != 0;
+         F == C3_RES || F == C3_A2 || (F & C3_GENERIC) != 0;
 }
 
 template <uint32_t F>
@@ -128,7 +130,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int i = 0; i < p.in_stages; ++i) { tc::mbar_init(&in_full[i], 1); tc::mbar_init(&in_empty[i], 1); }
     tc::mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tm_full[i], 1); tc::mbar_init(&tm_empty[i], kC3EpiWarps / G); }
-    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], p.inplace ? 1 : kC3EpiWarps / G); }
+    for (int i = 0; i < kC3MaxSide; ++i) { tc::mbar_init(&side_full[i], 1); tc::mbar_init(&side_empty[i], (p.inplace || (p.flags & C3_A2)) ? 1 : kC3EpiWarps / G); }
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
@@ -150,6 +152,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int kc = 0; kc < p.n_kc; ++kc)
         for (int r = 0; r < 3; ++r)
           tc::tma_load_2d(w_base + size_t(kc * 3 + r) * kC3WBox, &tmW, w_full, kc * 64, r * kC3N);
+      if (p.flags & C3_A2)   // 64 x 64 weights of the fused 1x1 term (their tensor map travels in the unused second-output slot)
+        tc::tma_load_2d(w_base + size_t(p.n_kc) * 3 * kC3WBox, &tmO2, w_full, 0, 0);
     }
     __syncwarp();
     int is = 0, iph = 0;
@@ -175,7 +179,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc::mbar_wait(&side_empty[ss], sph ^ 1);
         if (tc::elect_one()) {
           tc::mbar_expect_tx(&side_full[ss], 16384u);
-          tc::tma_load_2d(side_base + size_t(ss) * 16384, &tmS, &side_full[ss], 0, tile * kC3OutRows);
+          // epilogue side tiles start at the tile's first OWNED row; A2 tiles are MMA operands: row i = the MMA tile's row i
+          tc::tma_load_2d(side_base + size_t(ss) * 16384, &tmS, &side_full[ss], 0, tile * kC3OutRows - ((p.flags & C3_A2) ? 1 : 0));
         }
         __syncwarp();
         if (++ss == p.side_stages) { ss = 0; sph ^= 1; }
@@ -183,7 +188,8 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ================= MMA issuer: 3 filter rows x 4 K steps per 64-channel chunk, N = 192 =================
-    const uint32_t idesc = tc::idesc_bf16(128, kC3N, 0, 0);
+    const uint32_t idesc = tc::idesc_bf16(128, kC3N, 0, 0), idesc64 = tc::idesc_bf16(128, 64, 0, 0);
+    int ss2 = 0, sph2 = 0;
     const uint64_t desc0 = tc::smem_desc(0, 16, 1024, tc::SW_128);
     const uint32_t desc_hi = uint32_t(desc0 >> 32);
     const uint32_t desc_lo = uint32_t(desc0);
@@ -216,6 +222,21 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
         if (++is == p.in_stages) { is = 0; iph ^= 1; }
+      }
+      if (p.flags & C3_A2) {
+        // fused 1x1 term: E1 (the unshifted third of the accumulator) += A2 tile x W2^T, K = 64, N = 64
+        tc::mbar_wait(&side_full[ss2], uint32_t(sph2));
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t a2_lo = desc_lo | ((tc::smem_u32(side_base + size_t(ss2) * 16384) & 0x3FFFFu) >> 4);
+          const uint32_t w2_lo = w_lo0 + uint32_t(p.n_kc * 3) * (kC3WBox >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_bf16(tmem_d + 64u, (uint64_t(desc_hi) << 32) | (a2_lo + 2u * k), (uint64_t(desc_hi) << 32) | (w2_lo + 2u * k), idesc64, true);
+          tc::umma_commit(&side_empty[ss2]);
+        }
+        __syncwarp();
+        if (++ss2 == p.side_stages) { ss2 = 0; sph2 ^= 1; }
       }
       if (tc::elect_one()) tc::umma_commit(&tm_full[acc]);
       __syncwarp();
@@ -770,6 +791,11 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   if (a->dmask1 && a->dact1) return MV_OK;
   if (a->res_mask && (!a->res || a->dmask1)) return MV_OK;
   if (a->dact2) return MV_OK;
+  if (a->A2) {
+    MV_CHECK_ARG(a->W2 && a->Cin == 64 && !a->res && !a->dact1 && !a->out2 && !a->out2_mask && !a->dmask1 && !a->res_mask && !a->bias &&
+                     a->act == MV_ACT_NONE && a->a2_ld % 8 == 0 && reinterpret_cast<uintptr_t>(a->A2) % 16 == 0,
+                 "mv_tapgemm: the fused 1x1 term (A2 / W2) needs a plain 64 -> 64 3x3 convolution (no bias / activation / side input)");
+  }
   auto tma_ok = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && (ld % 8 == 0); };
   if (!tma_ok(a->out, a->out_ld) || (a->out2 && !tma_ok(a->out2, a->out2_ld))) return MV_OK;
   if (a->res && !tma_ok(a->res, a->res_ld)) return MV_OK;
@@ -786,7 +812,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.n_box = p.R > 256 ? 2 : 1;   // windows taller than the 256-row TMA box limit (64-pixel-wide images): two boxes
   p.box_rows = p.n_box == 1 ? p.R : (((p.R + 1) / 2 + 7) & ~7);
   p.in_stage_bytes = (uint32_t(p.n_box * p.box_rows) * 128u + 1023u) & ~1023u;
-  p.w_bytes = uint32_t(p.n_kc) * 3u * kC3WBox;
+  p.w_bytes = uint32_t(p.n_kc) * 3u * kC3WBox + (a->A2 ? 8192u : 0u);   // + the 64 x 64 weights of the fused 1x1 term
   const size_t fixed = 1024 + 2 * 4 * 2 * 64 * 4 + 64 * 4 + 2048 + (2 * kC3MaxStages + 5 + 2 * kC3MaxSide) * 8 + 16;
   const bool has_side = a->res || a->dact1;
   // staging tiles per epilogue group: with a side input the first output is written in place over the side tile
@@ -801,7 +827,12 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   };
   int G = 0, in_min = 3;
   const bool one_group = p.n_kc != 1;
-  if (!one_group && !has_side && plan(2, n_out, 0, 3) <= kC3SmemLimit) { G = 2; p.n_stg = n_out; p.side_stages = 0; }
+  if (a->A2) {   // A2 tiles are consumed by the MMA warp right after the tile's main MMAs: a ring of two is enough
+    if (plan(2, 1, 2, 3) <= kC3SmemLimit) { G = 2; p.n_stg = 1; p.side_stages = 2; in_min = 3; }
+    else if (plan(1, 1, 2, 2) <= kC3SmemLimit) { G = 1; p.n_stg = 1; p.side_stages = 2; in_min = 2; }
+    MV_CHECK_ARG(G != 0, "mv_tapgemm: the fused 1x1 term does not fit shared memory at this image width");
+  }
+  if (!G && !one_group && !has_side && plan(2, n_out, 0, 3) <= kC3SmemLimit) { G = 2; p.n_stg = n_out; p.side_stages = 0; }
   // single output + side input: the output is written IN PLACE over the side tile (same thread, same address) and stored from
   // there, which frees the staging tiles for a third input stage (side ring of 4: a tile is held until its TMA store has read
   // it).  Measured against separate staging with two input stages (tools/conv3_bench.py, 60 launches, us): bias|res|mask2
@@ -830,7 +861,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   p.slope1 = a->slope1;
   p.img_stride = a->img_stride; p.Wp = a->Wp; p.W = a->W; p.n_img = a->n_img;
   p.flags = (a->bias ? C3_BIAS : 0u) | (a->res ? C3_RES : 0u) | (a->dact1 ? C3_DACT1 : 0u) | (a->out2 ? C3_OUT2 : 0u) |
-            (a->out2_mask ? C3_MASK2 : 0u) | (a->dmask1 ? C3_DMASK1 : 0u) | (a->res_mask ? C3_RESMASK : 0u);
+            (a->out2_mask ? C3_MASK2 : 0u) | (a->dmask1 ? C3_DMASK1 : 0u) | (a->res_mask ? C3_RESMASK : 0u) | (a->A2 ? C3_A2 : 0u);
   p.rmask = static_cast<const uint64_t*>(a->res_mask);
   p.rs_pos = a->res_scale_pos; p.rs_neg = a->res_scale_neg;
   p.dmask1 = static_cast<const uint64_t*>(a->dmask1);
@@ -851,6 +882,9 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   if (ok && has_side)
     ok = tc::make_tmap_2d_bf16(&tmS, a->res ? a->res : a->dact1, uint64_t(a->P), 64, uint64_t(a->res ? a->res_ld : a->dact1_ld) * 2, 128,
                                64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (ok && a->A2)
+    ok = tc::make_tmap_2d_bf16(&tmS, a->A2, uint64_t(a->P), 64, uint64_t(a->a2_ld) * 2, 128, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+         tc::make_tmap_2d_bf16(&tmO2, a->W2, 64, 64, 128, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!ok) {
     mv::set_error("mv_tapgemm(conv3): cuTensorMapEncodeTiled failed for the outputs / side input");
     return MV_ERR_CUDA;
@@ -881,6 +915,7 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
     case C3_BIAS | C3_MASK2: MV_C3_LAUNCH(C3_BIAS | C3_MASK2); break;
     case C3_RES: MV_C3_LAUNCH(C3_RES); break;
     case C3_RES | C3_RESMASK: MV_C3_LAUNCH(C3_RES | C3_RESMASK); break;
+    case C3_A2: MV_C3_LAUNCH(C3_A2); break;
     default: MV_C3_LAUNCH(C3_GENERIC); break;
   }
 #undef MV_C3_LAUNCH

@@ -699,6 +699,7 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
   p.dmask2 = static_cast<const unsigned long long*>(a->dmask2 ? a->dmask2 : a->dmask1);   // one sign-mask word per row, either use
   MV_CHECK_ARG(!a->dmask2 || (a->N_total == 64 && !a->dact2), "mv_tapgemm: dmask2 needs N_total = 64 and no dact2");
   MV_CHECK_ARG(!a->dmask1 || (a->N_total == 64 && !a->dact1 && !a->dmask2), "mv_tapgemm: dmask1 needs N_total = 64, no dact1 and no dmask2");
+  MV_CHECK_ARG(!a->A2, "mv_tapgemm: the fused 1x1 term (A2 / W2) is only available for 3x3 convolutions with 64 inputs and outputs in the halo layout");
   MV_CHECK_ARG(!a->res_mask, "mv_tapgemm: res_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   MV_CHECK_ARG(!a->out2_mask, "mv_tapgemm: out2_mask is only available for 3x3 convolutions with 64 outputs in the halo layout");
   CUtensorMap tmA, tmW;

@@ -79,7 +79,8 @@ def pack_conv_weights(specs):
 
 def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act="none", alpha=1.0, res=None, dact1=None,
             slope1=0.2, out=None, out2=None, out2_pre=False, alpha2=1.0, dact2=None, slope2=0.2, geom=None,
-            nchw_out=None, n_valid=0, tag=None, out2_mask=None, dmask2=None, dmask1=None, res_mask=None, res_scale=(1.0, 1.0)):
+            nchw_out=None, n_valid=0, tag=None, out2_mask=None, dmask2=None, dmask1=None, res_mask=None, res_scale=(1.0, 1.0),
+            a2=None, w2=None):
     """out[p, n] = epilogue(sum_t sum_c A[p + tap_off[t], c] * Wt[t*N_total + n, c]); see mv_tapgemm."""
     lib = C.lib()
     Cin = A.shape[1] if Cin is None else Cin
@@ -121,6 +122,9 @@ def tapgemm(A, Wt, T, tap_off, N_total, P, *, Cin=None, BN=None, bias=None, act=
     if res_mask is not None:
         assert res is not None and res_mask.dtype == torch.int64 and res_mask.is_contiguous() and N_total == 64
         a.res_mask, a.res_scale_pos, a.res_scale_neg = res_mask.data_ptr(), float(res_scale[0]), float(res_scale[1])
+    if a2 is not None:   # fused 1x1 term: out += a2 @ w2^T (plain 64 -> 64 3x3 convolutions only)
+        assert a2.dtype == torch.bfloat16 and a2.stride(1) == 1 and w2.dtype == torch.bfloat16 and w2.is_contiguous() and w2.shape == (64, 64)
+        a.A2, a.a2_ld, a.W2 = a2.data_ptr(), a2.stride(0), w2.data_ptr()
     if geom is not None:
         a.img_stride, a.Wp, a.W, a.H, a.n_img = geom.S, geom.Wp, geom.W, geom.H, geom.n_img
     kw = {} if tag is None else {"tag": tag}

@@ -22,6 +22,7 @@ from . import halo as HL
 _LRELU = 0.2
 _MASK_D = os.environ.get("MULTIVAE_B200_MASK_D", "1") != "0"   # save the last block's `d` as a sign mask
 _SPLIT_C0D = os.environ.get("MULTIVAE_B200_SPLIT_C0D", "1") != "0"
+_FUSE_SCD = os.environ.get("MULTIVAE_B200_FUSE_SCD", "1") != "0"   # shortcut data gradient fused into the conv0 data-gradient launches
 _MASK_H = os.environ.get("MULTIVAE_B200_MASK_H", "1") != "0"   # sign mask of `h` next to h itself (64-channel hidden layers)
 
 
@@ -220,14 +221,22 @@ def _block_bwd(g_out, g_dpre, x, h, g, blk, tag, need_gx=True, arena=None, tg=No
         dW0, db0 = HL.wgrad(x, g_hpre, 9, taps, g.P, tag=f"{tag}.c0", want_db=True, dW=z(9, blk.hid, blk.cin), db=z(blk.hid))
     dWsc = None
     g_short = g_out
+    # 128 -> 64 blocks: the shortcut's data gradient rides on the conv0 data-gradient launches as a fused 1x1 term (no g_short tensor)
+    fuse_sc = need_gx and blk.w0d_halves is not None and blk.wsc is not None and blk.cout == 64 and _FUSE_SCD
     if blk.wsc is not None:
         if tg is not None:
             HL.wgrad(x, g_out, 1, [0], g.P, tag=f"{tag}.sc", grad_out=tg[4])
         else:
             dWsc = HL.wgrad(x, g_out, 1, [0], g.P, tag=f"{tag}.sc", dW=z(1, blk.cout, blk.cin))
-        g_short = HL.tapgemm(g_out, blk.wscd, 1, [0], blk.cin, g.P, geom=g, tag=f"{tag}.scd") if need_gx else None
+        if not fuse_sc:
+            g_short = HL.tapgemm(g_out, blk.wscd, 1, [0], blk.cin, g.P, geom=g, tag=f"{tag}.scd") if need_gx else None
     g_x = None
-    if need_gx and blk.w0d_halves is not None:
+    if fuse_sc:
+        g_x = torch.empty(g.P, blk.cin, device=g_hpre.device, dtype=torch.bfloat16)
+        for j, wd in enumerate(blk.w0d_halves):
+            HL.tapgemm(g_hpre, wd, 9, taps, 64, g.P, a2=g_out, w2=blk.wscd[64 * j:64 * j + 64], out=g_x[:, 64 * j:64 * j + 64], geom=g,
+                       tag=f"{tag}.c0d")
+    elif need_gx and blk.w0d_halves is not None:
         g_x = torch.empty(g.P, blk.cin, device=g_hpre.device, dtype=torch.bfloat16)
         for j, wd in enumerate(blk.w0d_halves):
             HL.tapgemm(g_hpre, wd, 9, taps, 64, g.P, res=g_short[:, 64 * j:64 * j + 64], out=g_x[:, 64 * j:64 * j + 64], geom=g,

@@ -198,3 +198,26 @@ def test_sign_mask_second_output_and_its_consumer(n_img):
     v = halo[: n_img * g.S].view(n_img, H + 1, g.Wp)
     v[:, 1:, :H] = False
     assert float(got[halo].abs().max()) == 0.0 and float(oc[halo].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n_img,H", [(23, 14), (301, 14), (7, 28)])
+def test_conv3x3_with_fused_1x1_term(n_img, H):
+    """out = conv3x3(x; w) + a2 @ w2^T in one launch (the conv0 data gradient of a ResnetBlock with a learned shortcut)."""
+    from multivae_b200.nn import halo as HL
+    x = _rnd(n_img, 64, H, H, seed=61).bfloat16()
+    w = _rnd(64, 64, 3, 3, seed=62, scale=64 ** -0.5).bfloat16()
+    x2 = _rnd(n_img, 64, H, H, seed=63).bfloat16()
+    w2 = _rnd(64, 64, seed=64, scale=0.125).bfloat16()
+    A, g = HL.to_halo(x)
+    A2, _ = HL.to_halo(x2)
+    out = HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), 64, g.P, a2=A2, w2=w2.contiguous(), geom=g)
+    ref = F.conv2d(x.float(), w.float(), padding=1) + F.conv2d(x2.float(), w2.float().view(64, 64, 1, 1))
+    _close(HL.from_halo(out, g), ref)
+    mask = torch.ones(g.P, dtype=torch.bool, device="cuda")
+    v = mask[: n_img * g.S].view(n_img, H + 1, g.Wp)
+    v[:, 1:, :H] = False
+    assert float(out[mask].abs().max()) == 0.0
+    # into a column slice of a wider tensor (how the 128-channel gradient of the block is assembled)
+    wide = torch.zeros(g.P, 128, device="cuda", dtype=torch.bfloat16)
+    HL.tapgemm(A, HL.pack_conv_weight(w), 9, g.taps3x3(), 64, g.P, a2=A2, w2=w2.contiguous(), out=wide[:, 64:], geom=g)
+    assert torch.equal(wide[:, 64:], out) and float(wide[:, :64].abs().max()) == 0.0
