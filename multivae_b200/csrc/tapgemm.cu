@@ -258,7 +258,7 @@ __device__ __forceinline__ void epi_tile(const TapGemmParams& p, const RowCtx& r
 }
 
 template <int CK, int BN, int TT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, (CK == 16 && BN == 64) ? 2 : 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
                const __grid_constant__ CUtensorMap tmS, const __grid_constant__ TapGemmParams p) {
@@ -471,6 +471,73 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int it = 0, ss = 0, sph = 0;
     bool stored = false;
     unsigned long long mask_next = 0ull;
+    if (BN == 64 && p.epi_flags == EF_DMASK1 && p.use_tma_store && p.n_tiles == 1 && p.act == MV_ACT_NONE) {
+      // ---- lean epilogue of the image head's data gradient: out = alpha * y * lrelu'(sign bit), halo rows -> 0 ----
+      // The layer has K = 16, so its nine MMAs per tile cost ~460 cycles and the epilogue IS the kernel.  The generic tile loop
+      // below spends ~500 warp-instructions per warp and tile on it (row decoding, variant dispatch, per-group validity
+      // branches: ncu, profiles/r2_ncu_headd_2cta.md); this one keeps everything that does not change between tiles (staging
+      // offsets, factors) in registers and folds the halo mask into the two factors.
+      const int rloc = q * 32 + lane;
+      const int cb = half * 32;
+      uint32_t soff[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) soff[g] = tile_off(cb + g * 8, rloc);
+      const float f1 = p.alpha, f0 = p.alpha * p.slope1;
+      {
+        const int row0 = int(blockIdx.x) * kBM + rloc;
+        if (blockIdx.x < n_tiles_total && row0 < p.P) mask_next = p.dmask2[row0];
+      }
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+        const int p0 = tile * kBM;
+        const int acc = it & 1, acc_ph = (it >> 1) & 1;
+        const int row = p0 + rloc;
+        bool valid = row < p.P;
+        if (p.img_stride > 0) {
+          const int img = fast_div(row, p.img_stride, inv_S);
+          const int rr = row - img * p.img_stride;
+          const int y = fast_div(rr, p.Wp, inv_Wp);
+          const int x = rr - y * p.Wp;
+          valid = valid && img < p.n_img && y >= 1 && x < p.W;
+        }
+        const uint32_t mw = uint32_t(mask_next >> cb);   // the 32 sign bits of this row's columns [cb, cb + 32)
+        {
+          // the next tile's mask word is requested now: its L2 / HBM round trip overlaps this tile
+          const int tn = tile + int(gridDim.x);
+          const int rown = tn * kBM + rloc;
+          if (tn < n_tiles_total && rown < p.P) mask_next = p.dmask2[rown];
+        }
+        const float a1 = valid ? f1 : 0.f, a0 = valid ? f0 : 0.f;
+        tc::mbar_wait(&tm_full[acc], uint32_t(acc_ph));
+        tc::fence_after_sync();
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16) + uint32_t(cb), v);
+        if (stored) {
+          // the previous TMA store of this quarter's slab must have finished READING it before it is rewritten
+          if (store_leader) tc::tma_store_wait_read<0>();
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        }
+        tc::tmem_ld_wait();
+        // accumulator drained: hand it back before the arithmetic
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[g * 8 + e]) * (((mw >> (g * 8 + e)) & 1u) ? a1 : a0);
+          *reinterpret_cast<uint4*>(st_out + soff[g]) = pack8(o);
+        }
+        tc::fence_proxy_async();
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (store_leader) {
+          tc::tma_store_2d(&tmO, st_out + q * 4096, 0, p0 + q * 32);
+          tc::tma_store_commit();
+        }
+        stored = true;
+      }
+      if (store_leader) tc::tma_store_wait_all<0>();
+    } else {
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles;   // (no integer division in the common single-column-tile case)
       const int p0 = mt * kBM, n0 = (tile - mt * p.n_tiles) * BN;
@@ -571,6 +638,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (p.use_tma_store && store_leader) tc::tma_store_wait_all<0>();
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -733,7 +801,11 @@ extern "C" int mv_tapgemm(const mv_tapgemm_args* a, void* stream) {
                       round1k(size_t(p.w_stages) * p.w_stage_bytes);
   MV_CHECK_ARG(smem <= kSmemLimit, "mv_tapgemm: shared-memory plan exceeds the limit (%zu bytes)", smem);
   const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  // Cin = 16 with 64 outputs (data gradient of the image head, the encoders' image convolution): one MMA per tap and tile, so the
+  // kernel is paced by the latency of its per-tile epilogue chain, not by the tensor pipe or by HBM.  These instantiations are
+  // compiled for two resident CTAs per SM (80 registers; 128 of the 512 TMEM columns and ~56 KB of shared memory each).
+  const int ctas_per_sm = (CK == 16 && a->BN == 64 && 2 * (smem + 1024) <= kSmemLimit) ? 2 : 1;
+  const int grid = tiles < ctas_per_sm * num_sms() ? tiles : ctas_per_sm * num_sms();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
 #define MV_TG_LAUNCH(CK_, BN_, TT_)                                                                                      \

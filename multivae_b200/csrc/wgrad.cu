@@ -44,8 +44,9 @@ struct WgradParams {
   int n_box, box_rows;          // the X window is loaded as n_box TMA boxes of box_rows rows
   uint32_t x_chunk_bytes;       // bytes of one chunk buffer (R rows x 128 B, 1 KB aligned)
   uint32_t g_bytes, g_row_bytes, g_box_cols;
-  uint32_t stage_bytes;
-  int stages;
+  uint32_t stage_bytes[8];      // per pass: a pass stages only the 64-channel chunks its accumulators read
+  int stages[8];
+  int chunk_lo[8], chunk_n[8];  // first chunk / number of chunks staged by the pass (WgAcc::chunk is relative to chunk_lo)
   int n_acc[8];                 // accumulators per pass
   int acc_begin[8];
   WgAcc acc[48];
@@ -60,20 +61,23 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(p.stages) * p.stage_bytes);
+  const int pass = blockIdx.y;
+  const int n_stages = p.stages[pass];
+  const uint32_t stage_bytes = p.stage_bytes[pass];
+  const int chunk_lo = p.chunk_lo[pass], chunk_n = p.chunk_n[pass];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(n_stages) * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWgMaxStages;
   uint64_t* done = empty + kWgMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   float* red = reinterpret_cast<float*>(tmem_slot + 4);   // 128 x 8 partial column sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pass = blockIdx.y;
   const bool do_db = p.db != nullptr && pass == 0;   // the bias gradient is independent of the pass: pass 0 owns it
   const int nacc = p.n_acc[pass];
   const WgAcc* accs = p.acc + p.acc_begin[pass];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], do_db ? 5 : 1); }
+    for (int i = 0; i < n_stages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], do_db ? 5 : 1); }
     tc::mbar_init(done, 1);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&tmX);
@@ -84,7 +88,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t g_off = uint32_t(p.n_chunks) * p.x_chunk_bytes;  // G tile follows the X chunk buffers in a stage
+  const uint32_t g_off = uint32_t(chunk_n) * p.x_chunk_bytes;  // G tile follows the X chunk buffers in a stage
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -92,18 +96,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x) {
       tc::mbar_wait(&empty[s], ph ^ 1);
       if (tc::elect_one()) {
-        uint8_t* st = smem + size_t(s) * p.stage_bytes;
-        tc::mbar_expect_tx(&full[s], uint32_t(p.n_chunks) * uint32_t(p.n_box * p.box_rows) * 128u + p.g_bytes);
-        for (int c = 0; c < p.n_chunks; ++c)
+        uint8_t* st = smem + size_t(s) * stage_bytes;
+        tc::mbar_expect_tx(&full[s], uint32_t(chunk_n) * uint32_t(p.n_box * p.box_rows) * 128u + p.g_bytes);
+        for (int c = 0; c < chunk_n; ++c)
           for (int bx = 0; bx < p.n_box; ++bx)   // windows taller than the 256-row TMA box limit arrive as two boxes
-            tc::tma_load_2d(st + size_t(c) * p.x_chunk_bytes + size_t(bx * p.box_rows) * 128u, &tmX, &full[s], c * 64,
+            tc::tma_load_2d(st + size_t(c) * p.x_chunk_bytes + size_t(bx * p.box_rows) * 128u, &tmX, &full[s], (chunk_lo + c) * 64,
                             kt * 128 - p.halo_lo + bx * p.box_rows);
         const int nbox = p.N / int(p.g_box_cols);
         for (int b = 0; b < nbox; ++b)
           tc::tma_load_2d(st + g_off + size_t(b) * p.g_rows * p.g_row_bytes, &tmG, &full[s], b * int(p.g_box_cols), kt * 128);
       }
       __syncwarp();
-      if (++s == p.stages) { s = 0; ph ^= 1; }
+      if (++s == n_stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -116,7 +120,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x, ++it) {
       tc::mbar_wait(&full[s], ph);
       tc::fence_after_sync();
-      const uint32_t st = tc::smem_u32(smem + size_t(s) * p.stage_bytes);
+      const uint32_t st = tc::smem_u32(smem + size_t(s) * stage_bytes);
       if (tc::elect_one()) {
         for (int a = 0; a < nacc; ++a) {
           const WgAcc& A = accs[a];
@@ -133,7 +137,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         tc::umma_commit(&empty[s]);
       }
       __syncwarp();
-      if (++s == p.stages) { s = 0; ph ^= 1; }
+      if (++s == n_stages) { s = 0; ph ^= 1; }
     }
     if (tc::elect_one()) tc::umma_commit(done);
     __syncwarp();
@@ -148,7 +152,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       int s = 0, ph = 0;
       for (int kt = blockIdx.x; kt < p.n_ktiles; kt += gridDim.x) {
         tc::mbar_wait(&full[s], ph);
-        const uint8_t* gt = smem + size_t(s) * p.stage_bytes + g_off;
+        const uint8_t* gt = smem + size_t(s) * stage_bytes + g_off;
         for (int i = 0; i < rpt; ++i) {
           const int row = rg * rpt + i;
           uint32_t off;
@@ -160,7 +164,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+        if (++s == n_stages) { s = 0; ph ^= 1; }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) red[et * 8 + e] = acc[e];
@@ -265,7 +269,10 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
       for (int s2 = 0; s2 < 3; ++s2)
         if (tap_off[3 * r + s2] != (r - 1) * Wp3 + (s2 - 1)) pair = false;
   }
-  const int n_shift = !pair ? 1 : (N == 64 ? 2 : 8);   // N = 16: eight row-shifted copies of the 16-column G tile (N = 128)
+  // N = 16 (image head): four row-shifted copies of the 16-column G tile (MMA N = 64; shifts 0..2 are the three taps of a filter
+  // row, the fourth copy is padding).  Eight copies (N = 128) cost 64.5 cycles per MMA against 51 and made the kernel MMA-bound
+  // (16 MMAs per 128-row tile) on a layer that moves 1.7 GB for 0.2 TFLOP.
+  const int n_shift = !pair ? 1 : (N == 64 ? 2 : 4);
   p.g_row_bytes = N >= 64 ? 128u : uint32_t(N) * 2u;
   p.g_box_cols = N >= 64 ? 64u : uint32_t(N);
   p.g_rows = pair ? 136u : 128u;
@@ -273,7 +280,6 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   p.g_lbo = pair ? p.g_row_bytes : 128u * p.g_row_bytes;
   p.Ncols = p.n_mma < 32 ? 32 : p.n_mma;
   p.g_bytes = p.g_rows * uint32_t(N) * 2u;
-  p.stage_bytes = uint32_t(p.n_chunks) * p.x_chunk_bytes + ((p.g_bytes + 1023u) & ~1023u);
   // accumulator table
   int na = 0;
   if (pair && N == 64) {
@@ -329,8 +335,10 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
     }
   } else {
     MV_CHECK_ARG(p.n_chunks % 2 == 0, "mv_wgrad: Cin must be 64 or a multiple of 128");
-    for (int t = 0; t < T; ++t)
-      for (int c = 0; c < p.n_chunks; c += 2) {
+    // chunk pair outermost: the accumulators of a pass then read as few chunks as possible and the pass stages only those
+    // (256 -> 128 at 7x7: 18 accumulators in 5 passes; four of them now load 2 of the 4 chunks per 128-row tile)
+    for (int c = 0; c < p.n_chunks; c += 2)
+      for (int t = 0; t < T; ++t) {
         WgAcc& A = p.acc[na++];
         A.row_off = p.halo_lo + tap_off[t];
         A.chunk = c;
@@ -341,22 +349,61 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
       }
   }
   const int per_pass_max = 512 / p.Ncols > kWgMaxAcc ? kWgMaxAcc : 512 / p.Ncols;
-  const int passes = (na + per_pass_max - 1) / per_pass_max;
-  MV_CHECK_ARG(passes <= 8, "mv_wgrad: too many passes (%d)", passes);
-  for (int i = 0, b = 0; i < passes; ++i) {
-    const int cnt = (na - b + (passes - i) - 1) / (passes - i);  // balanced split
-    p.acc_begin[i] = b;
-    p.n_acc[i] = cnt;
-    b += cnt;
+  int passes = (na + per_pass_max - 1) / per_pass_max;
+  // Several chunk pairs and more accumulators than TMEM holds: every pass takes the taps of ONE chunk pair, the same number in
+  // every pass (256 -> 128 at 7x7: 6 passes of 3 taps instead of 5 passes of 4 / 3 accumulators over all four chunks).  A pass
+  // then stages 2 chunks + the G tile per 128-row tile (72 KB instead of 112 KB: the kernel is bound by the L2 -> shared-memory
+  // feed, ncu: 41 B/clk/SM), and all passes walk the rows in lock-step, so every tile is read from HBM once (a 5-pass split with
+  // unequal passes drifted apart and missed in L2: profiles/r2_ncu_wgrad_b1c0.md).
+  const int n_pairs = p.n_chunks >= 2 ? p.n_chunks / 2 : 1;
+  const int per_pair = na / n_pairs;
+  const bool by_pair = n_pairs > 1 && na > per_pass_max && na == per_pair * n_pairs;
+  if (by_pair) {
+    const int ppp = (per_pair + per_pass_max - 1) / per_pass_max;   // passes per chunk pair
+    passes = ppp * n_pairs;
+    MV_CHECK_ARG(passes <= 8, "mv_wgrad: too many passes (%d)", passes);
+    int i = 0;
+    for (int pr = 0; pr < n_pairs; ++pr)
+      for (int j = 0, b = pr * per_pair; j < ppp; ++j, ++i) {
+        const int cnt = (pr * per_pair + per_pair - b + (ppp - j) - 1) / (ppp - j);
+        p.acc_begin[i] = b;
+        p.n_acc[i] = cnt;
+        b += cnt;
+      }
+  } else {
+    MV_CHECK_ARG(passes <= 8, "mv_wgrad: too many passes (%d)", passes);
+    for (int i = 0, b = 0; i < passes; ++i) {
+      const int cnt = (na - b + (passes - i) - 1) / (passes - i);  // balanced split
+      p.acc_begin[i] = b;
+      p.n_acc[i] = cnt;
+      b += cnt;
+    }
   }
   int max_acc = 0;
   for (int i = 0; i < passes; ++i) max_acc = p.n_acc[i] > max_acc ? p.n_acc[i] : max_acc;
   int cols = max_acc * p.Ncols;
   p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
   const size_t fixed = 2048 + (2 * kWgMaxStages + 1) * 8 + 16 + 128 * 8 * 4;
-  p.stages = int((kWgSmemLimit - fixed) / p.stage_bytes);
-  if (p.stages > kWgMaxStages) p.stages = kWgMaxStages;
-  MV_CHECK_ARG(p.stages >= 1, "mv_wgrad: stage does not fit shared memory");
+  size_t smem = 0;
+  for (int i = 0; i < passes; ++i) {
+    // the chunks this pass reads: [chunk_lo, chunk_lo + chunk_n); WgAcc::chunk becomes the slot inside the stage
+    int c_lo = p.n_chunks, c_hi = 0;
+    for (int a = 0; a < p.n_acc[i]; ++a) {
+      const WgAcc& A = p.acc[p.acc_begin[i] + a];
+      const int last = A.chunk + (A.lbo == p.x_chunk_bytes && p.n_chunks > 1 ? 1 : 0);   // block 1 in the next chunk buffer
+      c_lo = A.chunk < c_lo ? A.chunk : c_lo;
+      c_hi = last > c_hi ? last : c_hi;
+    }
+    p.chunk_lo[i] = c_lo;
+    p.chunk_n[i] = c_hi - c_lo + 1;
+    for (int a = 0; a < p.n_acc[i]; ++a) p.acc[p.acc_begin[i] + a].chunk -= c_lo;
+    p.stage_bytes[i] = uint32_t(p.chunk_n[i]) * p.x_chunk_bytes + ((p.g_bytes + 1023u) & ~1023u);
+    p.stages[i] = int((kWgSmemLimit - fixed) / p.stage_bytes[i]);
+    if (p.stages[i] > kWgMaxStages) p.stages[i] = kWgMaxStages;
+    MV_CHECK_ARG(p.stages[i] >= 1, "mv_wgrad: stage does not fit shared memory");
+    const size_t need = fixed + size_t(p.stages[i]) * p.stage_bytes[i];
+    smem = need > smem ? need : smem;
+  }
   CUtensorMap tmX, tmG;
   const bool ok = tc::make_tmap_2d_bf16(&tmX, X, uint64_t(x_rows), uint64_t(Cin), uint64_t(x_ld) * 2, uint32_t(p.box_rows), 64,
                                         CU_TENSOR_MAP_SWIZZLE_128B) &&
@@ -369,7 +416,6 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   int gx = num_sms() / passes;
   if (gx > p.n_ktiles) gx = p.n_ktiles;
   if (gx < 1) gx = 1;
-  const size_t smem = fixed + size_t(p.stages) * p.stage_bytes;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kWgSmemLimit));

@@ -11,6 +11,8 @@ using namespace tc;
 
 struct Cfg {
   int N, a_mn, b_mn, alt_acc, walk, iters;  // walk: 0 = same A address, 1 = conv-like (9 row shifts x 4 k-steps), 2 = MN k-walk
+  int sw;                                   // K-major only: 0 = 128-byte rows SWIZZLE_128B, 1 = 32-byte rows SWIZZLE_32B (a 16-channel
+                                            // layer: one K step per tap), 2 = two 16-byte column panels, no swizzle
 };
 
 __global__ void __launch_bounds__(128) rate_kernel(Cfg c, long long* out) {
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(128) rate_kernel(Cfg c, long long* out) {
         } else {
           aa = a0 + (c.walk ? uint32_t(t * 29) * 128u + k * 32 : 0u);
           ad = smem_desc(aa, 16, 1024, SW_128);
+          if (c.sw == 1) ad = smem_desc(a0 + (c.walk ? uint32_t(t * 29 + k * 3) * 32u : 0u), 16, 256, SW_32);
+          if (c.sw == 2) ad = smem_desc(a0 + (c.walk ? uint32_t(t * 29 + k * 3) * 16u : 0u), 192 * 16, 128, SW_NONE);
         }
         if (c.b_mn) {
           bb = b0 + (c.walk ? uint32_t(k * 16) * 128u : 0u);
@@ -56,6 +60,8 @@ __global__ void __launch_bounds__(128) rate_kernel(Cfg c, long long* out) {
           bb = b0 + (c.walk ? uint32_t(t) * uint32_t(c.N) * 128u + k * 32 : 0u);
           if (bb + c.N * 128 > b0 + 136 * 1024) bb = b0 + k * 32;
           bd = smem_desc(bb, 16, 1024, SW_128);
+          if (c.sw == 1) bd = smem_desc(b0 + uint32_t(t) * uint32_t(c.N) * 32u, 16, 256, SW_32);
+          if (c.sw == 2) bd = smem_desc(b0 + uint32_t(t) * uint32_t(c.N) * 32u, uint32_t(c.N) * 16u, 128, SW_NONE);
         }
         alo[t * 4 + k] = uint32_t(ad); ahi = uint32_t(ad >> 32);
         blo[t * 4 + k] = uint32_t(bd); bhi = uint32_t(bd >> 32);
@@ -102,6 +108,11 @@ int main() {
       {"A MN / B K-major N=64", {64, 1, 0, 0, 1, iters}},
       {"A K / B MN-major N=64", {64, 0, 1, 0, 1, iters}},
       {"A K / B MN-major N=192", {192, 0, 1, 0, 1, iters}},
+      {"K-major  N=64  32-byte rows SW_32", {64, 0, 0, 0, 1, iters, 1}},
+      {"K-major  N=64  32-byte rows SW_32 alt-acc", {64, 0, 0, 1, 1, iters, 1}},
+      {"K-major  N=64  16-byte panels no swizzle", {64, 0, 0, 0, 1, iters, 2}},
+      {"K-major  N=128 32-byte rows SW_32", {128, 0, 0, 0, 1, iters, 1}},
+      {"K-major  N=128 16-byte panels no swizzle", {128, 0, 0, 0, 1, iters, 2}},
   };
   for (auto& cs : cases) {
     for (int grid : {1, 148}) {
