@@ -260,29 +260,50 @@ static int wgrad_launch(const void* X, int64_t x_rows, int x_ld, int Cin, const 
   //   rows over all tiles; rows outside the tensors read as zeros)
   // with xa in {base - 1, base + 1}, gb in {0, 1}: offsets base-1, base-2 (unused), base+1, base -> the three taps of a
   // filter row from 8 MMAs instead of 12, each twice as efficient.
+  // Cin = 128, N = 64 (conv0 of the 128 -> 64 block at 14x14): the same idea with the two 64-channel chunks as the M side:
+  //   D[(chunk, c), (gb, n)] = sum_p X[p + xa, chunk*64 + c] G[p + gb, n] = dW at tap offset xa - gb
+  // xa = base gives the taps s = 1 and s = 0 of a filter row, xa = base + 1 the tap s = 2 (its second half repeats s = 1 and is not
+  // stored): 2 MMAs of N = 128 (64.5 cycles each) per filter row and K step instead of 3 of N = 64 (51 each), and the six
+  // accumulators split into two equal passes of 3 x 128 TMEM columns (before: 9 accumulators in passes of 5 and 4).
   int Wp3 = 0;
-  bool pair = false;
-  if (Cin == 64 && (N == 64 || N == 16) && T == 9 && (N_total == N || nct)) {
+  bool pair = false, pair128 = false;
+  if ((Cin == 64 || Cin == 128) && (N == 64 || (N == 16 && Cin == 64)) && T == 9 && (N_total == N || nct)) {
     Wp3 = tap_off[7] - tap_off[4];
-    pair = Wp3 >= 2;
-    for (int r = 0; r < 3 && pair; ++r)
+    bool ok = Wp3 >= 2;
+    for (int r = 0; r < 3 && ok; ++r)
       for (int s2 = 0; s2 < 3; ++s2)
-        if (tap_off[3 * r + s2] != (r - 1) * Wp3 + (s2 - 1)) pair = false;
+        if (tap_off[3 * r + s2] != (r - 1) * Wp3 + (s2 - 1)) ok = false;
+    pair = ok && Cin == 64;
+    pair128 = ok && Cin == 128;
   }
   // N = 16 (image head): four row-shifted copies of the 16-column G tile (MMA N = 64; shifts 0..2 are the three taps of a filter
   // row, the fourth copy is padding).  Eight copies (N = 128) cost 64.5 cycles per MMA against 51 and made the kernel MMA-bound
   // (16 MMAs per 128-row tile) on a layer that moves 1.7 GB for 0.2 TFLOP.
-  const int n_shift = !pair ? 1 : (N == 64 ? 2 : 4);
+  const int n_shift = pair128 ? 2 : (!pair ? 1 : (N == 64 ? 2 : 4));
   p.g_row_bytes = N >= 64 ? 128u : uint32_t(N) * 2u;
   p.g_box_cols = N >= 64 ? 64u : uint32_t(N);
-  p.g_rows = pair ? 136u : 128u;
+  p.g_rows = (pair || pair128) ? 136u : 128u;
   p.n_mma = n_shift * N;
-  p.g_lbo = pair ? p.g_row_bytes : 128u * p.g_row_bytes;
+  p.g_lbo = (pair || pair128) ? p.g_row_bytes : 128u * p.g_row_bytes;
   p.Ncols = p.n_mma < 32 ? 32 : p.n_mma;
   p.g_bytes = p.g_rows * uint32_t(N) * 2u;
   // accumulator table
   int na = 0;
-  if (pair && N == 64) {
+  if (pair128) {
+    for (int r = 0; r < 3; ++r)
+      for (int half = 0; half < 2; ++half) {
+        WgAcc& A = p.acc[na++];
+        for (int i = 0; i < 16; ++i) (&A.tap[0][0])[i] = -1;
+        A.row_off = p.halo_lo + (r - 1) * Wp3 + half;   // xa = base | base + 1
+        A.chunk = 0;
+        A.lbo = p.x_chunk_bytes;                        // M block 1 = the second 64-channel chunk
+        A.cch[0] = 0; A.cch[1] = 1;
+        for (int b = 0; b < 2; ++b) {
+          A.tap[b][0] = 3 * r + (half ? 2 : 1);         // gb = 0: offset xa
+          A.tap[b][1] = half ? -1 : 3 * r + 0;          // gb = 1: offset xa - 1 (xa = base + 1: the centre tap again, not stored)
+        }
+      }
+  } else if (pair && N == 64) {
     for (int r = 0; r < 3; ++r) {
       WgAcc& A = p.acc[na++];
       for (int i = 0; i < 16; ++i) (&A.tap[0][0])[i] = -1;

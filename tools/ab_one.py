@@ -1,5 +1,5 @@
 """One kernel case at the north-star size, a few launches, for ncu captures: python tools/ab_one.py <lib.so|-> <case> [reps]
-cases: headd, wg_b1c0, wg_head, wg_b2c0"""
+cases: headd, wg_b1c0, wg_head, wg_b2c0, c3_c0, c3_c1, c3_c0d, c3_c1d"""
 import os
 import sys
 
@@ -44,6 +44,20 @@ elif case == "wg_b2c0":
     x14, gg14 = halo_rand(g14, 128), halo_rand(g14, 64)
     dW14 = torch.zeros(9, 64, 128, device=dev)
     fn = lambda: HL.wgrad(x14, gg14, 9, g14.taps3x3(), g14.P, dW=dW14)
+elif case.startswith("c3_"):
+    # the four 64 -> 64 3x3 convolutions of the last decoder block (three-taps-per-MMA kernel)
+    x = halo_rand(g28, 64)
+    r = x.flip(1).contiguous()
+    w = (torch.randn(9 * 64, 64, device=dev) * 0.05).bfloat16()
+    b = torch.randn(64, device=dev)
+    mask = torch.randint(-2 ** 62, 2 ** 62, (HL.mask_rows(g28.P),), device=dev, dtype=torch.int64)
+    m2 = torch.empty_like(mask)
+    out = torch.empty(g28.P, 64, device=dev, dtype=torch.bfloat16)
+    kw = {"c3_c0": dict(bias=b, act="lrelu", out2_mask=m2),
+          "c3_c1": dict(bias=b, act="lrelu", alpha=0.1, res=r, out2_mask=m2),
+          "c3_c1d": dict(dmask1=mask, slope1=0.2),
+          "c3_c0d": dict(res=r, res_mask=mask, res_scale=(10.0, 50.0))}[case]
+    fn = lambda: HL.tapgemm(x, w, 9, g28.taps3x3(), 64, g28.P, geom=g28, out=out, **kw)
 else:
     raise SystemExit("unknown case " + case)
 for _ in range(reps):

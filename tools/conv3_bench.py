@@ -1,11 +1,15 @@
 """Times the four 64 -> 64 3x3 convolution variants of the last decoder block at the north-star size (12800 images, 28x28) with CUDA
-events: python tools/conv3_bench.py [reps]"""
+events: python tools/conv3_bench.py [reps] [path/to/lib.so]"""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
+from multivae_b200 import _cabi  # noqa: E402
+
+if len(sys.argv) > 2:
+    _cabi.LIB_PATH = os.path.abspath(sys.argv[2])
 from multivae_b200.nn import halo as HL  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
@@ -34,6 +38,7 @@ variants = {
     "dact1": dict(dact1=r, slope1=0.2),
 }
 flops = 2.0 * n_img * H * H * 64 * 64 * 9
+print("library:", _cabi.LIB_PATH)
 for name, kw in variants.items():
     for _ in range(3):
         HL.tapgemm(x, w, 9, taps, 64, g.P, geom=g, out=out, **kw)
@@ -45,4 +50,4 @@ for name, kw in variants.items():
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
-    print(f"{name:32s} {us:8.1f} us   {flops / us / 1e6:7.1f} TFLOP/s useful")
+    print(f"{name:32s} {us:8.1f} us   {flops / us / 1e6:7.1f} TFLOP/s useful   checksum {out.float().abs().sum().item():.6e}", flush=True)
