@@ -56,8 +56,12 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(kGThreads, 1)
+// OCC = 2: the variant for short reductions (<= 2 K blocks per tile, e.g. the decoders' first Linear layer: K = 64, 419 MB of
+// output).  Such a tile costs ~260 cycles of MMAs, so the kernel is paced by the latency of the per-tile epilogue chain (TMEM load ->
+// arithmetic -> staging -> TMA store): two resident CTAs per SM (2 stages + staging = 100 KB, 256 TMEM columns, <= 80 registers
+// each) overlap two such chains.
+template <int EPI, int OCC>
+__global__ void __launch_bounds__(kGThreads, OCC)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
             const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -204,8 +208,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int e = 0; e < 8; ++e) y[e] += s_bias[cb + g * 8 + e];
           }
           if (EPI != GEPI_F32_ADD) {
+            if (p.neg != 1.f) {   // relu / leaky-relu as one max (no activation: skipped, warp-uniform)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);
+              for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], p.neg * y[e]);
+            }
             if (p.act == MV_ACT_SIGMOID) {
               // the result is rounded to bf16 (8 mantissa bits) or feeds a Bernoulli / sigmoid decoder: the fast exponential and
               // reciprocal (2 ulp of fp32) cost a fifth of the instructions of expf + IEEE division in this issue-bound epilogue
@@ -364,6 +370,9 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
   p.kb_per_split = (p.k_blocks + p.splits - 1) / p.splits;
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   p.stages = a->out_kind == GEPI_BF16 ? 5 : 6;
+  // short reductions with many tiles: two CTAs per SM with two stages each (see gemm_kernel)
+  const bool occ2 = a->out_kind == GEPI_BF16 && p.kb_per_split <= 2 && tiles >= 4 * sms;
+  if (occ2) p.stages = 2;
   p.bias = a->bias; p.act = a->act;
   p.neg = a->act == MV_ACT_LRELU02 ? 0.2f : (a->act == MV_ACT_RELU ? 0.f : 1.f);
   p.alpha = a->alpha;
@@ -388,20 +397,22 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
                       kGEpiWarps * 64 * 4;
   MV_CHECK_ARG(smem <= kGSmemLimit, "mv_gemm: shared-memory plan exceeds the limit");
   const int items = tiles * p.splits;
-  const int grid = items < sms ? items : sms;
+  const int ctas = occ2 ? 2 * sms : sms;
+  const int grid = items < ctas ? items : ctas;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define MV_G_LAUNCH(E)                                                                                          \
-  do {                                                                                                          \
-    static bool attr_done = false;                                                                              \
-    if (!attr_done) {                                                                                           \
-      cudaFuncSetAttribute(gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemLimit));      \
-      attr_done = true;                                                                                         \
-    }                                                                                                           \
-    gemm_kernel<E><<<grid, kGThreads, smem, st>>>(tmA, tmB, tmO, p);                                            \
+#define MV_G_LAUNCH(E, O)                                                                                          \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      cudaFuncSetAttribute(gemm_kernel<E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGSmemLimit));      \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    gemm_kernel<E, O><<<grid, kGThreads, smem, st>>>(tmA, tmB, tmO, p);                                            \
   } while (0)
-  if (a->out_kind == GEPI_BF16) MV_G_LAUNCH(GEPI_BF16);
-  else if (a->out_kind == GEPI_F32) MV_G_LAUNCH(GEPI_F32);
-  else MV_G_LAUNCH(GEPI_F32_ADD);
+  if (a->out_kind == GEPI_BF16 && occ2) MV_G_LAUNCH(GEPI_BF16, 2);
+  else if (a->out_kind == GEPI_BF16) MV_G_LAUNCH(GEPI_BF16, 1);
+  else if (a->out_kind == GEPI_F32) MV_G_LAUNCH(GEPI_F32, 1);
+  else MV_G_LAUNCH(GEPI_F32_ADD, 1);
 #undef MV_G_LAUNCH
   MV_CHECK_LAUNCH("mv_gemm");
   return MV_OK;

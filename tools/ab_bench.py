@@ -119,3 +119,18 @@ def wg_b2c0():
 
 
 timed("wgrad b2.c0 (128 x 64 @14)", wg_b2c0, 2.0 * n_img * 196 * 128 * 64 * 9)
+
+# ---- decoder fc: [12800, 64] x [16384, 64]^T + bias -> bf16 [12800, 16384] (K = 64: one K block per tile) ----
+del x14, gg14
+from multivae_b200.nn import linear_native as LN  # noqa: E402
+
+zin = torch.randn(n_img, 64, device=dev).bfloat16()
+wfc = (torch.randn(16384, 64, device=dev) * 0.1).bfloat16()
+bfc = torch.randn(16384, device=dev)
+ofc = torch.empty(n_img, 16384, device=dev, dtype=torch.bfloat16)
+timed("dec.fc (12800 x 16384 x 64)", lambda: LN.gemm(zin, wfc, n_img, 16384, 64, ofc, bias=bfc), 2.0 * n_img * 16384 * 64)
+ref = (zin[:64].float() @ wfc.float().t() + bfc)
+print("  dec.fc max |err| on the first 64 rows:", (ofc[:64].float() - ref).abs().max().item(), "of", ref.abs().max().item())
+ofr = torch.empty(n_img, 16384, device=dev, dtype=torch.bfloat16)
+timed("dec.fc + relu", lambda: LN.gemm(zin, wfc, n_img, 16384, 64, ofr, bias=bfc, act="relu"), 2.0 * n_img * 16384 * 64)
+print("  relu max |err|:", (ofr[:64].float() - ref.clamp_min(0)).abs().max().item())
