@@ -371,6 +371,8 @@ extern "C" int mv_gemm(const mv_gemm_args* a, void* stream) {
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
   p.stages = a->out_kind == GEPI_BF16 ? 5 : 6;
   // short reductions with many tiles: two CTAs per SM with two stages each (see gemm_kernel)
+  // (tried for the fp32 results of the transposed convolutions' patch-matrix products as well: no gain — those tiles are bound by
+  //  their 64 KB of direct fp32 stores, cfg3 `convt1` 308 -> 344 us)
   const bool occ2 = a->out_kind == GEPI_BF16 && p.kb_per_split <= 2 && tiles >= 4 * sms;
   if (occ2) p.stages = 2;
   p.bias = a->bias; p.act = a->act;
