@@ -782,9 +782,6 @@ int conv3_try_launch(const mv_tapgemm_args* a, void* stream, bool* handled) {
   *handled = false;
   if (a->T != 9 || a->N_total != 64 || a->BN != 64 || (a->Cin != 64 && a->Cin != 128) || a->out_mode != 0) return MV_OK;
   if (a->img_stride <= 0 || a->Wp < 2) return MV_OK;
-#ifdef MV_EXP_DMASK1_TAPGEMM
-  if (a->dmask1 && a->Cin == 64 && !a->res && !a->bias && !a->out2 && !a->out2_mask && !a->A2 && a->act == MV_ACT_NONE) return MV_OK;
-#endif
   for (int r = 0; r < 3; ++r)
     for (int s2 = 0; s2 < 3; ++s2)
       if (a->tap_off[3 * r + s2] != (r - 1) * a->Wp + (s2 - 1)) return MV_OK;

@@ -511,23 +511,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::fence_after_sync();
         uint32_t v[32];
         tc::tmem_ld_32x32(tmem_base + uint32_t(acc * p.acc_stride) + (uint32_t(q * 32) << 16) + uint32_t(cb), v);
-#ifdef MV_EXP_LEAN_DIRECT
-        tc::tmem_ld_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tm_empty[acc]);
-        if (row < p.P) {
-          bf16* dst = p.out + size_t(row) * p.out_ld + cb;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[g * 8 + e]) * (((mw >> (g * 8 + e)) & 1u) ? a1 : a0);
-            *reinterpret_cast<uint4*>(dst + g * 8) = pack8(o);
-          }
-        }
-      }
-#else
         if (stored) {
           // the previous TMA store of this quarter's slab must have finished READING it before it is rewritten
           if (store_leader) tc::tma_store_wait_read<0>();
@@ -554,7 +537,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         stored = true;
       }
       if (store_leader) tc::tma_store_wait_all<0>();
-#endif
     } else {
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles;   // (no integer division in the common single-column-tile case)
