@@ -23,6 +23,8 @@
 //             (double-buffered in TMEM so the next tile's MMAs overlap), bias / activation / activation-derivative /
 //             residual / halo mask, bf16 pack into a swizzled staging tile, 32-row TMA stores
 // 3x3 convolutions with 64 (or <= 16, NCHW) output channels are routed to the three-taps-per-MMA kernels of tapconv3.cu.
+// 16-channel inputs with 64 outputs (one MMA per tap: the epilogue IS the kernel) run two resident CTAs per SM, and the
+// sign-mask-only epilogue of the image head's data gradient has its own lean tile loop (profiles/r2_ncu_headd_2cta.md).
 #include "common.cuh"
 #include "tc.cuh"
 

@@ -11,7 +11,10 @@
 // Cin = 64 — the SAME buffer shifted by the row distance to another tap, so two taps share one MMA.
 // Every (tap pair | chunk pair) owns one fp32 accumulator of N columns in TMEM for the whole kernel;
 // a CTA walks its share of the 128-pixel K tiles, then adds its partial dW into global memory with
-// fp32 reductions.  Layers whose dW exceeds 512 TMEM columns are split into passes (grid.y).
+// fp32 reductions.  Layers whose dW exceeds 512 TMEM columns are split into passes (grid.y); every pass
+// walks ALL row tiles, so the passes are planned to be identical (same chunks staged, same number of
+// accumulators): they then move through the rows in lock-step and each tile is read from HBM once
+// (profiles/r2_ncu_wgrad_b1c0.md), and a pass stages only the 64-channel chunks its accumulators read.
 #include <cstdlib>
 
 #include "common.cuh"
